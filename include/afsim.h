@@ -1,0 +1,260 @@
+/*
+ * afsim.h -- C ABI of the B200-native batched chain simulator (libafsim.so).
+ *
+ * This is the drop-in boundary for ONE path of FueledByRedBull/audio-forge: the
+ * native offline chain simulator.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout).  The Rust
+ * host would bind these with `extern "C"` / `libloading`, exactly as it already
+ * binds its DeepFilterNet plugin (rust-core/src/dsp/deepfilter_ffi.rs:164-176,
+ * 335-386: opaque handle create/free, caller-owned buffers, integer status).
+ * INTEGRATION.md shows that binding and the ctypes shim used in this repo.
+ *
+ * Conventions
+ *   - plain C, POD structs only (all `#[repr(C)]`-compatible), no torch types;
+ *   - the caller owns every buffer; the library owns only the handle (CUDA
+ *     context objects, stream, scratch);
+ *   - every call is synchronous (work is queued on the handle's stream and the
+ *     stream is synchronised before returning) unless it says "async";
+ *   - return value: AfStatus; afsim_last_error(handle) gives the message;
+ *   - there is NO CPU fallback: without a CUDA device afsim_create fails.
+ */
+#ifndef AFSIM_H
+#define AFSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFSIM_NUM_BANDS 10
+#define AFSIM_ABI_VERSION 1
+
+typedef enum AfStatus {
+    AFSIM_OK = 0,
+    AFSIM_INVALID_ARGUMENT = 1, /* reference: PyValueError (python_api.rs:388-398, lib.rs:105-141,160-186) */
+    AFSIM_CUDA_ERROR = 2,
+    AFSIM_OUT_OF_MEMORY = 3,
+    AFSIM_UNSUPPORTED = 4 /* a settings combination this build does not run on the GPU (fails loudly) */
+} AfStatus;
+
+/* Stable filter ids, reference rust-core/src/dsp/eq.rs:46-53 (EqFilterType). */
+typedef enum AfFilterType {
+    AF_LOW_SHELF = 0,
+    AF_BELL = 1,
+    AF_HIGH_SHELF = 2,
+    AF_NOTCH = 3,
+    AF_HIGH_PASS = 4,
+    AF_LOW_PASS = 5
+} AfFilterType;
+
+/* Input stage in front of the chain.  The reference's offline simulator has none
+ * (AF_INPUT_NONE reproduces it exactly); the other values add the live loop's
+ * input stage (rust-core/src/audio/processor/routing.rs:826-843 DC block + 80 Hz
+ * high-pass, and routing.rs:213-609 adaptive hum/rumble cleanup, block = 480
+ * samples as in processor/tests.rs:500-549). */
+typedef enum AfInputStage {
+    AF_INPUT_NONE = 0,
+    AF_INPUT_DC_HP80 = 1,       /* cleanup "off": DC block then fixed 80 Hz HP */
+    AF_INPUT_CLEANUP_GENTLE = 2,
+    AF_INPUT_CLEANUP_STRONG = 3
+} AfInputStage;
+
+/* One EQ band.  Legacy 3-tuple callers (python_api.rs:383, lib.rs:100-104) fill
+ * frequency/gain/q only; typed callers (lib.rs:152 PyEqBandV2) fill everything. */
+typedef struct AfBand {
+    double frequency_hz;
+    double gain_db;
+    double q;
+    uint8_t filter_type;          /* AfFilterType */
+    uint8_t slope_db_per_octave;  /* 12, 24, 36 or 48 (pass filters) */
+    uint8_t enabled;
+    uint8_t reserved[5];
+} AfBand;
+
+/* The flat settings dict of simulate_auto_eq_chain (python_api.rs:415-487; the
+ * keys headroom.py:48-84 sends, plus eq_before_deesser, limiter_lookahead_ms and
+ * eq_bands_v2 presence = use_typed_bands).  afsim_chain_settings_default() fills
+ * the reference defaults. */
+typedef struct AfChainSettings {
+    uint8_t use_typed_bands;      /* 1: eq_bands_v2 branch (set_band_config + reset) ; 0: legacy setters (72-sample fade-in) */
+    uint8_t eq_before_deesser;
+    uint8_t deesser_enabled;
+    uint8_t deesser_auto_enabled;
+    uint8_t compressor_enabled;
+    uint8_t compressor_adaptive_release;
+    uint8_t compressor_auto_makeup_enabled;
+    uint8_t compressor_sidechain_highpass_enabled;
+    uint8_t limiter_enabled;
+    uint8_t limiter_careful_output_enabled;
+    uint8_t input_stage;          /* AfInputStage; 0 = reference offline behaviour */
+    uint8_t reserved[5];
+    double deesser_auto_amount;
+    double deesser_low_cut_hz;
+    double deesser_high_cut_hz;
+    double deesser_threshold_db;
+    double deesser_ratio;
+    double deesser_attack_ms;
+    double deesser_release_ms;
+    double deesser_max_reduction_db;
+    double compressor_threshold_db;
+    double compressor_ratio;
+    double compressor_attack_ms;
+    double compressor_release_ms;
+    double compressor_makeup_gain_db;
+    double compressor_base_release_ms;
+    double compressor_target_lufs;
+    double limiter_ceiling_db;
+    double limiter_release_ms;
+    double limiter_lookahead_ms;
+} AfChainSettings;
+
+/* One candidate of a sweep = 10 bands + the chain settings. */
+typedef struct AfCandidate {
+    AfBand bands[AFSIM_NUM_BANDS];
+    AfChainSettings settings;
+} AfCandidate;
+
+/* The dict simulate_auto_eq_chain returns (python_api.rs:649-713), 1:1. */
+typedef struct AfChainMetrics {
+    float input_sample_peak_db;
+    float input_rms_db;
+    float output_sample_peak_db;
+    float pre_limiter_true_peak_db;
+    float output_true_peak_db;
+    float output_rms_db;
+    float limiter_effective_ceiling_db;
+    float sample_headroom_db;
+    float pre_limiter_true_peak_headroom_db;
+    float true_peak_headroom_db;
+    float limiter_gain_reduction_db;
+    float true_peak_limiter_gain_reduction_db;
+    float compressor_gain_reduction_db;
+    float deesser_gain_reduction_db;
+    float compressor_gain_reduction_median_db;
+    float compressor_gain_reduction_p95_db;
+    float compressor_gain_reduction_active_ratio;
+    float active_output_gain_db;
+    float silence_output_gain_db;
+    float silence_level_delta_db;
+    float compressor_pumping_score_db;
+    float deesser_gain_reduction_median_db;
+    float deesser_gain_reduction_p95_db;
+    float analysis_block_ms;
+    float active_analysis_threshold_db;
+    uint32_t non_finite_output;
+    uint64_t true_peak_limited_events;
+    uint64_t active_analysis_block_count;
+    uint64_t processed_samples;
+    double candidate_runtime_ms; /* wall time of the call divided over its streams */
+} AfChainMetrics;
+
+/* The dict simulate_eq_v2 returns (lib.rs:269-286). */
+typedef struct AfEqRenderStats {
+    float input_sample_peak;
+    float output_sample_peak;
+    float input_true_peak;
+    float output_true_peak;
+    double input_rms;
+    double output_rms;
+    double max_response_db;
+    double runtime_ms;
+    uint64_t sample_count;
+    uint64_t algorithmic_latency_samples;
+    uint32_t non_finite_output;
+    uint32_t reserved;
+} AfEqRenderStats;
+
+typedef struct AfsimHandle AfsimHandle;   /* opaque */
+typedef struct AfsimSweep AfsimSweep;     /* opaque: a sweep resident in HBM */
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+int afsim_abi_version(void);
+
+/* Create a simulator bound to CUDA device `device_ordinal`.  `cuda_stream` may
+ * be NULL (the library creates its own stream) or an existing cudaStream_t to
+ * launch on (so a caller's CUDA events see the work).  Fails (AFSIM_CUDA_ERROR)
+ * when no usable sm_100 device is present: there is no CPU path. */
+int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle);
+void afsim_destroy(AfsimHandle* handle);
+/* Message of the last failure on this handle ("" if none).  Valid until the next call. */
+const char* afsim_last_error(const AfsimHandle* handle);
+/* Message of the last afsim_create failure in this thread. */
+const char* afsim_create_error(void);
+
+/* Reference defaults of every settings key (python_api.rs:415-487). */
+void afsim_chain_settings_default(AfChainSettings* out);
+/* Reference default band layout (dsp/eq.rs:11-23,127-140). */
+void afsim_default_bands(AfBand out[AFSIM_NUM_BANDS]);
+
+/* ---- single-stream entry points (the reference's pyfunctions) ------------ */
+
+/* Replaces simulate_auto_eq_chain (python_api.rs:378-714).  `out_audio` is NULL
+ * or n floats (settings["return_output_audio"]). */
+int afsim_chain_render(AfsimHandle* handle, const float* audio, size_t n, double sample_rate,
+                       const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings* settings,
+                       AfChainMetrics* out_metrics, float* out_audio);
+
+/* Replaces simulate_eq_v2 (lib.rs:214-288).  Non-finite input is rejected. */
+int afsim_eq_render(AfsimHandle* handle, const float* audio, size_t n, double sample_rate,
+                    const AfBand bands[AFSIM_NUM_BANDS], AfEqRenderStats* out_stats,
+                    float* out_audio);
+
+/* Replaces eq_magnitude_response (typed=0, lib.rs:99-150) and
+ * eq_magnitude_response_v2 (typed=1, lib.rs:191-212) for `n_sets` band sets at
+ * once: out_db[set * n_freqs + i]. */
+int afsim_eq_response(AfsimHandle* handle, const double* frequencies_hz, size_t n_freqs,
+                      const AfBand* bands /* n_sets * 10 */, size_t n_sets, int typed,
+                      double sample_rate, double* out_db);
+
+/* ---- batched sweeps ------------------------------------------------------ */
+
+/* Candidate x passage sweep: what apply_headroom_validation (headroom.py:292-354)
+ * and _calibrate_compressor_threshold (voice_setup.py:742-1079) do one call at a
+ * time.  pair_passage/pair_candidate (n_pairs each) select the streams; both NULL
+ * means the full cross product, candidate-major: pair = candidate * n_passages +
+ * passage.  out_metrics has n_pairs entries.  out_audio is NULL or n_pairs
+ * pointers (each NULL or passage_len floats). */
+int afsim_chain_sweep(AfsimHandle* handle, const float* const* passages, const size_t* passage_len,
+                      size_t n_passages, double sample_rate, const AfCandidate* candidates,
+                      size_t n_candidates, const uint32_t* pair_passage,
+                      const uint32_t* pair_candidate, size_t n_pairs, AfChainMetrics* out_metrics,
+                      float* const* out_audio);
+
+/* The same sweep split into upload / run / download so that a caller can keep
+ * the inputs resident in HBM and re-run (bench.py's kernel-only number). */
+int afsim_sweep_prepare(AfsimHandle* handle, const float* const* passages,
+                        const size_t* passage_len, size_t n_passages, double sample_rate,
+                        const AfCandidate* candidates, size_t n_candidates,
+                        const uint32_t* pair_passage, const uint32_t* pair_candidate,
+                        size_t n_pairs, int want_audio, AfsimSweep** out_sweep);
+/* Device-side synthetic passages (bench only: avoids a 94 GB host buffer for the
+ * batch true-peak config).  kind 0 = speech-like, 1 = hot white noise; seeds as
+ * SURVEY 8(d). */
+int afsim_sweep_prepare_synthetic(AfsimHandle* handle, int kind, size_t n_passages,
+                                  size_t passage_len, double sample_rate,
+                                  const AfCandidate* candidates, size_t n_candidates,
+                                  const uint32_t* pair_passage, const uint32_t* pair_candidate,
+                                  size_t n_pairs, int want_audio, AfsimSweep** out_sweep);
+/* async: queues the render + reduction kernels on the handle's stream. */
+int afsim_sweep_launch(AfsimHandle* handle, AfsimSweep* sweep);
+/* Waits for the stream and copies n_pairs metrics to the host. */
+int afsim_sweep_collect(AfsimHandle* handle, AfsimSweep* sweep, AfChainMetrics* out_metrics);
+/* Copies one stream's rendered audio (want_audio sweeps) to the host. */
+int afsim_sweep_collect_audio(AfsimHandle* handle, AfsimSweep* sweep, size_t pair, float* out_audio,
+                              size_t n);
+/* Device pointer of the n_pairs AfChainMetrics (for an NCCL gather without a host hop). */
+void* afsim_sweep_metrics_device_ptr(AfsimSweep* sweep);
+/* Kernels launched by one afsim_sweep_launch. */
+int afsim_sweep_kernel_count(const AfsimSweep* sweep);
+/* Milliseconds the render kernel(s) of the last afsim_sweep_launch took (CUDA
+ * events on the handle's stream); waits for completion. */
+int afsim_sweep_last_render_ms(AfsimHandle* handle, AfsimSweep* sweep, float* out_ms);
+void afsim_sweep_release(AfsimHandle* handle, AfsimSweep* sweep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFSIM_H */
