@@ -1,0 +1,733 @@
+// afsim_api.cu -- the C ABI of include/afsim.h: handle, batching, the chunk x stage wavefront.
+//
+// Host orchestration only; all signal arithmetic is in the kernels (afsim_kernels.cu) and all
+// settings arithmetic in the planner (afsim_plan.cpp).  There is no CPU render path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/afsim.h"
+#include "afsim_kernels.h"
+#include "afsim_plan.h"
+#include "afsim_render.h"
+
+using namespace afsim;
+
+namespace {
+thread_local std::string g_create_error;
+constexpr int kMaxStages = 16;
+}  // namespace
+
+struct AfsimHandle {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // caller-visible stream: every call starts and ends on it
+    bool own_stream = false;
+    cudaStream_t stage_stream[kMaxStages] = {};
+    cudaEvent_t ev_fork = nullptr;
+    std::string error;
+};
+
+namespace {
+
+struct DeviceBuffers {  // frees what it allocated
+    std::vector<void*> ptrs;
+    ~DeviceBuffers() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        const cudaError_t err = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (err != cudaSuccess) return err;
+        ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return cudaSuccess;
+    }
+};
+
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT };
+struct StageDesc {
+    StageKind kind;
+    int arg;  // SK_EQ: first section
+};
+
+struct Batch {
+    BatchArgs args{};
+    std::vector<StageDesc> stages;
+    int chunk = 0, slots = 0, eq_k = 0;
+    std::vector<cudaEvent_t> events;  // [stage][slot]
+    ~Batch() {
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+};
+
+}  // namespace
+
+struct AfsimSweep {
+    DeviceBuffers mem;
+    std::vector<std::unique_ptr<Batch>> batches;
+    AfChainMetrics* d_metrics = nullptr;   // [n_pairs], caller's pair order
+    StreamAccum* d_accum_first = nullptr;  // accum table of batch 0 (afsim_eq_render reads stream 0)
+    float* d_audio = nullptr;
+    std::vector<uint64_t> audio_off;       // per pair
+    std::vector<uint64_t> pair_len;
+    size_t n_pairs = 0;
+    int kernels_per_launch = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool launched = false;
+    ~AfsimSweep() {
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_stop) cudaEventDestroy(ev_stop);
+    }
+};
+
+namespace {
+
+int set_error(AfsimHandle* h, int status, const std::string& msg) {
+    if (h) h->error = msg;
+    return status;
+}
+int cuda_fail(AfsimHandle* h, cudaError_t err, const char* what) {
+    const int status = err == cudaErrorMemoryAllocation ? AFSIM_OUT_OF_MEMORY : AFSIM_CUDA_ERROR;
+    if (err == cudaErrorMemoryAllocation) cudaGetLastError();  // clear the sticky-free error
+    return set_error(h, status, std::string(what) + ": " + cudaGetErrorString(err));
+}
+#define AF_CUDA(h, expr)                                         \
+    do {                                                         \
+        const cudaError_t af_err__ = (expr);                     \
+        if (af_err__ != cudaSuccess) return cuda_fail((h), af_err__, #expr); \
+    } while (0)
+
+int env_int(const char* name, int fallback) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return fallback;
+    const long parsed = std::strtol(v, nullptr, 10);
+    return parsed > 0 ? static_cast<int>(parsed) : fallback;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ---- sweep construction ----------------------------------------------------------------------------------
+
+struct PassageSource {
+    const float* const* host = nullptr;  // host passages (nullptr: synthetic on device)
+    int synth_kind = 0;
+};
+
+int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_len, size_t n_passages, double fs,
+                const AfCandidate* candidates, size_t n_candidates, const CandidatePlan* preplanned,
+                const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs, int want_audio,
+                AfsimSweep** out_sweep) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (!out_sweep) return set_error(h, AFSIM_INVALID_ARGUMENT, "out_sweep is null");
+    *out_sweep = nullptr;
+    if ((pair_passage == nullptr) != (pair_candidate == nullptr))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "pair_passage and pair_candidate must both be given or both be null");
+    if (n_pairs > 0 && (n_passages == 0 || n_candidates == 0))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "a sweep needs at least one passage and one candidate");
+    if (!pair_passage && n_pairs != n_passages * n_candidates)
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "n_pairs must equal n_candidates * n_passages for a full cross product");
+    AF_CUDA(h, cudaSetDevice(h->device));
+
+    // plan every candidate (reference constructor + setters -> constants)
+    std::vector<CandidatePlan> plans(n_candidates);
+    for (size_t c = 0; c < n_candidates; ++c) {
+        if (preplanned) {
+            plans[c] = preplanned[c];
+        } else {
+            std::string msg;
+            const int rc = plan_candidate(candidates[c].bands, candidates[c].settings, fs, &plans[c], &msg);
+            if (rc != AFSIM_OK) return set_error(h, rc, msg);
+        }
+    }
+    const RateConstants rate = rate_constants(fs);
+
+    auto sweep = std::make_unique<AfsimSweep>();
+    sweep->n_pairs = n_pairs;
+
+    // passages -> one device pool
+    std::vector<uint64_t> passage_off(n_passages + 1, 0);
+    for (size_t p = 0; p < n_passages; ++p) {
+        if (passage_len[p] > 0x7fffff00u) return set_error(h, AFSIM_INVALID_ARGUMENT, "passage too long");
+        passage_off[p + 1] = passage_off[p] + passage_len[p];
+    }
+    float* d_signals = nullptr;
+    AF_CUDA(h, sweep->mem.alloc(&d_signals, passage_off[n_passages]));
+    if (src.host) {
+        for (size_t p = 0; p < n_passages; ++p)
+            if (passage_len[p])
+                AF_CUDA(h, cudaMemcpyAsync(d_signals + passage_off[p], src.host[p], passage_len[p] * sizeof(float),
+                                           cudaMemcpyHostToDevice, h->stream));
+    } else if (n_passages) {
+        for (size_t p = 1; p < n_passages; ++p)
+            if (passage_len[p] != passage_len[0])
+                return set_error(h, AFSIM_INVALID_ARGUMENT, "synthetic passages must share one length");
+        AF_CUDA(h, launch_synth(d_signals, passage_len[0], static_cast<int>(n_passages), src.synth_kind, fs, h->stream));
+    }
+
+    // candidate constants
+    CandidateParams* d_params = nullptr;
+    AF_CUDA(h, sweep->mem.alloc(&d_params, n_candidates));
+    {
+        std::vector<CandidateParams> host_params(n_candidates);
+        for (size_t c = 0; c < n_candidates; ++c) host_params[c] = plans[c].params;
+        if (n_candidates)
+            AF_CUDA(h, cudaMemcpyAsync(d_params, host_params.data(), n_candidates * sizeof(CandidateParams),
+                                       cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaStreamSynchronize(h->stream));  // host_params goes out of scope
+    }
+    double* d_eq_default = nullptr;
+    AF_CUDA(h, sweep->mem.alloc(&d_eq_default, 50));
+    AF_CUDA(h, cudaMemcpyAsync(d_eq_default, rate.eq_default, sizeof rate.eq_default, cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+
+    AF_CUDA(h, sweep->mem.alloc(&sweep->d_metrics, n_pairs));
+    AF_CUDA(h, cudaMemsetAsync(sweep->d_metrics, 0, std::max<size_t>(n_pairs, 1) * sizeof(AfChainMetrics), h->stream));
+
+    // output audio pool, caller's pair order
+    sweep->audio_off.assign(n_pairs + 1, 0);
+    sweep->pair_len.assign(n_pairs, 0);
+    auto passage_of = [&](size_t i) { return pair_passage ? pair_passage[i] : static_cast<uint32_t>(i % n_passages); };
+    auto candidate_of = [&](size_t i) { return pair_candidate ? pair_candidate[i] : static_cast<uint32_t>(i / n_passages); };
+    for (size_t i = 0; i < n_pairs; ++i) {
+        if (passage_of(i) >= n_passages || candidate_of(i) >= n_candidates)
+            return set_error(h, AFSIM_INVALID_ARGUMENT, "pair index out of range");
+        sweep->pair_len[i] = passage_len[passage_of(i)];
+        sweep->audio_off[i + 1] = sweep->audio_off[i] + (want_audio ? sweep->pair_len[i] : 0);
+    }
+    if (want_audio) AF_CUDA(h, sweep->mem.alloc(&sweep->d_audio, sweep->audio_off[n_pairs]));
+
+    // batches: streams that share structure, lookahead, input stage and length
+    typedef std::tuple<uint32_t, uint32_t, uint32_t, uint64_t> Key;
+    std::map<Key, std::vector<uint32_t>> groups;
+    for (size_t i = 0; i < n_pairs; ++i) {
+        const CandidatePlan& pl = plans[candidate_of(i)];
+        groups[Key(pl.structure, pl.lookahead, pl.input_stage, sweep->pair_len[i])].push_back(static_cast<uint32_t>(i));
+    }
+    for (auto& kv : groups) {
+        const std::vector<uint32_t>& members = kv.second;
+        auto batch = std::make_unique<Batch>();
+        BatchArgs& a = batch->args;
+        const int S = static_cast<int>(members.size());
+        const int S_pad = round_up(S, 32);
+        const int T = static_cast<int>(std::get<3>(kv.first));
+        a.structure = std::get<0>(kv.first);
+        a.lookahead = static_cast<int>(std::get<1>(kv.first));
+        a.input_stage = static_cast<int>(std::get<2>(kv.first));
+        a.n_streams = S;
+        a.stride = S_pad;
+        a.n_samples = T;
+        a.block_samples = rate.block_samples;
+        a.fade_samples = rate.fade_samples;
+        a.n_rows = (T + rate.block_samples - 1) / rate.block_samples;
+        a.n_pad = 2;
+        while (a.n_pad < a.n_rows) a.n_pad <<= 1;
+        a.params = d_params;
+        a.signals = d_signals;
+        a.audio = sweep->d_audio;
+        a.eq_default = d_eq_default;
+        a.metrics = sweep->d_metrics;
+
+        // chunking: a multiple of 8 (true-peak FIR groups) and of the compressor micro-tile, long
+        // enough to hold the biquad crossfade and the limiter lookback
+        int chunk = env_int("AFSIM_CHUNK", 1024);
+        chunk = std::max(chunk, std::max(rate.fade_samples, a.lookahead + 1));
+        chunk = round_up(chunk, 8);
+        batch->chunk = chunk;
+        const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
+        // ring slots = chunks in flight + 1; few-stream batches need the stage wavefront to fill the GPU
+        int slots = S <= 16384 ? 12 : (S <= 65536 ? 4 : 2);
+        slots = env_int("AFSIM_SLOTS", slots);
+        slots = std::max(2, std::min(slots, std::max(2, n_chunks + 1)));
+        batch->slots = slots;
+        a.ring_rows = slots * chunk;
+
+        // per-stream tables
+        std::vector<uint32_t> cand(S_pad, 0), pair(S_pad, 0);
+        std::vector<uint64_t> src_off(S_pad, 0), audio_off(S_pad, 0);
+        uint32_t max_sections = 0;
+        for (int s = 0; s < S; ++s) {
+            const uint32_t i = members[s];
+            cand[s] = candidate_of(i);
+            pair[s] = i;
+            src_off[s] = passage_off[passage_of(i)];
+            audio_off[s] = sweep->audio_off[i];
+            max_sections = std::max(max_sections, plans[cand[s]].params.n_sections);
+        }
+        uint32_t *d_cand = nullptr, *d_pair = nullptr;
+        uint64_t *d_src = nullptr, *d_aoff = nullptr;
+        AF_CUDA(h, sweep->mem.alloc(&d_cand, S_pad));
+        AF_CUDA(h, sweep->mem.alloc(&d_pair, S_pad));
+        AF_CUDA(h, sweep->mem.alloc(&d_src, S_pad));
+        AF_CUDA(h, sweep->mem.alloc(&d_aoff, S_pad));
+        AF_CUDA(h, cudaMemcpyAsync(d_cand, cand.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(d_pair, pair.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(d_src, src_off.data(), S_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(d_aoff, audio_off.data(), S_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaStreamSynchronize(h->stream));
+        a.cand = d_cand;
+        a.pair = d_pair;
+        a.src_off = d_src;
+        a.audio_off = d_aoff;
+
+        const size_t sp = static_cast<size_t>(S_pad);
+        AF_CUDA(h, sweep->mem.alloc(&a.buf_a, static_cast<size_t>(a.ring_rows) * sp));
+        if (a.structure & ST_LIMITER) {
+            AF_CUDA(h, sweep->mem.alloc(&a.buf_b, static_cast<size_t>(a.ring_rows) * sp));
+            AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
+            AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
+        }
+        AF_CUDA(h, sweep->mem.alloc(&a.st_input, kStateInput * sp));
+        AF_CUDA(h, sweep->mem.alloc(&a.st_tp, kStateTruePeak * sp));
+        if (a.structure & ST_DEESSER) {
+            AF_CUDA(h, sweep->mem.alloc(&a.st_deesser, kStateDeEsser * sp));
+            double* de_tab = nullptr;
+            AF_CUDA(h, sweep->mem.alloc(&de_tab, DE_FIELDS * sp));
+            a.de_tab = de_tab;
+        }
+        if (a.structure & ST_COMPRESSOR) AF_CUDA(h, sweep->mem.alloc(&a.st_comp, kStateCompressor * sp));
+        AF_CUDA(h, sweep->mem.alloc(&a.st_eq, static_cast<size_t>(kStateEqPerSection * kMaxSections) * sp));
+        AF_CUDA(h, sweep->mem.alloc(&a.rows, static_cast<size_t>(4) * std::max(a.n_rows, 1) * sp));
+        AF_CUDA(h, sweep->mem.alloc(&a.accum, sp));
+        if (finalize_workspace_bytes(a.n_rows, a.n_pad) > kFinalizeSmemLimit)
+            AF_CUDA(h, sweep->mem.alloc(&a.fin_scratch,
+                                        static_cast<size_t>(S) * (finalize_workspace_bytes(a.n_rows, a.n_pad) / sizeof(float))));
+        if (!sweep->d_accum_first) sweep->d_accum_first = a.accum;
+
+        // stage list in chain order (block_processor.rs:106-161)
+        batch->eq_k = S >= 32768 ? 10 : 5;
+        batch->eq_k = env_int("AFSIM_EQ_K", batch->eq_k) == 10 ? 10 : 5;
+        auto push_eq = [&]() {
+            if (!(a.structure & ST_EQ)) return;
+            for (uint32_t first = 0; first < max_sections; first += batch->eq_k)
+                batch->stages.push_back({SK_EQ, static_cast<int>(first)});
+        };
+        batch->stages.push_back({SK_INPUT, 0});
+        if (a.structure & ST_INPUT_TRUE_PEAK) batch->stages.push_back({SK_INPUT_TP, 0});
+        if (a.structure & ST_EQ_BEFORE_DEESSER) {
+            push_eq();
+            if (a.structure & ST_DEESSER) batch->stages.push_back({SK_DEESSER, 0});
+        } else {
+            if (a.structure & ST_DEESSER) batch->stages.push_back({SK_DEESSER, 0});
+            push_eq();
+        }
+        if (a.structure & ST_COMPRESSOR) batch->stages.push_back({SK_COMPRESSOR, 0});
+        if (a.structure & ST_LIMITER) batch->stages.push_back({SK_LIMITER, 0});
+        batch->stages.push_back({SK_OUTPUT, 0});
+        if (static_cast<int>(batch->stages.size()) > kMaxStages) return set_error(h, AFSIM_UNSUPPORTED, "too many stages");
+        batch->events.resize(batch->stages.size() * static_cast<size_t>(slots));
+        for (cudaEvent_t& e : batch->events) AF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sweep->kernels_per_launch += static_cast<int>(batch->stages.size()) * n_chunks + 1 + ((a.structure & ST_DEESSER) ? 1 : 0);
+        sweep->batches.push_back(std::move(batch));
+    }
+    AF_CUDA(h, cudaEventCreate(&sweep->ev_start));
+    AF_CUDA(h, cudaEventCreate(&sweep->ev_stop));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out_sweep = sweep.release();
+    return AFSIM_OK;
+}
+
+cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& ck, cudaStream_t stream) {
+    switch (st.kind) {
+        case SK_INPUT: return launch_input(b.args, ck, stream);
+        case SK_INPUT_TP: return launch_input_true_peak(b.args, ck, stream);
+        case SK_DEESSER: return launch_deesser(b.args, ck, stream);
+        case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
+        case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
+        case SK_LIMITER: return launch_limiter(b.args, ck, stream);
+        default: return launch_output(b.args, ck, (b.args.structure & ST_LIMITER) != 0, stream);
+    }
+}
+
+// One batch: the chunk x stage wavefront.  Stage i runs on its own CUDA stream (so its chunks stay
+// ordered, which carries the parked state); stage i of chunk c waits for stage i-1 of chunk c; the
+// first stage of chunk c waits for the last stage of chunk c - slots + 1 before it reuses a ring slot.
+int run_batch(AfsimHandle* h, Batch& b) {
+    const BatchArgs& a = b.args;
+    const int n_stages = static_cast<int>(b.stages.size());
+    const int T = a.n_samples;
+    AF_CUDA(h, cudaMemsetAsync(a.accum, 0, static_cast<size_t>(a.stride) * sizeof(StreamAccum), h->stream));
+    AF_CUDA(h, cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
+    if (a.structure & ST_DEESSER) AF_CUDA(h, launch_expand_deesser(a, h->stream));
+    if (T > 0) {
+        AF_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(h->stage_stream[i], h->ev_fork, 0));
+        const int n_chunks = (T + b.chunk - 1) / b.chunk;
+        for (int c = 0; c < n_chunks; ++c) {
+            ChunkArgs ck;
+            ck.n0 = c * b.chunk;
+            ck.len = std::min(b.chunk, T - ck.n0);
+            const int slot = c % b.slots;
+            ck.row0 = slot * b.chunk;
+            for (int i = 0; i < n_stages; ++i) {
+                cudaStream_t st = h->stage_stream[i];
+                if (i > 0) AF_CUDA(h, cudaStreamWaitEvent(st, b.events[static_cast<size_t>(i - 1) * b.slots + slot], 0));
+                if (i == 0 && c - b.slots + 1 >= 0) {
+                    const int old_slot = (c - b.slots + 1) % b.slots;
+                    AF_CUDA(h, cudaStreamWaitEvent(st, b.events[static_cast<size_t>(n_stages - 1) * b.slots + old_slot], 0));
+                }
+                AF_CUDA(h, launch_stage(b, b.stages[i], ck, st));
+                AF_CUDA(h, cudaEventRecord(b.events[static_cast<size_t>(i) * b.slots + slot], st));
+            }
+        }
+        // join: the last stage's stream has seen every other stage through the event chain
+        const int last_slot = (n_chunks - 1) % b.slots;
+        AF_CUDA(h, cudaStreamWaitEvent(h->stream, b.events[static_cast<size_t>(n_stages - 1) * b.slots + last_slot], 0));
+    }
+    AF_CUDA(h, launch_finalize(a, h->stream));
+    return AFSIM_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int afsim_abi_version(void) { return AFSIM_ABI_VERSION; }
+
+const char* afsim_create_error(void) { return g_create_error.c_str(); }
+
+int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle) {
+    g_create_error.clear();
+    if (!out_handle) {
+        g_create_error = "out_handle is null";
+        return AFSIM_INVALID_ARGUMENT;
+    }
+    *out_handle = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                         " (libafsim has no CPU path)";
+        cudaGetLastError();
+        return AFSIM_CUDA_ERROR;
+    }
+    if (device_ordinal < 0 || device_ordinal >= count) {
+        g_create_error = "device ordinal out of range";
+        return AFSIM_INVALID_ARGUMENT;
+    }
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, device_ordinal);
+    if (err != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(err);
+        return AFSIM_CUDA_ERROR;
+    }
+    if (prop.major != 10) {
+        g_create_error = "libafsim is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return AFSIM_CUDA_ERROR;
+    }
+    err = cudaSetDevice(device_ordinal);
+    if (err != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(err);
+        return AFSIM_CUDA_ERROR;
+    }
+    auto h = std::make_unique<AfsimHandle>();
+    h->device = device_ordinal;
+    if (cuda_stream) {
+        h->stream = static_cast<cudaStream_t>(cuda_stream);
+    } else {
+        err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (err != cudaSuccess) {
+            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(err);
+            return AFSIM_CUDA_ERROR;
+        }
+        h->own_stream = true;
+    }
+    for (int i = 0; i < kMaxStages; ++i) {
+        err = cudaStreamCreateWithFlags(&h->stage_stream[i], cudaStreamNonBlocking);
+        if (err != cudaSuccess) {
+            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(err);
+            return AFSIM_CUDA_ERROR;
+        }
+    }
+    err = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (err != cudaSuccess) {
+        g_create_error = std::string("cudaEventCreate: ") + cudaGetErrorString(err);
+        return AFSIM_CUDA_ERROR;
+    }
+    *out_handle = h.release();
+    return AFSIM_OK;
+}
+
+void afsim_destroy(AfsimHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < kMaxStages; ++i)
+        if (h->stage_stream[i]) cudaStreamDestroy(h->stage_stream[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* afsim_last_error(const AfsimHandle* h) { return h ? h->error.c_str() : "null handle"; }
+
+void afsim_chain_settings_default(AfChainSettings* out) {
+    if (out) chain_settings_default(out);
+}
+void afsim_default_bands(AfBand out[AFSIM_NUM_BANDS]) {
+    if (out) default_bands(out);
+}
+
+// ---- sweeps ----------------------------------------------------------------------------------------------------
+
+int afsim_sweep_prepare(AfsimHandle* h, const float* const* passages, const size_t* passage_len, size_t n_passages,
+                        double sample_rate, const AfCandidate* candidates, size_t n_candidates,
+                        const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs, int want_audio,
+                        AfsimSweep** out_sweep) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    if ((n_passages && (!passages || !passage_len)) || (n_candidates && !candidates))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "null passages / candidates");
+    PassageSource src;
+    src.host = passages;
+    return build_sweep(h, src, passage_len, n_passages, sample_rate, candidates, n_candidates, nullptr, pair_passage,
+                       pair_candidate, n_pairs, want_audio, out_sweep);
+}
+
+int afsim_sweep_prepare_synthetic(AfsimHandle* h, int kind, size_t n_passages, size_t passage_len, double sample_rate,
+                                  const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
+                                  const uint32_t* pair_candidate, size_t n_pairs, int want_audio, AfsimSweep** out_sweep) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    if (n_candidates && !candidates) return set_error(h, AFSIM_INVALID_ARGUMENT, "null candidates");
+    if (kind != 0 && kind != 1) return set_error(h, AFSIM_INVALID_ARGUMENT, "synthetic kind must be 0 or 1");
+    std::vector<size_t> lens(n_passages, passage_len);
+    PassageSource src;
+    src.host = nullptr;
+    src.synth_kind = kind;
+    return build_sweep(h, src, lens.data(), n_passages, sample_rate, candidates, n_candidates, nullptr, pair_passage,
+                       pair_candidate, n_pairs, want_audio, out_sweep);
+}
+
+int afsim_sweep_launch(AfsimHandle* h, AfsimSweep* sweep) {
+    if (!h || !sweep) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    AF_CUDA(h, cudaSetDevice(h->device));
+    AF_CUDA(h, cudaEventRecord(sweep->ev_start, h->stream));
+    for (auto& b : sweep->batches) {
+        const int rc = run_batch(h, *b);
+        if (rc != AFSIM_OK) return rc;
+    }
+    AF_CUDA(h, cudaEventRecord(sweep->ev_stop, h->stream));
+    sweep->launched = true;
+    return AFSIM_OK;
+}
+
+int afsim_sweep_collect(AfsimHandle* h, AfsimSweep* sweep, AfChainMetrics* out_metrics) {
+    if (!h || !sweep || (!out_metrics && sweep->n_pairs)) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    AF_CUDA(h, cudaSetDevice(h->device));
+    if (sweep->n_pairs)
+        AF_CUDA(h, cudaMemcpyAsync(out_metrics, sweep->d_metrics, sweep->n_pairs * sizeof(AfChainMetrics),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.0f;
+    if (sweep->launched && cudaEventElapsedTime(&ms, sweep->ev_start, sweep->ev_stop) == cudaSuccess && sweep->n_pairs)
+        for (size_t i = 0; i < sweep->n_pairs; ++i) out_metrics[i].candidate_runtime_ms = static_cast<double>(ms) / sweep->n_pairs;
+    return AFSIM_OK;
+}
+
+int afsim_sweep_collect_audio(AfsimHandle* h, AfsimSweep* sweep, size_t pair, float* out_audio, size_t n) {
+    if (!h || !sweep) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (!sweep->d_audio) return set_error(h, AFSIM_INVALID_ARGUMENT, "sweep was prepared without want_audio");
+    if (pair >= sweep->n_pairs || n > sweep->pair_len[pair] || (!out_audio && n))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "audio request out of range");
+    AF_CUDA(h, cudaSetDevice(h->device));
+    if (n)
+        AF_CUDA(h, cudaMemcpyAsync(out_audio, sweep->d_audio + sweep->audio_off[pair], n * sizeof(float),
+                                   cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AFSIM_OK;
+}
+
+void* afsim_sweep_metrics_device_ptr(AfsimSweep* sweep) { return sweep ? sweep->d_metrics : nullptr; }
+
+int afsim_sweep_kernel_count(const AfsimSweep* sweep) { return sweep ? sweep->kernels_per_launch : 0; }
+
+int afsim_sweep_last_render_ms(AfsimHandle* h, AfsimSweep* sweep, float* out_ms) {
+    if (!h || !sweep || !out_ms) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (!sweep->launched) return set_error(h, AFSIM_INVALID_ARGUMENT, "sweep has not been launched");
+    AF_CUDA(h, cudaSetDevice(h->device));
+    AF_CUDA(h, cudaEventSynchronize(sweep->ev_stop));
+    AF_CUDA(h, cudaEventElapsedTime(out_ms, sweep->ev_start, sweep->ev_stop));
+    return AFSIM_OK;
+}
+
+void afsim_sweep_release(AfsimHandle* h, AfsimSweep* sweep) {
+    if (!sweep) return;
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        for (int i = 0; i < kMaxStages; ++i) cudaStreamSynchronize(h->stage_stream[i]);
+    }
+    delete sweep;
+}
+
+int afsim_chain_sweep(AfsimHandle* h, const float* const* passages, const size_t* passage_len, size_t n_passages,
+                      double sample_rate, const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
+                      const uint32_t* pair_candidate, size_t n_pairs, AfChainMetrics* out_metrics, float* const* out_audio) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    bool want_audio = false;
+    if (out_audio)
+        for (size_t i = 0; i < n_pairs; ++i) want_audio = want_audio || out_audio[i] != nullptr;
+    AfsimSweep* sweep = nullptr;
+    int rc = afsim_sweep_prepare(h, passages, passage_len, n_passages, sample_rate, candidates, n_candidates, pair_passage,
+                                 pair_candidate, n_pairs, want_audio ? 1 : 0, &sweep);
+    if (rc != AFSIM_OK) return rc;
+    rc = afsim_sweep_launch(h, sweep);
+    if (rc == AFSIM_OK) rc = afsim_sweep_collect(h, sweep, out_metrics);
+    if (rc == AFSIM_OK && want_audio)
+        for (size_t i = 0; i < n_pairs && rc == AFSIM_OK; ++i)
+            if (out_audio[i]) rc = afsim_sweep_collect_audio(h, sweep, i, out_audio[i], sweep->pair_len[i]);
+    const std::string keep = h->error;
+    afsim_sweep_release(h, sweep);
+    h->error = keep;
+    return rc;
+}
+
+// ---- single-stream entry points ----------------------------------------------------------------------------------
+
+int afsim_chain_render(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
+                       const AfChainSettings* settings, AfChainMetrics* out_metrics, float* out_audio) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    if (!bands || !settings || !out_metrics || (!audio && n)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    const auto started = std::chrono::steady_clock::now();
+    AfCandidate cand;
+    std::memcpy(cand.bands, bands, sizeof cand.bands);
+    cand.settings = *settings;
+    const float* passages[1] = {audio};
+    const size_t lens[1] = {n};
+    float* outs[1] = {out_audio};
+    const int rc = afsim_chain_sweep(h, passages, lens, 1, sample_rate, &cand, 1, nullptr, nullptr, 1, out_metrics,
+                                     out_audio ? outs : nullptr);
+    if (rc == AFSIM_OK)  // python_api.rs:387,694-697: wall time of the whole call
+        out_metrics->candidate_runtime_ms =
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - started).count();
+    return rc;
+}
+
+int afsim_eq_response(AfsimHandle* h, const double* frequencies_hz, size_t n_freqs, const AfBand* bands, size_t n_sets,
+                      int typed, double sample_rate, double* out_db) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if ((!frequencies_hz && n_freqs) || (!bands && n_sets) || (!out_db && n_freqs && n_sets))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    std::string msg;
+    for (size_t s = 0; s < n_sets; ++s) {
+        const int rc = typed ? validate_typed_bands(bands + s * AFSIM_NUM_BANDS, sample_rate, &msg)
+                             : validate_legacy_response_bands(bands + s * AFSIM_NUM_BANDS, sample_rate, &msg);
+        if (rc != AFSIM_OK) return set_error(h, rc, msg);
+    }
+    if (n_sets == 0 && (!std::isfinite(sample_rate) || sample_rate <= 0.0))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "sample_rate must be finite and positive");
+    {
+        const int rc = validate_response_frequencies(frequencies_hz, n_freqs, sample_rate, &msg);
+        if (rc != AFSIM_OK) return set_error(h, rc, msg);
+    }
+    if (n_freqs == 0 || n_sets == 0) return AFSIM_OK;
+    if (n_freqs * n_sets > 0x7fffffffu) return set_error(h, AFSIM_INVALID_ARGUMENT, "response grid too large");
+    AF_CUDA(h, cudaSetDevice(h->device));
+    std::vector<double> coeffs(n_sets * kMaxSections * 5);
+    std::vector<int> sections(n_sets * AFSIM_NUM_BANDS);
+    for (size_t s = 0; s < n_sets; ++s)
+        plan_eq_sections(bands + s * AFSIM_NUM_BANDS, typed != 0, sample_rate,
+                         reinterpret_cast<double(*)[5]>(coeffs.data() + s * kMaxSections * 5), sections.data() + s * AFSIM_NUM_BANDS);
+    DeviceBuffers mem;
+    double *d_coeffs = nullptr, *d_freqs = nullptr, *d_out = nullptr;
+    int* d_sections = nullptr;
+    AF_CUDA(h, mem.alloc(&d_coeffs, coeffs.size()));
+    AF_CUDA(h, mem.alloc(&d_sections, sections.size()));
+    AF_CUDA(h, mem.alloc(&d_freqs, n_freqs));
+    AF_CUDA(h, mem.alloc(&d_out, n_freqs * n_sets));
+    AF_CUDA(h, cudaMemcpyAsync(d_coeffs, coeffs.data(), coeffs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(d_sections, sections.data(), sections.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(d_freqs, frequencies_hz, n_freqs * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, launch_eq_response(d_coeffs, d_sections, d_freqs, static_cast<int>(n_freqs), static_cast<int>(n_sets), sample_rate,
+                                  d_out, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(out_db, d_out, n_freqs * n_sets * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AFSIM_OK;
+}
+
+int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
+                    AfEqRenderStats* out_stats, float* out_audio) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (!bands || !out_stats || (!audio && n)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    CandidatePlan plan;
+    std::string msg;
+    int rc = plan_eq_only(bands, sample_rate, &plan, &msg);
+    if (rc != AFSIM_OK) return set_error(h, rc, msg);
+    for (size_t i = 0; i < n; ++i)  // lib.rs:225-229
+        if (!std::isfinite(audio[i])) return set_error(h, AFSIM_INVALID_ARGUMENT, "audio must contain only finite samples");
+    const float* passages[1] = {audio};
+    const size_t lens[1] = {n};
+    PassageSource src;
+    src.host = passages;
+    AfsimSweep* sweep = nullptr;
+    rc = build_sweep(h, src, lens, 1, sample_rate, nullptr, 1, &plan, nullptr, nullptr, 1, out_audio ? 1 : 0, &sweep);
+    if (rc != AFSIM_OK) return rc;
+    std::unique_ptr<AfsimSweep> guard(sweep);
+    rc = afsim_sweep_launch(h, sweep);
+    if (rc != AFSIM_OK) return rc;
+    StreamAccum acc;
+    AF_CUDA(h, cudaMemcpyAsync(&acc, sweep->d_accum_first, sizeof acc, cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.0f;
+    AF_CUDA(h, cudaEventElapsedTime(&ms, sweep->ev_start, sweep->ev_stop));
+    if (out_audio && n) {
+        rc = afsim_sweep_collect_audio(h, sweep, 0, out_audio, n);
+        if (rc != AFSIM_OK) return rc;
+    }
+    // max of the configured response over 512 log-spaced points 20 Hz .. 20 kHz (lib.rs:252-262)
+    std::vector<double> freqs(512), resp(512);
+    for (int i = 0; i < 512; ++i) freqs[i] = 20.0 * std::pow(20000.0 / 20.0, static_cast<double>(i) / 511.0);
+    double max_resp = -std::numeric_limits<double>::infinity();
+    {
+        std::vector<double> coeffs(kMaxSections * 5);
+        std::vector<int> sections(AFSIM_NUM_BANDS);
+        plan_eq_sections(bands, true, sample_rate, reinterpret_cast<double(*)[5]>(coeffs.data()), sections.data());
+        DeviceBuffers mem;
+        double *d_coeffs = nullptr, *d_freqs = nullptr, *d_out = nullptr;
+        int* d_sections = nullptr;
+        AF_CUDA(h, mem.alloc(&d_coeffs, coeffs.size()));
+        AF_CUDA(h, mem.alloc(&d_sections, sections.size()));
+        AF_CUDA(h, mem.alloc(&d_freqs, freqs.size()));
+        AF_CUDA(h, mem.alloc(&d_out, resp.size()));
+        AF_CUDA(h, cudaMemcpyAsync(d_coeffs, coeffs.data(), coeffs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(d_sections, sections.data(), sections.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(d_freqs, freqs.data(), freqs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, launch_eq_response(d_coeffs, d_sections, d_freqs, 512, 1, sample_rate, d_out, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(resp.data(), d_out, resp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        AF_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (double v : resp) max_resp = std::fmax(max_resp, v);
+    }
+    std::memset(out_stats, 0, sizeof *out_stats);
+    const double divisor = static_cast<double>(std::max<size_t>(n, 1));
+    out_stats->input_sample_peak = acc.peak_in;
+    out_stats->output_sample_peak = acc.peak_out;
+    out_stats->input_true_peak = acc.peak_in_tp;
+    out_stats->output_true_peak = acc.peak_out_tp;
+    out_stats->input_rms = std::sqrt(acc.sum_in / divisor);
+    out_stats->output_rms = std::sqrt(acc.sum_out / divisor);
+    out_stats->max_response_db = max_resp;
+    out_stats->runtime_ms = static_cast<double>(ms);
+    out_stats->sample_count = n;
+    out_stats->algorithmic_latency_samples = 0;
+    out_stats->non_finite_output = acc.non_finite;
+    guard.reset();
+    return AFSIM_OK;
+}
+
+}  // extern "C"

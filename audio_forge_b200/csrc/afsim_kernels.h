@@ -1,0 +1,28 @@
+// afsim_kernels.h -- launchers of the stage kernels (afsim_kernels.cu), called by afsim_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "afsim_params.h"
+
+namespace afsim {
+
+struct ChunkArgs;
+
+constexpr int kFinalizeThreads = 128;
+constexpr size_t kFinalizeSmemLimit = 200 * 1024;
+
+cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);
+cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first_section, int k, cudaStream_t st);
+cudaError_t launch_deesser(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_limiter(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_output(const BatchArgs& a, const ChunkArgs& ck, bool limiter, cudaStream_t st);
+cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);
+size_t finalize_workspace_bytes(int n_rows, int n_pad);
+cudaError_t launch_eq_response(const double* coeffs, const int* n_sections, const double* freqs, int n_freqs,
+                               int n_sets, double fs, double* out, cudaStream_t st);
+cudaError_t launch_synth(float* out, size_t n_per, int n_passages, int kind, double fs, cudaStream_t st);
+
+}  // namespace afsim

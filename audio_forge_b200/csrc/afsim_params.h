@@ -1,0 +1,154 @@
+// afsim_params.h -- data the host planner hands to the sm_100a kernels.
+//
+// Execution model.  A sweep is cut into BATCHES of streams (candidate x passage
+// pairs) that share stage structure, length and limiter lookahead.  Inside a batch
+//   * one thread renders one stream; 32 consecutive streams form a warp, so every access to the
+//     time-major work buffers `buf[row][stream]` is one coalesced 128-byte transaction;
+//   * the chain is cut into STAGE KERNELS (input, de-esser, EQ slices, compressor, limiter,
+//     true-peak limiter + detector).  Each stage kernel advances all streams of the batch over one
+//     CHUNK of samples, keeping its recurrence state in registers for the whole chunk and parking
+//     it in a stream-minor state table between chunks;
+//   * the stage kernels of consecutive chunks form a wavefront (stage k of chunk c only depends on
+//     stage k-1 of chunk c and stage k of chunk c-1), which the host issues on one CUDA stream per
+//     stage so that few-stream sweeps still fill the GPU.
+//
+//   CandidateParams   per candidate: every constant the recurrences need, derived on the host with
+//                     the host libm exactly as the reference's constructor + setters do
+//                     (rust-core/src/audio/processor/python_api.rs:400-487)
+//   BatchArgs         per batch: tables and buffers (device pointers)
+//   rows              [4][n_rows][S_pad] f32: the per-analysis-block rows (python_api.rs:549-557)
+//   StreamAccum       per stream: running maxima / f64 square sums -> finalize kernel
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace afsim {
+
+constexpr int kMaxSections = 40;       // 10 bands x <=4 Butterworth sections (dsp/eq.rs:32)
+constexpr int kTpDelay = 20;           // dsp/true_peak.rs:11
+constexpr int kMaxLookahead = 1024;    // dsp/limiter.rs:7
+constexpr int kInputBlock = 480;       // block contract of the input cleanup stage (processor/tests.rs:500-549)
+
+// per-candidate flags
+enum LaneFlag : uint32_t {
+    LF_EQ_FADE = 1u << 0,       // legacy band path: 10 sections fade in over F samples
+    LF_DE_AUTO = 1u << 1,
+    LF_C_ADAPTIVE = 1u << 2,
+    LF_C_SIDECHAIN = 1u << 3,
+};
+
+// De-esser constants (CandidateParams::de).
+enum DeField : int {
+    DE_DET = 0,                 // 6 detector biquads x 5 (band b: hp at 10*b, lp at 10*b+5)
+    DE_DYN_COS = 30,            // 3: cos(omega) of the dynamic EQ
+    DE_DYN_ALPHA = 33,          // 3: sin(omega)/(2q)
+    DE_ATTACK = 36,
+    DE_RELEASE,
+    DE_DET_ATTACK,
+    DE_DET_RELEASE,
+    DE_MAX_RED,
+    DE_THRESHOLD,
+    DE_RATIO_FACTOR,            // 1 - 1/ratio
+    DE_RATIO_THR,               // clamp((threshold+60)*0.1, 0, 6)
+    DE_TRIGGER,                 // lerp(8.0, 0.8, amount)
+    DE_SLOPE,
+    DE_CAP,                     // min(auto_cap, max_reduction*0.75)
+    DE_CONF_FLOOR,              // clamp(lerp(0.28,0.06,amount), 0, 0.95)
+    DE_BASE_FALL,
+    DE_BASE_RISE,
+    DE_BASE_INACTIVE,
+    DE_MANUAL_CAP,              // max_reduction*0.75
+    DE_FIELDS
+};
+
+struct CandidateParams {
+    uint32_t flags;             // LaneFlag
+    uint32_t n_sections;        // EQ sections (flattened band-major)
+    float tp_ceil;              // 10f32.powf(ceiling_db as f32 / 20) clamped [1e-6, 1] (block_processor.rs:150-151)
+    float tp_release;           // exp(-1/(clamp(ms,5,500)/1000*fs)) as f32 (dsp/true_peak.rs:308-313)
+    float effective_ceiling_db; // python_api.rs:472-473
+    uint32_t reserved;
+    double eq[kMaxSections][5]; // b0 b1 b2 a1 a2 (target coefficients)
+    double de[DE_FIELDS];       // DeField
+    double de_det0[6][5];       // constructor coefficients of the detector biquads (fade source)
+    double de_dyn0[3][5];       // dynamic EQ: constructor coefficients
+    double de_dyn1[3][5];       // dynamic EQ: configured coefficients at gain 0 (fade target)
+    // compressor (dsp/compressor.rs)
+    double c_threshold, c_factor, c_knee, c_attack, c_det_release, c_release, c_rms, c_makeup_lin, c_sc, c_band,
+        c_fast, c_charge, c_slow;
+    // limiter (dsp/limiter.rs)
+    double l_ceil, l_release;
+    // fixed input high-pass (audio/processor/routing.rs:826-843)
+    double in_hp[5];
+};
+
+// Stage set of a batch; every stream of a batch shares it.
+enum StructureFlag : uint32_t {
+    ST_DEESSER = 1u << 0,
+    ST_EQ_BEFORE_DEESSER = 1u << 1,
+    ST_COMPRESSOR = 1u << 2,
+    ST_LIMITER = 1u << 3,
+    ST_EQ = 1u << 4,
+    ST_INPUT_TRUE_PEAK = 1u << 5,   // simulate_eq_v2: true-peak detector over the input as well
+};
+
+struct StreamAccum {
+    double sum_in;
+    double sum_out;
+    float peak_in;
+    float peak_out;
+    float peak_pre_tp;      // true-peak limiter input oversampler maximum
+    float peak_out_tp;      // detector
+    float peak_in_tp;       // ST_INPUT_TRUE_PEAK
+    float limiter_gr_db;
+    float tp_gr_db;
+    uint32_t events;
+    uint32_t non_finite;
+    uint32_t reserved;
+};
+
+// Slots (doubles per stream) of the per-stage state tables.
+constexpr int kStateInput = 48;
+constexpr int kStateDeEsser = 96;
+constexpr int kStateEqPerSection = 2;
+constexpr int kStateCompressor = 12;
+constexpr int kStateLimiter = 4;
+constexpr int kStateTruePeak = 80;
+
+struct BatchArgs {
+    const CandidateParams* params;
+    const uint32_t* cand;         // [S_pad] candidate index per stream
+    const uint32_t* pair;         // [S_pad] caller's pair index per stream (where its metrics go)
+    const uint64_t* src_off;      // [S_pad] element offset of the stream's source signal in `signals`
+    const uint64_t* audio_off;    // [S_pad] element offset of the stream's output audio in `audio`
+    const float* signals;
+    float* audio;                 // output audio pool, or nullptr
+    float* buf_a;                 // [ring_rows][S_pad] signal up to the sample limiter's input
+    float* buf_b;                 // [ring_rows][S_pad] signal after the sample limiter
+    float* lim_sfx;               // [lookahead + 1][S_pad] suffix maxima of the previous limiter block
+    double* st_input;             // [kStateInput][S_pad]
+    double* st_deesser;           // [kStateDeEsser][S_pad]
+    double* st_eq;                // [kStateEqPerSection * kMaxSections][S_pad]
+    double* st_comp;              // [kStateCompressor][S_pad]
+    double* st_lim;               // [kStateLimiter][S_pad]
+    double* st_tp;                // [kStateTruePeak][S_pad]
+    float* rows;                  // [4][n_rows][S_pad]
+    StreamAccum* accum;           // [S_pad]
+    const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
+    const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)
+    void* metrics;                // AfChainMetrics[n_pairs of the sweep], indexed by pair[s]
+    float* fin_scratch;           // per-block finalize workspace when it does not fit shared memory
+    int n_streams;                // S
+    int stride;                   // S_pad
+    int n_samples;                // T (uniform in the batch)
+    int ring_rows;                // rows of buf_a / buf_b (a multiple of the chunk, >= chunk + lookahead + 1)
+    int n_rows;                   // analysis blocks per stream
+    int n_pad;                    // power of two >= n_rows (finalize sort)
+    int block_samples;            // analysis block (round(fs*0.020), python_api.rs:512-513)
+    int fade_samples;             // biquad crossfade length F (dsp/biquad.rs:12-19)
+    int lookahead;                // limiter lookahead L in samples
+    int input_stage;              // AfInputStage
+    uint32_t structure;           // StructureFlag
+};
+
+}  // namespace afsim

@@ -1,16 +1,15 @@
-// afsim_plan.h -- host planner: candidate settings -> the lane tables the kernels read.
+// afsim_plan.h -- host planner: candidate settings -> the constants the kernels read.
 //
 // This is the host side of the drop-in: it plays the role of the reference's constructor +
 // setter sequence (rust-core/src/audio/processor/python_api.rs:400-487) and reduces it to the
 // constants each recurrence needs, using the host libm exactly as the reference does (so the
-// coefficients are bit-identical to a CPU render), then packs 32 streams per warp.
+// coefficients are bit-identical to a CPU render).
 #pragma once
 #include <cstdint>
 #include <string>
-#include <vector>
 
 #include "../../include/afsim.h"
-#include "afsim_layout.h"
+#include "afsim_params.h"
 
 namespace afsim {
 
@@ -22,45 +21,35 @@ enum class BqKind { LowShelf, HighShelf, Peaking, Notch, HighPass, LowPass };
 BiquadCoeffs design_biquad(BqKind kind, double frequency_hz, double gain_db, double q, double sample_rate);
 double time_constant_to_coeff(double time_ms, double sample_rate);
 
-// Everything one stream needs, before packing.
-struct StreamPlan {
-    double params[P_COUNT];
-    float fparams[FP_COUNT];
-    uint32_t lane_flags;
-    uint32_t n_sections;
-    uint32_t group_flags;     // structural flags every lane of a warp must share
-    uint32_t lookahead;
-    float effective_ceiling_db;
-    int band_sections[AFSIM_NUM_BANDS];  // sections per band (for the response renderer)
+struct CandidatePlan {
+    CandidateParams params;
+    uint32_t structure;   // StructureFlag
+    uint32_t lookahead;   // limiter lookahead in samples (0 when the limiter is off)
+    uint32_t input_stage; // AfInputStage
 };
 
 struct RateConstants {
-    uint32_t block_samples;
-    uint32_t fade_samples;
-    double eq_default[10][5];
+    int block_samples;            // python_api.rs:512-513
+    int fade_samples;             // dsp/biquad.rs:12-19
+    double eq_default[10][5];     // constructor coefficients of the 10 default bands (dsp/eq.rs:125-140)
 };
 
-// Returns "" on success, else the reference's validation message (status in *status).
-std::string plan_stream(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& settings, double sample_rate,
-                        StreamPlan* out, int* status);
-std::string validate_typed_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate);
-std::string validate_legacy_response_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate);
+// Fills `out`; returns AFSIM_OK or a status with the reference's message in *error.
+int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& settings, double sample_rate,
+                   CandidatePlan* out, std::string* error);
+// simulate_eq_v2 (lib.rs:214-288): typed bands, EQ only, true-peak detectors on both sides.
+int plan_eq_only(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate, CandidatePlan* out, std::string* error);
+int validate_typed_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate, std::string* error);
+int validate_legacy_response_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate, std::string* error);
+int validate_response_frequencies(const double* freqs, size_t n, double sample_rate, std::string* error);
 RateConstants rate_constants(double sample_rate);
 
-// EQ sections only (for afsim_eq_response): coefficient table [40][5] in band*4+section order.
+// EQ sections only (afsim_eq_response): coefficient table [40][5] in band*4+section order and the
+// number of sections per band.
 void plan_eq_sections(const AfBand bands[AFSIM_NUM_BANDS], bool typed, double sample_rate, double coeffs[kMaxSections][5],
                       int band_sections[AFSIM_NUM_BANDS]);
 
-// Packing: streams -> warps.
-struct PackedStream {
-    uint32_t pair;       // caller's pair index
-    uint32_t passage;
-    uint32_t candidate;
-};
-struct PackedGroup {
-    GroupHeader header;
-    uint32_t pair_of_lane[kLanes];  // 0xffffffff for padding lanes
-    uint32_t plan_of_lane[kLanes];  // candidate index whose plan the lane uses
-};
+void chain_settings_default(AfChainSettings* out);
+void default_bands(AfBand out[AFSIM_NUM_BANDS]);
 
 }  // namespace afsim

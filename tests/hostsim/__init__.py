@@ -1,0 +1,64 @@
+"""Test harness: the product's stage-kernel bodies compiled for the CPU (see hostsim.cpp).
+
+TEST INFRASTRUCTURE ONLY.  Lets the CPU test-suite check the chunk x stage schedule, state
+parking, ring addressing and the finalize reduction against the oracle without a GPU.  The
+product package never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from audio_forge_b200 import abi
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "libhostsim.so"
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", str(_HERE), "libhostsim.so"], check=True, capture_output=True)
+        L = C.CDLL(str(_LIB))
+        f32p = C.POINTER(C.c_float)
+        u32p = C.POINTER(C.c_uint32)
+        L.hostsim_last_error.restype = C.c_char_p
+        L.hostsim_chain_sweep.argtypes = [C.POINTER(f32p), C.POINTER(C.c_size_t), C.c_size_t, C.c_double,
+                                          C.POINTER(abi.AfCandidate), C.c_size_t, u32p, u32p, C.c_size_t, C.c_int,
+                                          C.c_int, C.c_int, C.POINTER(abi.AfChainMetrics), f32p, f32p]
+        _lib = L
+    return _lib
+
+
+class HostsimError(ValueError):
+    pass
+
+
+def chain_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate, *, chunk=1024, slots=2, eq_k=5,
+                want_audio=False, want_rows=False):
+    """-> (AfChainMetrics array, audio [n_pairs, T] | None, rows [4, n_rows, n_pairs] | None)."""
+    passages = [np.ascontiguousarray(p, dtype=np.float32) for p in passages]
+    f32p = C.POINTER(C.c_float)
+    ptrs = (f32p * len(passages))(*[p.ctypes.data_as(f32p) for p in passages])
+    lens = (C.c_size_t * len(passages))(*[p.size for p in passages])
+    pp = np.ascontiguousarray(pair_passage, dtype=np.uint32)
+    pc = np.ascontiguousarray(pair_candidate, dtype=np.uint32)
+    n_pairs = pp.size
+    T = passages[int(pp[0])].size if n_pairs else 0
+    out = (abi.AfChainMetrics * max(n_pairs, 1))()
+    audio = np.zeros((n_pairs, T), dtype=np.float32) if want_audio else None
+    block = max(1, min(8192, int(round(sample_rate * 0.020))))
+    n_rows = (T + block - 1) // block
+    rows = np.zeros((4, n_rows, n_pairs), dtype=np.float32) if want_rows else None
+    rc = lib().hostsim_chain_sweep(ptrs, lens, len(passages), float(sample_rate), candidates, len(candidates),
+                                   pp.ctypes.data_as(C.POINTER(C.c_uint32)), pc.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   n_pairs, int(chunk), int(slots), int(eq_k), out,
+                                   audio.ctypes.data_as(f32p) if audio is not None else None,
+                                   rows.ctypes.data_as(f32p) if rows is not None else None)
+    if rc != abi.AFSIM_OK:
+        raise HostsimError(lib().hostsim_last_error().decode())
+    return out, audio, rows

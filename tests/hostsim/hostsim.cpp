@@ -1,0 +1,184 @@
+// hostsim.cpp -- TEST HARNESS ONLY: runs the stage-kernel bodies of audio_forge_b200/csrc on the CPU.
+//
+// The CUDA kernels of the product are thin wrappers around the per-stream bodies in afsim_render.h.
+// This harness compiles the same bodies (and the same host planner) with g++ and walks the same
+// chunk x stage schedule with plain loops, so that chunking, state parking, ring addressing and the
+// finalize reduction can be checked against the oracle in a container without a GPU.  It is never
+// linked into libafsim.so and nothing in audio_forge_b200/ loads it.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -shared -fPIC (tests/hostsim/Makefile)
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../audio_forge_b200/csrc/afsim_plan.h"
+#include "../../audio_forge_b200/csrc/afsim_render.h"
+
+using namespace afsim;
+
+namespace {
+const float kFir[4][32] = {
+#include "../../audio_forge_b200/csrc/true_peak_fir.inc"
+};
+thread_local std::string g_error;
+}  // namespace
+
+extern "C" {
+
+const char* hostsim_last_error() { return g_error.c_str(); }
+
+// All pairs must share structure / lookahead / length (one batch).  chunk / slots / eq_k select the
+// schedule to exercise.  out_audio: nullptr or [n_pairs][T].
+int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len, size_t n_passages, double fs,
+                        const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
+                        const uint32_t* pair_candidate, size_t n_pairs, int chunk, int slots, int eq_k,
+                        AfChainMetrics* out_metrics, float* out_audio, float* out_rows /* [4][n_rows][n_pairs] or null */) {
+    g_error.clear();
+    std::vector<CandidatePlan> plans(n_candidates);
+    for (size_t c = 0; c < n_candidates; ++c) {
+        const int rc = plan_candidate(candidates[c].bands, candidates[c].settings, fs, &plans[c], &g_error);
+        if (rc != AFSIM_OK) return rc;
+    }
+    if (n_pairs == 0) return AFSIM_OK;
+    const RateConstants rate = rate_constants(fs);
+    const CandidatePlan& first = plans[pair_candidate[0]];
+    const int T = static_cast<int>(passage_len[pair_passage[0]]);
+    for (size_t i = 0; i < n_pairs; ++i) {
+        const CandidatePlan& pl = plans[pair_candidate[i]];
+        if (pl.structure != first.structure || pl.lookahead != first.lookahead || pl.input_stage != first.input_stage ||
+            static_cast<int>(passage_len[pair_passage[i]]) != T) {
+            g_error = "hostsim: pairs must form one batch";
+            return AFSIM_INVALID_ARGUMENT;
+        }
+    }
+    std::vector<uint64_t> passage_off(n_passages + 1, 0);
+    for (size_t p = 0; p < n_passages; ++p) passage_off[p + 1] = passage_off[p] + passage_len[p];
+    std::vector<float> signals(passage_off[n_passages] + 1);
+    for (size_t p = 0; p < n_passages; ++p)
+        std::memcpy(signals.data() + passage_off[p], passages[p], passage_len[p] * sizeof(float));
+    std::vector<CandidateParams> params(n_candidates);
+    for (size_t c = 0; c < n_candidates; ++c) params[c] = plans[c].params;
+
+    const int S = static_cast<int>(n_pairs);
+    const int S_pad = (S + 31) / 32 * 32;
+    const size_t sp = static_cast<size_t>(S_pad);
+    BatchArgs a{};
+    a.structure = first.structure;
+    a.lookahead = static_cast<int>(first.lookahead);
+    a.input_stage = static_cast<int>(first.input_stage);
+    a.n_streams = S;
+    a.stride = S_pad;
+    a.n_samples = T;
+    a.block_samples = rate.block_samples;
+    a.fade_samples = rate.fade_samples;
+    a.n_rows = (T + rate.block_samples - 1) / rate.block_samples;
+    a.n_pad = 2;
+    while (a.n_pad < a.n_rows) a.n_pad <<= 1;
+    chunk = std::max(chunk, std::max(rate.fade_samples, a.lookahead + 1));
+    chunk = (chunk + 7) / 8 * 8;
+    slots = std::max(slots, 2);
+    a.ring_rows = slots * chunk;
+
+    std::vector<uint32_t> cand(S_pad, 0), pair(S_pad, 0);
+    std::vector<uint64_t> src_off(S_pad, 0), audio_off(S_pad, 0);
+    uint32_t max_sections = 0;
+    for (int s = 0; s < S; ++s) {
+        cand[s] = pair_candidate[s];
+        pair[s] = static_cast<uint32_t>(s);
+        src_off[s] = passage_off[pair_passage[s]];
+        audio_off[s] = static_cast<uint64_t>(s) * T;
+        max_sections = std::max(max_sections, params[cand[s]].n_sections);
+    }
+    std::vector<float> buf_a(static_cast<size_t>(a.ring_rows) * sp), buf_b(static_cast<size_t>(a.ring_rows) * sp);
+    std::vector<float> lim_sfx(static_cast<size_t>(a.lookahead + 1) * sp), rows(static_cast<size_t>(4) * std::max(a.n_rows, 1) * sp, 0.0f);
+    std::vector<double> st_input(kStateInput * sp), st_de(kStateDeEsser * sp), st_eq(kStateEqPerSection * kMaxSections * sp),
+        st_comp(kStateCompressor * sp), st_lim(kStateLimiter * sp), st_tp(kStateTruePeak * sp), de_tab(DE_FIELDS * sp);
+    std::vector<StreamAccum> accum(sp);
+    std::memset(accum.data(), 0, sp * sizeof(StreamAccum));
+    std::vector<AfChainMetrics> metrics(n_pairs);
+    a.params = params.data();
+    a.cand = cand.data();
+    a.pair = pair.data();
+    a.src_off = src_off.data();
+    a.audio_off = audio_off.data();
+    a.signals = signals.data();
+    a.audio = out_audio;
+    a.buf_a = buf_a.data();
+    a.buf_b = buf_b.data();
+    a.lim_sfx = lim_sfx.data();
+    a.st_input = st_input.data();
+    a.st_deesser = st_de.data();
+    a.st_eq = st_eq.data();
+    a.st_comp = st_comp.data();
+    a.st_lim = st_lim.data();
+    a.st_tp = st_tp.data();
+    a.rows = rows.data();
+    a.accum = accum.data();
+    a.eq_default = &rate.eq_default[0][0];
+    a.de_tab = de_tab.data();
+    a.metrics = metrics.data();
+
+    if (a.structure & ST_DEESSER)
+        for (int s = 0; s < S; ++s) body_expand_deesser(a, s);
+    const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
+    auto run_eq = [&](const ChunkArgs& ck) {
+        for (uint32_t f = 0; f < max_sections; f += eq_k)
+            for (int s = 0; s < S; ++s) {
+                if (eq_k == 10)
+                    body_eq<10>(a, ck, s, static_cast<int>(f));
+                else
+                    body_eq<5>(a, ck, s, static_cast<int>(f));
+            }
+    };
+    for (int c = 0; c < n_chunks; ++c) {
+        ChunkArgs ck;
+        ck.n0 = c * chunk;
+        ck.len = std::min(chunk, T - ck.n0);
+        ck.row0 = (c % slots) * chunk;
+        for (int s = 0; s < S; ++s) body_input(a, ck, s);
+        if (a.structure & ST_EQ_BEFORE_DEESSER) {
+            run_eq(ck);
+            if (a.structure & ST_DEESSER)
+                for (int s = 0; s < S; ++s) body_deesser(a, ck, s);
+        } else {
+            if (a.structure & ST_DEESSER)
+                for (int s = 0; s < S; ++s) body_deesser(a, ck, s);
+            run_eq(ck);
+        }
+        if (a.structure & ST_COMPRESSOR)
+            for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
+        if (a.structure & ST_LIMITER) {
+            for (int s = 0; s < S; ++s) body_limiter(a, ck, s);
+            for (int s = 0; s < S; ++s) body_output<true>(a, ck, s, kFir);
+        } else {
+            for (int s = 0; s < S; ++s) body_output<false>(a, ck, s, kFir);
+        }
+    }
+    std::vector<float> ws(finalize_workspace_floats(a.n_rows, a.n_pad));
+    const Coop co{0, 1};
+    for (int s = 0; s < S; ++s) body_finalize(a, s, co, ws.data());
+    std::memcpy(out_metrics, metrics.data(), n_pairs * sizeof(AfChainMetrics));
+    if (out_rows)
+        for (int k = 0; k < 4; ++k)
+            for (int r = 0; r < a.n_rows; ++r)
+                for (int s = 0; s < S; ++s)
+                    out_rows[(static_cast<size_t>(k) * a.n_rows + r) * S + s] = rows[(static_cast<size_t>(k) * a.n_rows + r) * sp + s];
+    return AFSIM_OK;
+}
+
+// Planner outputs, for coefficient-level tests against the oracle.
+int hostsim_plan(const AfBand* bands, const AfChainSettings* settings, double fs, CandidateParams* out, uint32_t* structure,
+                 uint32_t* lookahead) {
+    CandidatePlan plan;
+    const int rc = plan_candidate(bands, *settings, fs, &plan, &g_error);
+    if (rc != AFSIM_OK) return rc;
+    *out = plan.params;
+    *structure = plan.structure;
+    *lookahead = plan.lookahead;
+    return AFSIM_OK;
+}
+size_t hostsim_candidate_params_size() { return sizeof(CandidateParams); }
+
+}  // extern "C"
