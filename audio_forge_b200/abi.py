@@ -244,3 +244,15 @@ def metrics_to_dict(m: AfChainMetrics) -> dict[str, object]:
 
 
 METRIC_F32_KEYS = _METRIC_F32
+
+
+# sizeof(afsim::CandidateParams) (csrc/afsim_params.h): what one planned candidate costs on the H2D path
+CANDIDATE_PARAMS_BYTES = 24 + 8 * (40 * 5 + 52 + 30 + 15 + 15 + 13 + 2 + 5)
+
+
+def ctypes_sizeof_metrics() -> int:
+    return C.sizeof(AfChainMetrics)
+
+
+def ctypes_sizeof_candidate_params() -> int:
+    return CANDIDATE_PARAMS_BYTES

@@ -574,6 +574,107 @@ void afsim_sweep_release(AfsimHandle* h, AfsimSweep* sweep) {
     delete sweep;
 }
 
+int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks, int capacity, int* out_kind,
+                               float* out_ms, int* out_launches, int* out_n) {
+    if (!h || !sweep || !out_kind || !out_ms || !out_launches || !out_n) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    *out_n = 0;
+    if (sweep->batches.empty()) return AFSIM_OK;
+    AF_CUDA(h, cudaSetDevice(h->device));
+    Batch& b = *sweep->batches[0];
+    const BatchArgs& a = b.args;
+    const int n_stages = static_cast<int>(b.stages.size());
+    if (capacity < n_stages + 1) return set_error(h, AFSIM_INVALID_ARGUMENT, "capacity too small");
+    const int T = a.n_samples;
+    const int n_chunks = T > 0 ? (T + b.chunk - 1) / b.chunk : 0;
+    const int timed_chunks = max_chunks > 0 ? std::min(max_chunks, n_chunks) : n_chunks;
+    std::vector<cudaEvent_t> ev(static_cast<size_t>(timed_chunks) * n_stages * 2 + 2);
+    for (cudaEvent_t& e : ev) AF_CUDA(h, cudaEventCreate(&e));
+    auto destroy = [&]() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    };
+    cudaError_t err = cudaMemsetAsync(a.accum, 0, static_cast<size_t>(a.stride) * sizeof(StreamAccum), h->stream);
+    if (err == cudaSuccess)
+        err = cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream);
+    if (err == cudaSuccess && (a.structure & ST_DEESSER)) err = launch_expand_deesser(a, h->stream);
+    for (int c = 0; c < n_chunks && err == cudaSuccess; ++c) {
+        ChunkArgs ck;
+        ck.n0 = c * b.chunk;
+        ck.len = std::min(b.chunk, T - ck.n0);
+        ck.row0 = (c % b.slots) * b.chunk;
+        for (int i = 0; i < n_stages && err == cudaSuccess; ++i) {
+            const bool timed = c < timed_chunks;
+            const size_t e0 = (static_cast<size_t>(c) * n_stages + i) * 2;
+            if (timed) err = cudaEventRecord(ev[e0], h->stream);
+            if (err == cudaSuccess) err = launch_stage(b, b.stages[i], ck, h->stream);
+            if (timed && err == cudaSuccess) err = cudaEventRecord(ev[e0 + 1], h->stream);
+        }
+    }
+    const size_t fin = ev.size() - 2;
+    if (err == cudaSuccess) err = cudaEventRecord(ev[fin], h->stream);
+    if (err == cudaSuccess) err = launch_finalize(a, h->stream);
+    if (err == cudaSuccess) err = cudaEventRecord(ev[fin + 1], h->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    if (err != cudaSuccess) {
+        destroy();
+        return cuda_fail(h, err, "afsim_sweep_profile_stages");
+    }
+    static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
+                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT};
+    for (int i = 0; i < n_stages; ++i) {
+        double total = 0.0;
+        for (int c = 0; c < timed_chunks; ++c) {
+            float ms = 0.0f;
+            const size_t e0 = (static_cast<size_t>(c) * n_stages + i) * 2;
+            cudaEventElapsedTime(&ms, ev[e0], ev[e0 + 1]);
+            total += ms;
+        }
+        out_kind[i] = kind_map[b.stages[i].kind];
+        out_ms[i] = static_cast<float>(total);
+        out_launches[i] = timed_chunks;
+    }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev[fin], ev[fin + 1]);
+    out_kind[n_stages] = AF_STAGE_FINALIZE;
+    out_ms[n_stages] = ms;
+    out_launches[n_stages] = 1;
+    *out_n = n_stages + 1;
+    destroy();
+    return AFSIM_OK;
+}
+
+int afsim_measure_issue_peak(AfsimHandle* h, int kind, double* out) {
+    if (!h || !out || (kind != 0 && kind != 1)) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    AF_CUDA(h, cudaSetDevice(h->device));
+    DeviceBuffers mem;
+    double* sink = nullptr;
+    AF_CUDA(h, mem.alloc(&sink, 1));
+    cudaDeviceProp prop;
+    AF_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+    cudaEvent_t e0, e1;
+    AF_CUDA(h, cudaEventCreate(&e0));
+    AF_CUDA(h, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        launch_issue_peak(kind, iters, blocks, sink, h->stream);
+        cudaEventRecord(e1, h->stream);
+        cudaStreamSynchronize(h->stream);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double instr = static_cast<double>(blocks) * 256.0 * iters * 8.0 * (kind == 0 ? 2.0 : 1.0);
+        if (rep > 0 && ms > 0.0f) best = std::max(best, instr / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(h, err, "afsim_measure_issue_peak");
+    *out = best;
+    return AFSIM_OK;
+}
+
 int afsim_chain_sweep(AfsimHandle* h, const float* const* passages, const size_t* passage_len, size_t n_passages,
                       double sample_rate, const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
                       const uint32_t* pair_candidate, size_t n_pairs, AfChainMetrics* out_metrics, float* const* out_audio) {

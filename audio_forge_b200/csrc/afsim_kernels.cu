@@ -136,9 +136,48 @@ __global__ void k_synth(float* out, size_t n_per, int n_passages, int kind, doub
     out[i] = v;
 }
 
+// Issue-rate microbenchmarks (bench.py's roofline denominators for the recurrence / FIR stages):
+// 8 independent dependent chains per thread of DMUL+DADD (kind 0; -fmad=false keeps them apart, the
+// same instruction mix the biquads issue) or FFMA (kind 1).
+__global__ void __launch_bounds__(256) k_issue_peak(int kind, int iters, double* sink) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kind == 0) {
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 1.0 + 1e-9 * (tid + j);
+        const double m = 1.0 - 1e-12 * (tid & 7), c = 1e-13;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = a[j] * m + c;
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r += a[j];
+        if (r == 12345.678) sink[0] = r;
+    } else {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 1.0f + 1e-6f * (tid + j);
+        const float m = 1.0f - 1e-7f * (tid & 7), c = 1e-8f;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __fmaf_rn(a[j], m, c);
+        }
+        float r = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r += a[j];
+        if (r == 12345.678f) sink[0] = r;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
+cudaError_t launch_issue_peak(int kind, int iters, int blocks, double* sink, cudaStream_t st) {
+    k_issue_peak<<<blocks, 256, 0, st>>>(kind, iters, sink);
+    return cudaGetLastError();
+}
+
 static inline dim3 stream_grid(const BatchArgs& a, int block) { return dim3((unsigned)((a.n_streams + block - 1) / block)); }
 
 // Few-stream batches use 32-thread blocks so that the warps spread over all SMs.

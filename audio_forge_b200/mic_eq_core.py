@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's PyO3 module for the chain-simulator path.
+
+Same function names, argument meaning and error behaviour as ``mic_eq.mic_eq_core``
+(rust-core/src/lib.rs:99-288, rust-core/src/audio/processor/python_api.rs:378-714); every call
+goes through the C ABI of ``libafsim.so`` onto the GPU.  Stands in for the Rust host in this
+repository (no Rust toolchain in the image): ``mic_eq/__init__.py:38-46`` falls back to a
+top-level ``import mic_eq_core``, so putting this package directory on ``sys.path`` makes the
+unmodified ``mic_eq`` callers (``headroom._native_simulate``) use it.  INTEGRATION.md shows the
+``extern "C"`` binding the Rust host would add instead.
+
+Only the chain-simulator entry points exist here; live-engine names (``AudioProcessor`` ...) are
+stubs that raise, exactly like a core built without them would.
+"""
+from __future__ import annotations
+
+import threading
+from collections.abc import Mapping, Sequence
+from typing import Any
+
+import numpy as np
+
+try:  # imported as audio_forge_b200.mic_eq_core
+    from . import abi, native
+except ImportError:  # imported as top-level mic_eq_core
+    from audio_forge_b200 import abi, native
+
+NUM_BANDS = abi.NUM_BANDS
+_lock = threading.Lock()
+_sims: dict[int, native.Simulator] = {}
+
+
+def simulator(device: int = 0) -> native.Simulator:
+    """Process-wide handle per device (created on first use; raises without an sm_100 GPU)."""
+    with _lock:
+        sim = _sims.get(device)
+        if sim is None:
+            sim = native.Simulator(device)
+            _sims[device] = sim
+        return sim
+
+
+# ---- settings dict -> AfChainSettings (python_api.rs:14-52, 415-487) -------------------------------------
+_BOOL_KEYS = {
+    "eq_before_deesser", "deesser_enabled", "deesser_auto_enabled", "compressor_enabled",
+    "compressor_adaptive_release", "compressor_auto_makeup_enabled", "compressor_sidechain_highpass_enabled",
+    "limiter_enabled", "limiter_careful_output_enabled",
+}
+_F64_KEYS = {
+    "deesser_auto_amount", "deesser_low_cut_hz", "deesser_high_cut_hz", "deesser_threshold_db", "deesser_ratio",
+    "deesser_attack_ms", "deesser_release_ms", "deesser_max_reduction_db", "compressor_threshold_db",
+    "compressor_ratio", "compressor_attack_ms", "compressor_release_ms", "compressor_makeup_gain_db",
+    "compressor_base_release_ms", "compressor_target_lufs", "limiter_ceiling_db", "limiter_release_ms",
+    "limiter_lookahead_ms",
+}
+
+
+def _extract_bool(key: str, value: object) -> bool:
+    if isinstance(value, (bool, np.bool_)):  # PyO3 `extract::<bool>` accepts bool only
+        return bool(value)
+    raise TypeError(f"settings[{key!r}]: argument must be bool, not {type(value).__name__}")
+
+
+def _extract_f64(key: str, value: object) -> float:
+    if isinstance(value, (bool, np.bool_)):
+        return float(value)
+    try:
+        return float(value)  # type: ignore[arg-type]
+    except (TypeError, ValueError) as error:
+        raise TypeError(f"settings[{key!r}]: argument must be a real number") from error
+
+
+def settings_from_mapping(settings: Mapping[str, object] | None) -> tuple[abi.AfChainSettings, Any, bool]:
+    """-> (AfChainSettings, eq_bands_v2 | None, return_output_audio); unknown keys are ignored like the reference."""
+    overrides: dict[str, object] = {}
+    typed = None
+    return_audio = False
+    if settings is not None:
+        for key, value in settings.items():
+            if key in _BOOL_KEYS:
+                overrides[key] = _extract_bool(key, value)
+            elif key in _F64_KEYS:
+                overrides[key] = _extract_f64(key, value)
+            elif key == "return_output_audio":
+                return_audio = _extract_bool(key, value)
+            elif key == "eq_bands_v2":
+                typed = value
+            elif key == "input_stage":  # new optional key (absent = reference behaviour)
+                overrides[key] = value
+    if typed is not None:
+        overrides["use_typed_bands"] = True
+    return abi.make_settings(**overrides), typed, return_audio
+
+
+def _legacy_bands(bands: Sequence[tuple[float, float, float]]):
+    bands = list(bands)
+    if len(bands) != NUM_BANDS:
+        raise ValueError(f"expected {NUM_BANDS} EQ bands, got {len(bands)}")
+    return abi.legacy_bands(bands)
+
+
+def _typed_bands(bands):
+    bands = list(bands)
+    if len(bands) != NUM_BANDS:
+        raise ValueError(f"expected {NUM_BANDS} EQ bands, got {len(bands)}")
+    for index, band in enumerate(bands):
+        if band[0] not in abi.FILTER_IDS:  # lib.rs:170-175
+            raise ValueError(f"band {index} has unsupported EQ filter type: {band[0]}")
+    return abi.typed_bands(bands)
+
+
+def _audio_1d(audio) -> np.ndarray:
+    arr = np.asarray(audio)
+    if arr.dtype != np.float32 or arr.ndim != 1:
+        raise TypeError("audio must be a one-dimensional float32 array")
+    if not arr.flags.c_contiguous:  # PyReadonlyArray1::as_slice (python_api.rs:505)
+        raise ValueError("audio must be C-contiguous")
+    return arr
+
+
+def _check_rate_chain(sample_rate: float) -> None:
+    if not np.isfinite(sample_rate) or sample_rate <= 0.0:
+        raise ValueError("sample_rate must be positive and finite")
+
+
+# ---- the reference's pyfunctions ---------------------------------------------------------------------------
+
+def simulate_auto_eq_chain(audio, sample_rate: float, bands, settings: Mapping[str, object] | None = None,
+                           *, device: int = 0) -> dict[str, Any]:
+    """python_api.rs:378-714."""
+    arr = _audio_1d(audio)
+    sample_rate = float(sample_rate)
+    _check_rate_chain(sample_rate)
+    legacy = _legacy_bands(bands)
+    st, typed, return_audio = settings_from_mapping(settings)
+    band_arr = _typed_bands(typed) if typed is not None else legacy
+    m, out = simulator(device).chain_render(arr, sample_rate, band_arr, st, return_audio=return_audio)
+    result = abi.metrics_to_dict(m)
+    if return_audio:
+        result["output_audio"] = out.tolist()
+    return result
+
+
+def simulate_auto_eq_chain_batch(passages, sample_rate: float, candidates, *, pair_passage=None, pair_candidate=None,
+                                 device: int = 0) -> list[dict[str, Any]]:
+    """Batched form: ``candidates`` = sequence of ``(bands, settings)`` as simulate_auto_eq_chain takes them.
+
+    Default pairing is the full cross product, candidate-major (pair = candidate * n_passages + passage).
+    What apply_headroom_validation (headroom.py:306-320) and _calibrate_compressor_threshold
+    (voice_setup.py:916-966) evaluate one call at a time."""
+    sample_rate = float(sample_rate)
+    _check_rate_chain(sample_rate)
+    arrs = [_audio_1d(p) for p in passages]
+    cands = (abi.AfCandidate * max(len(candidates), 1))()
+    for i, (bands, settings) in enumerate(candidates):
+        legacy = _legacy_bands(bands)
+        st, typed, _ = settings_from_mapping(settings)
+        band_arr = _typed_bands(typed) if typed is not None else legacy
+        for b in range(NUM_BANDS):
+            cands[i].bands[b] = band_arr[b]
+        cands[i].settings = st
+    cands_view = (abi.AfCandidate * len(candidates)).from_buffer(cands) if len(candidates) else cands
+    metrics, _ = simulator(device).chain_sweep(arrs, sample_rate, cands_view, pair_passage, pair_candidate)
+    n = len(arrs) * len(candidates) if pair_passage is None else len(pair_passage)
+    return [abi.metrics_to_dict(metrics[i]) for i in range(n)]
+
+
+def simulate_eq_v2(audio, sample_rate: float, bands, return_output_audio: bool = False, *, device: int = 0):
+    """lib.rs:214-288."""
+    sample_rate = float(sample_rate)
+    if not np.isfinite(sample_rate) or sample_rate <= 0.0:
+        raise ValueError("sample_rate must be finite and positive")
+    band_arr = _typed_bands(bands)
+    arr = _audio_1d(audio)
+    st, out = simulator(device).eq_render(arr, sample_rate, band_arr, return_audio=return_output_audio)
+    result: dict[str, Any] = {
+        "input_sample_peak": float(st.input_sample_peak),
+        "output_sample_peak": float(st.output_sample_peak),
+        "input_true_peak": float(st.input_true_peak),
+        "output_true_peak": float(st.output_true_peak),
+        "input_rms": float(st.input_rms),
+        "output_rms": float(st.output_rms),
+        "max_response_db": float(st.max_response_db),
+        "runtime_ms": float(st.runtime_ms),
+        "sample_count": int(st.sample_count),
+        "algorithmic_latency_samples": int(st.algorithmic_latency_samples),
+        "non_finite_output": bool(st.non_finite_output),
+    }
+    if return_output_audio:
+        result["output_audio"] = out.tolist()
+    return result
+
+
+def eq_magnitude_response(frequencies_hz, bands, sample_rate: float, *, device: int = 0) -> list[float]:
+    """lib.rs:99-150 (legacy 3-tuple bands)."""
+    sample_rate = float(sample_rate)
+    if not np.isfinite(sample_rate) or sample_rate <= 0.0:
+        raise ValueError("sample_rate must be finite and positive")
+    band_arr = _legacy_bands(bands)
+    return simulator(device).eq_response(list(frequencies_hz), band_arr, sample_rate, typed=False)[0].tolist()
+
+
+def eq_magnitude_response_v2(frequencies_hz, bands, sample_rate: float, *, device: int = 0) -> list[float]:
+    """lib.rs:191-212 (typed 6-tuple bands)."""
+    sample_rate = float(sample_rate)
+    if not np.isfinite(sample_rate) or sample_rate <= 0.0:
+        raise ValueError("sample_rate must be finite and positive")
+    band_arr = _typed_bands(bands)
+    return simulator(device).eq_response(list(frequencies_hz), band_arr, sample_rate, typed=True)[0].tolist()
+
+
+# ---- names mic_eq/__init__.py:55-58 reads unguarded; the live engine is out of scope here -------------------
+def _out_of_scope(*_args, **_kwargs):
+    raise ImportError("the live audio engine is not part of the B200 chain-simulator build")
+
+
+class AudioProcessor:  # noqa: D101
+    def __init__(self, *args, **kwargs):
+        _out_of_scope()
+
+
+class DeviceInfo:  # noqa: D101
+    def __init__(self, *args, **kwargs):
+        _out_of_scope()
+
+
+def list_input_devices():
+    return []
+
+
+def list_output_devices():
+    return []

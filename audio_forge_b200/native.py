@@ -1,0 +1,283 @@
+"""ctypes binding of libafsim.so (the sm_100a C-ABI library, include/afsim.h).
+
+This is the only door from Python into the product.  There is no CPU fallback: when the
+library is missing, or no sm_100 CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from . import abi
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libafsim.so"
+_lib = None
+
+EXPORTS = (
+    "afsim_abi_version", "afsim_create", "afsim_destroy", "afsim_last_error", "afsim_create_error",
+    "afsim_chain_settings_default", "afsim_default_bands", "afsim_chain_render", "afsim_eq_render",
+    "afsim_eq_response", "afsim_chain_sweep", "afsim_sweep_prepare", "afsim_sweep_prepare_synthetic",
+    "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
+    "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
+    "afsim_sweep_profile_stages", "afsim_measure_issue_peak",
+)
+STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize")
+
+
+class AfsimError(RuntimeError):
+    """Library-level failure (CUDA error, out of memory, unsupported settings)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"afsim status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+def build(force: bool = False) -> Path:
+    """Compile libafsim.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    csrc = _PKG / "csrc"
+    if force:
+        subprocess.run(["make", "-C", str(csrc), "clean"], check=True, capture_output=True)
+    proc = subprocess.run(["make", "-C", str(csrc)], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("building libafsim.so failed:\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: build it with `make -C audio_forge_b200/csrc` (or __graft_entry__.build()); "
+            "there is no CPU fallback")
+    L = C.CDLL(str(LIB_PATH))
+    f32p, f64p, u32p = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+    vp, szp = C.c_void_p, C.POINTER(C.c_size_t)
+    bands_p, settings_p = C.POINTER(abi.AfBand), C.POINTER(abi.AfChainSettings)
+    cand_p, metrics_p = C.POINTER(abi.AfCandidate), C.POINTER(abi.AfChainMetrics)
+    L.afsim_abi_version.restype = C.c_int
+    L.afsim_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.afsim_destroy.argtypes = [vp]
+    L.afsim_destroy.restype = None
+    L.afsim_last_error.argtypes = [vp]
+    L.afsim_last_error.restype = C.c_char_p
+    L.afsim_create_error.restype = C.c_char_p
+    L.afsim_chain_settings_default.argtypes = [settings_p]
+    L.afsim_chain_settings_default.restype = None
+    L.afsim_default_bands.argtypes = [bands_p]
+    L.afsim_default_bands.restype = None
+    L.afsim_chain_render.argtypes = [vp, f32p, C.c_size_t, C.c_double, bands_p, settings_p, metrics_p, f32p]
+    L.afsim_eq_render.argtypes = [vp, f32p, C.c_size_t, C.c_double, bands_p, C.POINTER(abi.AfEqRenderStats), f32p]
+    L.afsim_eq_response.argtypes = [vp, f64p, C.c_size_t, bands_p, C.c_size_t, C.c_int, C.c_double, f64p]
+    L.afsim_chain_sweep.argtypes = [vp, C.POINTER(f32p), szp, C.c_size_t, C.c_double, cand_p, C.c_size_t, u32p, u32p,
+                                    C.c_size_t, metrics_p, C.POINTER(f32p)]
+    L.afsim_sweep_prepare.argtypes = [vp, C.POINTER(f32p), szp, C.c_size_t, C.c_double, cand_p, C.c_size_t, u32p, u32p,
+                                      C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.afsim_sweep_prepare_synthetic.argtypes = [vp, C.c_int, C.c_size_t, C.c_size_t, C.c_double, cand_p, C.c_size_t,
+                                                u32p, u32p, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.afsim_sweep_launch.argtypes = [vp, vp]
+    L.afsim_sweep_collect.argtypes = [vp, vp, metrics_p]
+    L.afsim_sweep_collect_audio.argtypes = [vp, vp, C.c_size_t, f32p, C.c_size_t]
+    L.afsim_sweep_metrics_device_ptr.argtypes = [vp]
+    L.afsim_sweep_metrics_device_ptr.restype = vp
+    L.afsim_sweep_kernel_count.argtypes = [vp]
+    L.afsim_sweep_kernel_count.restype = C.c_int
+    L.afsim_sweep_last_render_ms.argtypes = [vp, vp, f32p]
+    L.afsim_sweep_release.argtypes = [vp, vp]
+    L.afsim_sweep_release.restype = None
+    L.afsim_sweep_profile_stages.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_int)]
+    L.afsim_measure_issue_peak.argtypes = [vp, C.c_int, f64p]
+    _lib = L
+    return L
+
+
+def _f32p(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32)) if a is not None else None
+
+
+class Sweep:
+    """A candidate x passage sweep resident in HBM (afsim_sweep_* in include/afsim.h)."""
+
+    def __init__(self, sim: "Simulator", ptr: int, n_pairs: int, pair_len):
+        self._sim, self._ptr, self.n_pairs, self._pair_len = sim, C.c_void_p(ptr), n_pairs, pair_len
+
+    def launch(self) -> None:
+        self._sim._check(lib().afsim_sweep_launch(self._sim._h, self._ptr))
+
+    def collect(self):
+        out = (abi.AfChainMetrics * max(self.n_pairs, 1))()
+        self._sim._check(lib().afsim_sweep_collect(self._sim._h, self._ptr, out))
+        return out
+
+    def collect_audio(self, pair: int) -> np.ndarray:
+        n = int(self._pair_len[pair])
+        out = np.zeros(n, dtype=np.float32)
+        self._sim._check(lib().afsim_sweep_collect_audio(self._sim._h, self._ptr, pair, _f32p(out), n))
+        return out
+
+    def render_ms(self) -> float:
+        ms = C.c_float(0.0)
+        self._sim._check(lib().afsim_sweep_last_render_ms(self._sim._h, self._ptr, C.byref(ms)))
+        return float(ms.value)
+
+    def profile_stages(self, max_chunks: int = 0):
+        """Serialised pass with CUDA events around every stage launch -> [(stage name, total ms, launches)]."""
+        cap = 32
+        kinds, ms, launches, n = (C.c_int * cap)(), (C.c_float * cap)(), (C.c_int * cap)(), C.c_int(0)
+        self._sim._check(lib().afsim_sweep_profile_stages(self._sim._h, self._ptr, int(max_chunks), cap, kinds, ms,
+                                                          launches, C.byref(n)))
+        return [(STAGE_NAMES[kinds[i]], float(ms[i]), int(launches[i])) for i in range(n.value)]
+
+    @property
+    def kernel_count(self) -> int:
+        return int(lib().afsim_sweep_kernel_count(self._ptr))
+
+    @property
+    def metrics_device_ptr(self) -> int:
+        return int(lib().afsim_sweep_metrics_device_ptr(self._ptr) or 0)
+
+    def release(self) -> None:
+        if self._ptr:
+            lib().afsim_sweep_release(self._sim._h, self._ptr)
+            self._ptr = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Simulator:
+    """One afsim handle = one CUDA device + stream.  Raises when no sm_100 GPU is usable."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.afsim_create(int(device), C.c_void_p(cuda_stream) if cuda_stream else None, C.byref(h))
+        if rc != abi.AFSIM_OK:
+            raise AfsimError(rc, L.afsim_create_error().decode())
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().afsim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc == abi.AFSIM_OK:
+            return
+        msg = lib().afsim_last_error(self._h).decode()
+        if rc == abi.AFSIM_INVALID_ARGUMENT:
+            raise ValueError(msg)  # the reference raises PyValueError here
+        raise AfsimError(rc, msg)
+
+    def issue_peak(self, kind: int) -> float:
+        """1e9 warp-lane instructions / s: kind 0 = FP64 DMUL+DADD chains, 1 = FP32 FFMA chains."""
+        out = C.c_double(0.0)
+        self._check(lib().afsim_measure_issue_peak(self._h, int(kind), C.byref(out)))
+        return float(out.value)
+
+    # ---- single-stream entry points ----
+    def chain_render(self, audio, sample_rate, bands, settings: abi.AfChainSettings, return_audio: bool = False):
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        m = abi.AfChainMetrics()
+        out = np.zeros_like(audio) if return_audio else None
+        self._check(lib().afsim_chain_render(self._h, _f32p(audio), audio.size, float(sample_rate), bands,
+                                             C.byref(settings), C.byref(m), _f32p(out) if out is not None else None))
+        return m, out
+
+    def eq_render(self, audio, sample_rate, bands, return_audio: bool = False):
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        st = abi.AfEqRenderStats()
+        out = np.zeros_like(audio) if return_audio else None
+        self._check(lib().afsim_eq_render(self._h, _f32p(audio), audio.size, float(sample_rate), bands, C.byref(st),
+                                          _f32p(out) if out is not None else None))
+        return st, out
+
+    def eq_response(self, frequencies_hz, band_sets, sample_rate, typed: bool) -> np.ndarray:
+        """band_sets: AfBand array holding n_sets * 10 bands -> [n_sets, n_freqs] dB."""
+        freqs = np.ascontiguousarray(frequencies_hz, dtype=np.float64)
+        n_sets = len(band_sets) // abi.NUM_BANDS
+        out = np.zeros((n_sets, freqs.size), dtype=np.float64)
+        self._check(lib().afsim_eq_response(self._h, freqs.ctypes.data_as(C.POINTER(C.c_double)), freqs.size, band_sets,
+                                            n_sets, 1 if typed else 0, float(sample_rate),
+                                            out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    # ---- sweeps ----
+    @staticmethod
+    def _pairs(n_passages, n_candidates, pair_passage, pair_candidate):
+        if pair_passage is None:
+            return None, None, n_passages * n_candidates
+        pp = np.ascontiguousarray(pair_passage, dtype=np.uint32)
+        pc = np.ascontiguousarray(pair_candidate, dtype=np.uint32)
+        if pp.size != pc.size:
+            raise ValueError("pair_passage and pair_candidate must have the same length")
+        return pp, pc, pp.size
+
+    def chain_sweep(self, passages, sample_rate, candidates, pair_passage=None, pair_candidate=None,
+                    return_audio: bool = False):
+        """-> (AfChainMetrics array, list of audio arrays | None); one blocking call."""
+        sweep = self.prepare_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate,
+                                   want_audio=return_audio)
+        try:
+            sweep.launch()
+            metrics = sweep.collect()
+            audio = [sweep.collect_audio(i) for i in range(sweep.n_pairs)] if return_audio else None
+        finally:
+            sweep.release()
+        return metrics, audio
+
+    def prepare_sweep(self, passages, sample_rate, candidates, pair_passage=None, pair_candidate=None,
+                      want_audio: bool = False) -> Sweep:
+        passages = [np.ascontiguousarray(p, dtype=np.float32) for p in passages]
+        f32p = C.POINTER(C.c_float)
+        ptrs = (f32p * max(len(passages), 1))(*[_f32p(p) for p in passages])
+        lens = (C.c_size_t * max(len(passages), 1))(*[p.size for p in passages])
+        pp, pc, n_pairs = self._pairs(len(passages), len(candidates), pair_passage, pair_candidate)
+        ptr = C.c_void_p()
+        self._check(lib().afsim_sweep_prepare(self._h, ptrs, lens, len(passages), float(sample_rate), candidates,
+                                              len(candidates), _u32p(pp), _u32p(pc), n_pairs, 1 if want_audio else 0,
+                                              C.byref(ptr)))
+        n_pass = max(len(passages), 1)
+        pair_len = [passages[int(pp[i]) if pp is not None else i % n_pass].size for i in range(n_pairs)]
+        return Sweep(self, ptr.value, n_pairs, pair_len)
+
+    def prepare_synthetic_sweep(self, kind: int, n_passages: int, passage_len: int, sample_rate, candidates,
+                                pair_passage=None, pair_candidate=None, want_audio: bool = False) -> Sweep:
+        pp, pc, n_pairs = self._pairs(n_passages, len(candidates), pair_passage, pair_candidate)
+        ptr = C.c_void_p()
+        self._check(lib().afsim_sweep_prepare_synthetic(self._h, int(kind), n_passages, passage_len, float(sample_rate),
+                                                        candidates, len(candidates), _u32p(pp), _u32p(pc), n_pairs,
+                                                        1 if want_audio else 0, C.byref(ptr)))
+        return Sweep(self, ptr.value, n_pairs, [passage_len] * n_pairs)
+
+
+def exported_symbols_present() -> list[str]:
+    """Names from include/afsim.h that libafsim.so does not export (empty when complete)."""
+    L = lib()
+    return [name for name in EXPORTS if not hasattr(L, name)]
+
+
+def library_loaded_path() -> str:
+    lib()
+    return os.fspath(LIB_PATH)

@@ -254,6 +254,30 @@ int afsim_sweep_kernel_count(const AfsimSweep* sweep);
 int afsim_sweep_last_render_ms(AfsimHandle* handle, AfsimSweep* sweep, float* out_ms);
 void afsim_sweep_release(AfsimHandle* handle, AfsimSweep* sweep);
 
+/* ---- measurement helpers (bench.py; no reference counterpart) ------------------ */
+
+/* Stage kinds reported by afsim_sweep_profile_stages. */
+typedef enum AfStageKind {
+    AF_STAGE_INPUT = 0,
+    AF_STAGE_INPUT_TRUE_PEAK = 1,
+    AF_STAGE_DEESSER = 2,
+    AF_STAGE_EQ = 3,
+    AF_STAGE_COMPRESSOR = 4,
+    AF_STAGE_LIMITER = 5,
+    AF_STAGE_OUTPUT = 6, /* true-peak limiter + detector + output statistics */
+    AF_STAGE_FINALIZE = 7
+} AfStageKind;
+
+/* Runs the first batch of the sweep once with the stage kernels SERIALISED on the handle's stream
+ * and CUDA events around every launch of the first `max_chunks` chunks (0 = all).  Per stage of the
+ * chain (in chain order; EQ slices are separate entries): out_kind[i] = AfStageKind, out_ms[i] = sum
+ * of its launch durations, out_launches[i] = launches timed.  *out_n = entries written (<= capacity). */
+int afsim_sweep_profile_stages(AfsimHandle* handle, AfsimSweep* sweep, int max_chunks, int capacity,
+                               int* out_kind, float* out_ms, int* out_launches, int* out_n);
+/* Sustained issue rate of this GPU in 1e9 warp-lane instructions per second: kind 0 = dependent
+ * FP64 DMUL+DADD chains (the instruction mix of the unfused biquads), kind 1 = FP32 FFMA chains. */
+int afsim_measure_issue_peak(AfsimHandle* handle, int kind, double* out_giga_instr_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,173 @@
+"""GPU parity: libafsim.so (sm_100a kernels through the C ABI) against the CPU oracle.
+
+Tolerances are the north_star's: rendered samples within 1e-5 relative or -100 dBFS absolute; gain
+reduction / true peak / level metrics within 0.01 dB; counts and decisions exact.  The only
+arithmetic that is not bit-identical to the oracle is the device libm (log10 / exp10 / sqrt are
+IEEE or <= 2 ulp); coefficients, time constants and every IEEE +,-,*,/ match bit for bit.
+"""
+import numpy as np
+import pytest
+
+from audio_forge_b200 import abi
+from oracle import pyoracle
+from tests.cases import CASES, FS, audio_within_tolerance, candidate, candidate_array, metric_mismatches
+from tests.signals import golden_chain_input, speech_like
+
+pytestmark = pytest.mark.gpu
+
+TOL_DB = 0.01
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from audio_forge_b200 import native
+    s = native.Simulator(0)
+    yield s
+    s.close()
+
+
+X = golden_chain_input(blocks=100)  # 48 000 samples = 47 chunks of 1024
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_chain_render_matches_oracle(sim, name):
+    bands, overrides = CASES[name]
+    settings = abi.make_settings(**overrides)
+    m0, a0, _ = pyoracle.chain_render(X, FS, bands, settings, return_audio=True)
+    m1, a1 = sim.chain_render(X, FS, bands, settings, return_audio=True)
+    assert audio_within_tolerance(a0, a1) <= 0.0
+    assert metric_mismatches(m0, m1, tol_db=TOL_DB) == {}
+
+
+def test_eq_only_paths_are_bit_exact(sim):
+    """No transcendental on the signal path -> the EQ render must equal the oracle bit for bit."""
+    for name in ("typed_pass", "typed_worst_40_sections"):
+        bands, _ = CASES[name]
+        st0, a0 = pyoracle.eq_render(X, FS, bands, return_audio=True)
+        st1, a1 = sim.eq_render(X, FS, bands, return_audio=True)
+        assert np.array_equal(a0, a1), name
+        for key in ("input_sample_peak", "output_sample_peak", "input_true_peak", "output_true_peak", "input_rms",
+                    "output_rms", "sample_count", "non_finite_output"):
+            assert getattr(st0, key) == getattr(st1, key), (name, key)
+        assert abs(st0.max_response_db - st1.max_response_db) < 1e-9
+
+
+def test_default_eq_is_bit_exact_passthrough(sim):
+    """test_eq_filter_types.py:123-142: default (flat) typed bands leave the samples untouched."""
+    x = speech_like(48000, seed=11)
+    st, out = sim.eq_render(x, FS, abi.default_bands(), return_audio=True)
+    assert np.array_equal(out, x)
+    assert st.output_sample_peak == st.input_sample_peak
+
+
+def test_sweep_mixed_structures_and_lengths(sim):
+    """One call, several batches: candidates with different stage sets x passages of different lengths."""
+    passages = [speech_like(20000 + 777 * k, seed=k, level=0.5 + 0.1 * k) for k in range(3)]
+    names = ["default_legacy", "golden_like", "typed_pass", "no_limiter", "dc_hp", "long_lookahead"]
+    cand_list = [candidate(CASES[n][0], **CASES[n][1]) for n in names]
+    cands = candidate_array(cand_list)
+    metrics, audio = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    for c in range(len(cand_list)):
+        for p in range(len(passages)):
+            i = c * len(passages) + p
+            m0, a0, _ = pyoracle.chain_render(passages[p], FS, cand_list[c].bands, cand_list[c].settings, return_audio=True)
+            assert audio_within_tolerance(a0, audio[i]) <= 0.0, (names[c], p)
+            assert metric_mismatches(m0, metrics[i], tol_db=TOL_DB) == {}, (names[c], p)
+
+
+def test_sweep_many_streams_against_threaded_oracle(sim):
+    """A 24 x 4 compressor grid (ragged last warp: 96 streams + explicit pair lists)."""
+    passages = [speech_like(14400, seed=20 + k, level=0.8) for k in range(4)]
+    bands, overrides = CASES["legacy_eq"]
+    grid = [(thr, ratio, att) for thr in (-40.0, -30.0, -20.0, -12.0) for ratio in (1.5, 3.0, 6.0) for att in (3.0, 25.0)]
+    cand_list = [candidate(bands, **dict(overrides, compressor_threshold_db=t, compressor_ratio=r, compressor_attack_ms=a,
+                                         compressor_adaptive_release=(i % 2 == 0)))
+                 for i, (t, r, a) in enumerate(grid)]
+    cands = candidate_array(cand_list)
+    pp = np.array([p for c in range(len(grid)) for p in range(4)][:-1], dtype=np.uint32)  # 95 pairs
+    pc = np.array([c for c in range(len(grid)) for p in range(4)][:-1], dtype=np.uint32)
+    got, _ = sim.chain_sweep(passages, FS, cands, pp, pc)
+    want = pyoracle.chain_sweep(passages, FS, cands, pp, pc, n_threads=8)
+    for i in range(pp.size):
+        assert metric_mismatches(want[i], got[i], tol_db=TOL_DB) == {}, i
+
+
+def test_resident_sweep_relaunch_is_deterministic(sim):
+    bands, overrides = CASES["golden_like"]
+    cands = candidate_array([candidate(bands, **overrides)])
+    sweep = sim.prepare_sweep([X], FS, cands)
+    sweep.launch()
+    first = abi.metrics_to_dict(sweep.collect()[0])
+    sweep.launch()
+    second = abi.metrics_to_dict(sweep.collect()[0])
+    assert sweep.kernel_count > 0 and sweep.render_ms() > 0.0
+    sweep.release()
+    first.pop("candidate_runtime_ms"), second.pop("candidate_runtime_ms")
+    assert first == second
+
+
+@pytest.mark.parametrize("n", [0, 1, 71, 72, 73, 960, 961])
+def test_tiny_and_empty_inputs(sim, n):
+    x = speech_like(2000, seed=5, level=0.9)[:n].copy()
+    bands, overrides = CASES["golden_like"]
+    settings = abi.make_settings(**overrides)
+    m0, a0, _ = pyoracle.chain_render(x, FS, bands, settings, return_audio=True)
+    m1, a1 = sim.chain_render(x, FS, bands, settings, return_audio=True)
+    assert audio_within_tolerance(a0, a1) <= 0.0
+    assert metric_mismatches(m0, m1, tol_db=TOL_DB) == {}
+
+
+def test_non_finite_input_is_zeroed(sim):
+    x = speech_like(6000, seed=2)
+    x[100], x[2000], x[2001] = np.nan, np.inf, -np.inf
+    bands, overrides = CASES["default_legacy"]
+    settings = abi.make_settings(**overrides)
+    m0, a0, _ = pyoracle.chain_render(x, FS, bands, settings, return_audio=True)
+    m1, a1 = sim.chain_render(x, FS, bands, settings, return_audio=True)
+    assert audio_within_tolerance(a0, a1) <= 0.0
+    assert metric_mismatches(m0, m1, tol_db=TOL_DB) == {}
+
+
+def test_eq_response_matches_oracle_and_reference_pins(sim):
+    freqs = np.geomspace(20.0, 20000.0, 100)
+    for name, typed in (("typed_pass", True), ("typed_worst_40_sections", True), ("legacy_eq", False)):
+        bands, _ = CASES[name]
+        want = pyoracle.eq_response(freqs, bands, FS, typed)
+        got = sim.eq_response(freqs, bands, FS, typed)[0]
+        assert np.max(np.abs(want - got)) < 1e-8, name
+    # Butterworth cascades are -3.0103 dB at the cutoff for every slope (dsp/eq.rs:699-715, +-1e-8)
+    for slope in (12, 24, 36, 48):
+        bands = abi.typed_bands([("high_pass", 1000.0, 0, 0.7, slope, True)] +
+                                [("bell", f, 0, 1.41, 12, False) for f in abi.DEFAULT_FREQUENCIES[1:]])
+        got = sim.eq_response([1000.0], bands, FS, True)[0, 0]
+        assert abs(got - (-3.010299956639812)) < 1e-8, slope
+
+
+def test_validation_errors_mirror_the_reference(sim):
+    bad = abi.typed_bands([("bell", 10.0, 0, 1, 12, True)] + [("bell", f, 0, 1.41, 12, True) for f in abi.DEFAULT_FREQUENCIES[1:]])
+    with pytest.raises(ValueError, match=r"Band 0: frequency 10 Hz out of range \[20, 23999\]"):
+        sim.eq_response([100.0], bad, FS, True)
+    with pytest.raises(ValueError, match="sample_rate must be positive and finite"):
+        sim.chain_render(X[:100], float("nan"), abi.default_bands(), abi.make_settings())
+    x = X[:100].copy()
+    x[3] = np.nan
+    with pytest.raises(ValueError, match="audio must contain only finite samples"):
+        sim.eq_render(x, FS, abi.default_bands())
+
+
+def test_reference_python_door(sim):
+    """The reference-facing module: same names / dict shape as mic_eq_core (python_api.rs:649-713)."""
+    from audio_forge_b200 import mic_eq_core
+    x = (0.62 * np.sin(2 * np.pi * 5000.0 * np.arange(24000) / FS)).astype(np.float32)  # test_auto_eq.py:968-1001
+    bands = [(f, 0.0, 1.41) for f in abi.DEFAULT_FREQUENCIES]
+    bands[6] = (5000.0, 9.0, 1.41)
+    result = mic_eq_core.simulate_auto_eq_chain(x, FS, bands, {"compressor_enabled": False, "return_output_audio": True})
+    m0, a0, _ = pyoracle.chain_render(x, FS, abi.legacy_bands(bands), abi.make_settings(compressor_enabled=False),
+                                      return_audio=True)
+    want = abi.metrics_to_dict(m0)
+    assert set(want) | {"output_audio"} == set(result)
+    assert audio_within_tolerance(a0, np.asarray(result["output_audio"], dtype=np.float32)) <= 0.0
+    # headroom.py:278-289 decision inputs
+    for key in ("pre_limiter_true_peak_headroom_db", "limiter_gain_reduction_db", "true_peak_limiter_gain_reduction_db"):
+        assert abs(want[key] - result[key]) <= TOL_DB
+    assert result["limiter_gain_reduction_db"] > 1.0  # +9 dB at 5 kHz on a 0.62 sine engages the limiter

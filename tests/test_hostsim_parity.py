@@ -1,0 +1,90 @@
+"""CPU check of the product's stage-kernel bodies (tests/hostsim) against the oracle.
+
+The hostsim harness compiles audio_forge_b200/csrc/afsim_render.h + afsim_plan.cpp for the host and
+walks the same chunk x stage schedule as the CUDA launcher.  With the host libm on both sides the
+result must be BIT-EXACT with the oracle (audio, per-block rows and every metric), for any chunk
+size / ring depth / EQ slice width.  This pins the planner, the state parking, the ring addressing,
+the van Herk limiter window and the finalize reduction without a GPU.
+"""
+import numpy as np
+import pytest
+
+from audio_forge_b200 import abi
+from oracle import pyoracle
+from tests import hostsim
+from tests.cases import CASES, FS, candidate, candidate_array, metric_mismatches
+from tests.signals import golden_chain_input, speech_like
+
+X = golden_chain_input(blocks=60)  # 28 800 samples, the reference golden test's signal
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("schedule", [(1024, 2, 5), (264, 3, 10), (40000, 2, 5)])
+def test_stage_bodies_bit_exact_with_oracle(name, schedule):
+    bands, overrides = CASES[name]
+    settings = abi.make_settings(**overrides)
+    m0, a0, r0 = pyoracle.chain_render(X, FS, bands, settings, return_audio=True, return_rows=True)
+    chunk, slots, eq_k = schedule
+    cands = candidate_array([candidate(bands, **overrides)])
+    m1, a1, r1 = hostsim.chain_sweep([X], FS, cands, [0], [0], chunk=chunk, slots=slots, eq_k=eq_k, want_audio=True,
+                                     want_rows=True)
+    assert np.array_equal(a0, a1[0])
+    assert np.array_equal(r0, r1[:, :, 0].T)
+    assert metric_mismatches(m0, m1[0]) == {}
+
+
+def test_multi_stream_batch_and_ragged_tail():
+    """Several candidates x passages in one batch; length not a multiple of chunk, block or FIR group."""
+    n = 9 * 960 + 437
+    passages = [speech_like(n, seed=s, level=0.7) for s in range(3)]
+    bands, overrides = CASES["legacy_eq"]
+    cand_list = [candidate(bands, **dict(overrides, compressor_threshold_db=thr, compressor_ratio=ratio))
+                 for thr in (-30.0, -18.0) for ratio in (2.0, 6.0)]
+    cands = candidate_array(cand_list)
+    pp = np.array([p for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
+    pc = np.array([c for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
+    got, audio, _ = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=512, slots=2, want_audio=True)
+    for i in range(pp.size):
+        m0, a0, _ = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings,
+                                          return_audio=True)
+        assert np.array_equal(a0, audio[i]), i
+        assert metric_mismatches(m0, got[i]) == {}, i
+
+
+@pytest.mark.parametrize("n", [1, 7, 71, 72, 73, 959, 960, 961])
+def test_tiny_inputs(n):
+    """Shorter than the crossfade / one analysis block / the limiter latency."""
+    x = speech_like(2000, seed=5, level=0.9)[:n].copy()
+    for name in ("legacy_eq", "golden_like"):
+        bands, overrides = CASES[name]
+        m0, a0, _ = pyoracle.chain_render(x, FS, bands, abi.make_settings(**overrides), return_audio=True)
+        m1, a1, _ = hostsim.chain_sweep([x], FS, candidate_array([candidate(bands, **overrides)]), [0], [0],
+                                        want_audio=True)
+        assert np.array_equal(a0, a1[0])
+        assert metric_mismatches(m0, m1[0]) == {}
+
+
+def test_non_finite_input_is_zeroed():
+    x = speech_like(4000, seed=2)
+    x[100] = np.nan
+    x[2000] = np.inf
+    x[2001] = -np.inf
+    bands, overrides = CASES["default_legacy"]
+    m0, a0, _ = pyoracle.chain_render(x, FS, bands, abi.make_settings(**overrides), return_audio=True)
+    m1, a1, _ = hostsim.chain_sweep([x], FS, candidate_array([candidate(bands, **overrides)]), [0], [0], want_audio=True)
+    assert np.array_equal(a0, a1[0])
+    assert metric_mismatches(m0, m1[0]) == {}
+
+
+def test_other_sample_rates():
+    for fs in (44100.0, 96000.0, 16000.0):
+        x = speech_like(int(fs * 0.4), seed=3, fs=fs, level=0.8)
+        bands = abi.legacy_bands([(f if f < fs / 2 - 100 else fs / 2 - 500, g, q) for f, g, q in
+                                  [(80, 3, 1), (160, -2, 1.2), (320, 1, 1.41), (640, -4, 2), (1280, 2, 0.7), (2500, 5, 1),
+                                   (5000, -6, 3), (7000, 4, 1), (7400, 2, 1), (7600, -3, 0.8)]])
+        overrides = dict(compressor_makeup_gain_db=8.0, deesser_enabled=fs > 30000.0)
+        m0, a0, _ = pyoracle.chain_render(x, fs, bands, abi.make_settings(**overrides), return_audio=True)
+        m1, a1, _ = hostsim.chain_sweep([x], fs, candidate_array([candidate(bands, **overrides)]), [0], [0],
+                                        want_audio=True)
+        assert np.array_equal(a0, a1[0]), fs
+        assert metric_mismatches(m0, m1[0]) == {}, fs
