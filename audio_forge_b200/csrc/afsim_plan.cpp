@@ -40,10 +40,15 @@ int fail(std::string* error, int status, const std::string& message) {
     return status;
 }
 
-std::string fmt_num(double v) {  // Rust `{}` for f64: shortest form that round-trips
-    char buf[64];
-    for (int prec = 1; prec <= 17; ++prec) {
-        std::snprintf(buf, sizeof buf, "%.*g", prec, v);
+std::string fmt_num(double v) {
+    // Rust `{}` for f64: the shortest digits that round-trip, always in positional notation.
+    char buf[400];
+    if (!std::isfinite(v)) {
+        std::snprintf(buf, sizeof buf, "%s", std::isnan(v) ? "NaN" : (v > 0 ? "inf" : "-inf"));
+        return buf;
+    }
+    for (int decimals = 0; decimals <= 340; ++decimals) {
+        std::snprintf(buf, sizeof buf, "%.*f", decimals, v);
         if (std::strtod(buf, nullptr) == v) break;
     }
     return buf;

@@ -289,11 +289,14 @@ inline bool supported_slope(uint8_t s) { return s == 12 || s == 24 || s == 36 ||
 
 // eq.rs:154-201 validation; returns "" when valid, else the reference's message.
 inline std::string fmt_num(double v) {
-    // Rust `{}` for f64 prints the shortest round-trip form; integers print without ".0"? No:
-    // Rust prints 20.0 as "20" for `{}`.  Keep it simple: shortest %g-like form.
-    char buf[64];
-    for (int prec = 1; prec <= 17; ++prec) {
-        std::snprintf(buf, sizeof buf, "%.*g", prec, v);
+    // Rust `{}` for f64: the shortest digits that round-trip, always in positional notation.
+    char buf[400];
+    if (!std::isfinite(v)) {
+        std::snprintf(buf, sizeof buf, "%s", std::isnan(v) ? "NaN" : (v > 0 ? "inf" : "-inf"));
+        return buf;
+    }
+    for (int decimals = 0; decimals <= 340; ++decimals) {
+        std::snprintf(buf, sizeof buf, "%.*f", decimals, v);
         if (std::strtod(buf, nullptr) == v) break;
     }
     return buf;
