@@ -24,7 +24,7 @@ using namespace afsim;
 
 namespace {
 thread_local std::string g_create_error;
-constexpr int kMaxStages = 16;
+constexpr int kMaxStages = 32;
 }  // namespace
 
 struct AfsimHandle {
@@ -54,10 +54,10 @@ struct DeviceBuffers {  // frees what it allocated
     }
 };
 
-enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT };
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT };
 struct StageDesc {
     StageKind kind;
-    int arg;  // SK_EQ: first section
+    int arg;  // SK_EQ: first section; SK_SPLIT: SplitOp
 };
 
 struct Batch {
@@ -246,7 +246,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         batch->chunk = chunk;
         const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
         // ring slots = chunks in flight + 1; few-stream batches need the stage wavefront to fill the GPU
-        int slots = S <= 16384 ? 12 : (S <= 65536 ? 4 : 2);
+        // (a split batch runs up to ~24 stage kernels per chunk: one ring slot per stage keeps all of them busy)
+        int slots = S <= 16384 ? 26 : (S <= 65536 ? 4 : 2);
         slots = env_int("AFSIM_SLOTS", slots);
         slots = std::max(2, std::min(slots, std::max(2, n_chunks + 1)));
         batch->slots = slots;
@@ -281,11 +282,25 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         a.audio_off = d_aoff;
 
         const size_t sp = static_cast<size_t>(S_pad);
-        AF_CUDA(h, sweep->mem.alloc(&a.buf_a, static_cast<size_t>(a.ring_rows) * sp));
+        // Few-stream batches cannot fill the GPU with one thread per stream: cut the stages into serial
+        // recurrences + parallel maps (afsim_split.h).  AFSIM_SPLIT: 1 = never, 2 = always, else by size.
+        const int split_mode = env_int("AFSIM_SPLIT", 0);
+        const bool split = split_mode == 2 || (split_mode != 1 && S <= 16384);
+        const size_t ring_elems = static_cast<size_t>(a.ring_rows) * sp;
+        AF_CUDA(h, sweep->mem.alloc(&a.buf_a, ring_elems));
         if (a.structure & ST_LIMITER) {
-            AF_CUDA(h, sweep->mem.alloc(&a.buf_b, static_cast<size_t>(a.ring_rows) * sp));
-            AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
+            AF_CUDA(h, sweep->mem.alloc(&a.buf_b, ring_elems));
             AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
+            if (split) {
+                AF_CUDA(h, sweep->mem.alloc(&a.buf_c, ring_elems));
+                AF_CUDA(h, sweep->mem.alloc(&a.buf_p, ring_elems));
+            } else {
+                AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
+            }
+        }
+        if (split && (a.structure & (ST_LIMITER | ST_COMPRESSOR))) {
+            const int n_w = (a.structure & ST_COMPRESSOR) ? 4 : 1;
+            for (int k = 0; k < n_w; ++k) AF_CUDA(h, sweep->mem.alloc(&a.w[k], ring_elems));
         }
         AF_CUDA(h, sweep->mem.alloc(&a.st_input, kStateInput * sp));
         AF_CUDA(h, sweep->mem.alloc(&a.st_tp, kStateTruePeak * sp));
@@ -321,9 +336,20 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             if (a.structure & ST_DEESSER) batch->stages.push_back({SK_DEESSER, 0});
             push_eq();
         }
-        if (a.structure & ST_COMPRESSOR) batch->stages.push_back({SK_COMPRESSOR, 0});
-        if (a.structure & ST_LIMITER) batch->stages.push_back({SK_LIMITER, 0});
-        batch->stages.push_back({SK_OUTPUT, 0});
+        if (a.structure & ST_COMPRESSOR) {
+            if (split)
+                for (int op : {SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6})
+                    batch->stages.push_back({SK_SPLIT, op});
+            else
+                batch->stages.push_back({SK_COMPRESSOR, 0});
+        }
+        if (a.structure & ST_LIMITER) {
+            if (split)
+                for (int op : {SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT}) batch->stages.push_back({SK_SPLIT, op});
+            else
+                batch->stages.push_back({SK_LIMITER, 0});
+        }
+        if (!(split && (a.structure & ST_LIMITER))) batch->stages.push_back({SK_OUTPUT, 0});
         if (static_cast<int>(batch->stages.size()) > kMaxStages) return set_error(h, AFSIM_UNSUPPORTED, "too many stages");
         batch->events.resize(batch->stages.size() * static_cast<size_t>(slots));
         for (cudaEvent_t& e : batch->events) AF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -345,6 +371,7 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
         case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
         case SK_LIMITER: return launch_limiter(b.args, ck, stream);
+        case SK_SPLIT: return launch_split(static_cast<SplitOp>(st.arg), b.args, ck, stream);
         default: return launch_output(b.args, ck, (b.args.structure & ST_LIMITER) != 0, stream);
     }
 }
@@ -629,7 +656,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
             cudaEventElapsedTime(&ms, ev[e0], ev[e0 + 1]);
             total += ms;
         }
-        out_kind[i] = kind_map[b.stages[i].kind];
+        out_kind[i] = b.stages[i].kind == SK_SPLIT ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
         out_ms[i] = static_cast<float>(total);
         out_launches[i] = timed_chunks;
     }

@@ -67,6 +67,32 @@ __global__ void __launch_bounds__(128) k_input_true_peak(BatchArgs a, ChunkArgs 
     body_input_true_peak(a, ck, s, c_fir);
 }
 
+// ---- split (R/M) path: serial recurrences, one thread per stream --------------------------------------------
+#define AF_R_KERNEL(name, body)                                              \
+    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) { \
+        AF_STREAM_INDEX();                                                   \
+        body(a, ck, s);                                                      \
+    }
+AF_R_KERNEL(k_comp_r1, body_comp_r1)
+AF_R_KERNEL(k_comp_r3, body_comp_r3)
+AF_R_KERNEL(k_comp_r5, body_comp_r5)
+AF_R_KERNEL(k_lim_r, body_lim_r)
+AF_R_KERNEL(k_tp_r, body_tp_r)
+
+// ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
+#define AF_M_KERNEL(name, call)                                              \
+    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) { \
+        AF_STREAM_INDEX();                                                   \
+        const int g = (int)blockIdx.y;                                       \
+        call;                                                                \
+    }
+AF_M_KERNEL(k_comp_m2, body_comp_m2(a, ck, s, g))
+AF_M_KERNEL(k_comp_m4, body_comp_m4(a, ck, s, g))
+AF_M_KERNEL(k_comp_m6, body_comp_m6(a, ck, s, g))
+AF_M_KERNEL(k_lim_m, body_lim_m(a, ck, s, g))
+AF_M_KERNEL(k_tp_fir_in, body_tp_fir_in(a, ck, s, g, c_fir))
+AF_M_KERNEL(k_tp_fir_out, body_tp_fir_out(a, ck, s, g, c_fir))
+
 extern __shared__ float fin_smem[];
 
 // One thread block per stream: sorts and percentiles of the per-block rows.
@@ -229,6 +255,28 @@ cudaError_t launch_output(const BatchArgs& a, const ChunkArgs& ck, bool limiter,
 cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int b = pick_block(a);
     k_input_true_peak<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
+    const int rb = pick_block(a);
+    const dim3 rgrid = stream_grid(a, rb);
+    const int mb = a.n_streams >= 128 ? 128 : 32;
+    const dim3 mgrid((unsigned)((a.n_streams + mb - 1) / mb), (unsigned)((ck.len + kGroup - 1) / kGroup));
+    switch (op) {
+        case SP_COMP_R1: k_comp_r1<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_M2: k_comp_m2<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_COMP_R3: k_comp_r3<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_M4: k_comp_m4<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_COMP_R5: k_comp_r5<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_M6: k_comp_m6<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_LIM_M: k_lim_m<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_LIM_R: k_lim_r<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_TP_FIR_IN: k_tp_fir_in<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_TP_R: k_tp_r<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_TP_FIR_OUT: k_tp_fir_out<<<mgrid, mb, 0, st>>>(a, ck); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

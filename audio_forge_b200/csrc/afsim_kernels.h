@@ -19,6 +19,12 @@ cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStrea
 cudaError_t launch_limiter(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_output(const BatchArgs& a, const ChunkArgs& ck, bool limiter, cudaStream_t st);
 cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+// split (R/M) path, afsim_split.h
+enum SplitOp {
+    SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6,
+    SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT
+};
+cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);
 size_t finalize_workspace_bytes(int n_rows, int n_pad);
 cudaError_t launch_eq_response(const double* coeffs, const int* n_sections, const double* freqs, int n_freqs,

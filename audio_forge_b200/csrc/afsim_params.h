@@ -125,7 +125,11 @@ struct BatchArgs {
     float* audio;                 // output audio pool, or nullptr
     float* buf_a;                 // [ring_rows][S_pad] signal up to the sample limiter's input
     float* buf_b;                 // [ring_rows][S_pad] signal after the sample limiter
-    float* lim_sfx;               // [lookahead + 1][S_pad] suffix maxima of the previous limiter block
+    float* lim_sfx;               // [lookahead + 1][S_pad] suffix maxima of the previous limiter block (fused limiter)
+    // split (R/M) path, afsim_split.h: hand-off rings shared by the serial and the map kernels
+    double* w[4];                 // [ring_rows][S_pad] f64 each
+    float* buf_c;                 // [ring_rows][S_pad] true-peak limiter output
+    float* buf_p;                 // [ring_rows][S_pad] input true peaks
     double* st_input;             // [kStateInput][S_pad]
     double* st_deesser;           // [kStateDeEsser][S_pad]
     double* st_eq;                // [kStateEqPerSection * kMaxSections][S_pad]

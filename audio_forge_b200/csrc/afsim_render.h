@@ -8,7 +8,7 @@
 // Reference citations are relative to rust-core/src/.
 #pragma once
 #include "../../include/afsim.h"
-#include "afsim_stages.h"
+#include "afsim_split.h"
 
 namespace afsim {
 
@@ -223,6 +223,174 @@ AF_HD void body_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, int s, 
         StateIO<true> sio{table, stride};
         det.sync(sio);
     }
+}
+
+// =====================================================================================================================
+// split (R/M) path: see afsim_split.h.  R bodies: one call per stream and chunk; M bodies: one call per
+// (stream, group of kGroup samples).
+// =====================================================================================================================
+AF_HD bool group_span(const ChunkArgs& ck, int g, int* t0, int* valid) {
+    *t0 = g * kGroup;
+    *valid = ck.len - *t0 < kGroup ? ck.len - *t0 : kGroup;
+    return *valid > 0;
+}
+template <typename T>
+AF_HD T* col_at(T* ring, const BatchArgs& a, const ChunkArgs& ck, int s, int t0 = 0) {
+    return ring + (size_t)(ck.row0 + t0) * (size_t)a.stride + s;
+}
+
+AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    if (ck.n0 != 0) {
+        StateIO<false> io{a.st_comp + s, stride};
+        st.sync_r1(io);
+    }
+    st.run_r1(col_at(a.buf_a, a, ck, s), col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s),
+              col_at(a.w[3], a, ck, s), stride, ck.len);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{a.st_comp + s, stride};
+        st.sync_r1(io);
+    }
+}
+AF_HD void body_comp_m2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    st.map_m2(col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
+              col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
+}
+AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    double* table = a.st_comp + (size_t)5 * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync_r3(io);
+    }
+    st.run_r3(col_at(a.w[0], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride, ck.len);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync_r3(io);
+    }
+}
+AF_HD void body_comp_m4(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    st.map_m4(col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
+}
+AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    double* table = a.st_comp + (size_t)7 * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync_r5(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    st.run_r5(col_at(a.w[1], a, ck, s), stride, ck.n0, ck.len, clk, a.rows + (size_t)2 * a.n_rows * stride + s);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync_r5(io);
+    }
+}
+AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    CompSplit st;
+    st.init(stream_params(a, s));
+    st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);
+}
+
+AF_HD void body_lim_m(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    limiter_targets(a.buf_a + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, a.lookahead,
+                    stream_params(a, s).l_ceil, col_at(a.w[0], a, ck, s, t0));
+}
+AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    const CandidateParams& p = stream_params(a, s);
+    LimiterR st;
+    if (ck.n0 == 0) {
+        st.init();
+    } else {
+        StateIO<false> io{a.st_lim + s, stride};
+        st.sync(io);
+    }
+    st.run(col_at(a.w[0], a, ck, s), a.buf_a + s, col_at(a.buf_b, a, ck, s), stride, a.ring_rows, ck.row0, ck.n0, ck.len,
+           a.lookahead, p.l_ceil, p.l_release);
+    if (ck.n0 + ck.len >= a.n_samples) {
+        a.accum[s].limiter_gr_db = st.peak_reduction_db();
+    } else {
+        StateIO<true> io{a.st_lim + s, stride};
+        st.sync(io);
+    }
+}
+
+AF_HD void atomic_max_nonneg(float* addr, float v) {
+    if (!(v == v)) return;  // f32::max ignores NaN
+#if defined(__CUDA_ARCH__)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+#else
+    if (v > *addr) *addr = v;
+#endif
+}
+
+// input true peaks of the true-peak limiter: buf_b -> buf_p
+AF_HD void body_tp_fir_in(const BatchArgs& a, const ChunkArgs& ck, int s, int g, const FirTable& fir) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    float pk[kFirChunk];
+    fir_group_peaks(a.buf_b + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, fir, pk);
+    store_tile(col_at(a.buf_p, a, ck, s, t0), (size_t)a.stride, valid, pk);
+}
+AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    const CandidateParams& p = stream_params(a, s);
+    TpR st;
+    if (ck.n0 == 0) {
+        st.init();
+    } else {
+        StateIO<false> io{a.st_tp + s, stride};
+        st.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    float* audio = a.audio ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
+    st.run(col_at(a.buf_p, a, ck, s), a.buf_b + s, col_at(a.buf_c, a, ck, s), audio, stride, a.ring_rows, ck.row0, ck.n0,
+           ck.len, p.tp_ceil, p.tp_release, clk, a.rows + (size_t)1 * a.n_rows * stride + s);
+    if (ck.n0 + ck.len >= a.n_samples) {
+        StreamAccum& acc = a.accum[s];
+        acc.sum_out = st.sum_out;
+        acc.peak_out = st.peak_out;
+        acc.non_finite = st.non_finite ? 1u : 0u;
+        acc.peak_pre_tp = st.peak_pre;
+        acc.tp_gr_db = st.peak_reduction_db();
+        acc.events = st.events;
+    } else {
+        StateIO<true> io{a.st_tp + s, stride};
+        st.sync(io);
+    }
+}
+// detector over the true-peak limiter's output: buf_c -> accum.peak_out_tp (order-independent maximum)
+AF_HD void body_tp_fir_out(const BatchArgs& a, const ChunkArgs& ck, int s, int g, const FirTable& fir) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid)) return;
+    float pk[kFirChunk];
+    fir_group_peaks(a.buf_c + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, fir, pk);
+    float m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kFirChunk; ++j)
+        if (j < valid) m = fmaxf(m, pk[j]);
+    atomic_max_nonneg(&a.accum[s].peak_out_tp, m);
 }
 
 // ---- de-esser constant table: CandidateParams::de -> [DE_FIELDS][S_pad] -------------------------------------------

@@ -1,0 +1,420 @@
+// afsim_split.h -- the chain stages split into thin serial recurrences (R) and parallel maps (M).
+//
+// Few-stream sweeps (4096 candidates x one 30 s passage is only 128 warps) cannot fill a B200 with
+// one thread per stream: a warp that walks a recurrence is latency bound at ~0.25 instructions per
+// cycle.  But almost all of the chain's arithmetic is feed-forward: the transcendental maps of the
+// compressor (log10 / exp10 / sqrt), the limiter's window maximum and target gain, and both 4x
+// polyphase true-peak FIRs depend on the recurrences only through a few per-sample values.  So every
+// stage is cut along that line:
+//     R kernels   one thread per stream walks the chunk (short dependent chain, a few flops per sample)
+//     M kernels   one thread per (stream, 8 samples): fully parallel over time, fills every SM
+// The hand-off arrays are time-major rings ([row][stream], f64 `w0..w3` and f32 `buf_*`), so both
+// kinds of kernel access them coalesced.  Per sample the operations and their order are exactly those
+// of the fused stage in afsim_stages.h (and of the reference), so results are bit-identical to the
+// fused path; tests/hostsim checks that on the CPU.
+//
+// Reference citations are relative to rust-core/src/.
+#pragma once
+#include "afsim_stages.h"
+
+namespace afsim {
+
+constexpr int kGroup = 8;  // samples per map thread; chunks are multiples of it
+
+AF_HD int ring_row(int row0, int t, int ring_rows) {
+    int r = row0 + t;
+    if (r < 0) r += ring_rows;
+    return r;
+}
+
+template <typename T, int U>
+AF_HD void load_tile(const T* col, size_t stride, int valid, T (&v)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = u < valid ? col[(size_t)u * stride] : (T)0;
+}
+template <typename T, int U>
+AF_HD void store_tile(T* col, size_t stride, int valid, const T (&v)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (u < valid) col[(size_t)u * stride] = v[u];
+}
+
+// ---- compressor (dsp/compressor.rs:725-774) ------------------------------------------------------------------
+// Constants come from CompressorStage::init; the recurrence state of the three serial passes lives in
+// the same slots of the compressor state table as the fused stage uses.
+struct CompSplit : CompressorStage {
+    template <class IO>
+    AF_HD void sync_r1(IO& io) {
+        io.f64(prev_in);
+        io.f64(prev_out);
+        io.f64(low_sq);
+        io.f64(voiced_sq);
+        io.f64(presence_sq);
+    }
+    template <class IO>
+    AF_HD void sync_r3(IO& io) {  // table offset 5
+        io.f64(peak_env);
+        io.f64(rms_env);
+    }
+    template <class IO>
+    AF_HD void sync_r5(IO& io) {  // table offset 7
+        io.f64(gr);
+        io.f64(fast_env);
+        io.f64(slow_env);
+    }
+
+    // R1: sidechain high-pass + band envelopes (:407-450).  x -> w0 = det, w1..w3 = band envelopes^2
+    AF_HD void run_r1(const float* x, double* w0, double* w1, double* w2, double* w3, size_t stride, int len) {
+        constexpr int U = kGroup;
+        for (int t0 = 0; t0 < len; t0 += U) {
+            const int valid = len - t0 < U ? len - t0 : U;
+            float xin[U];
+            load_tile(x + (size_t)t0 * stride, stride, valid, xin);
+            double det[U], lsq[U], vsq[U], psq[U];
+            if (sidechain) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (u < valid) {
+                        const double xv = (double)xin[u];
+                        const double d = sc_c * (prev_out + xv - prev_in);
+                        prev_in = xv;
+                        prev_out = d;
+                        const double low = xv - d;
+                        const double presence = 0.65 * d + 0.35 * (d - low);
+                        low_sq = band_c * low_sq + one_m_band * low * low;
+                        voiced_sq = band_c * voiced_sq + one_m_band * d * d;
+                        presence_sq = band_c * presence_sq + one_m_band * presence * presence;
+                        det[u] = d;
+                    } else {
+                        det[u] = 0.0;
+                    }
+                    lsq[u] = low_sq;
+                    vsq[u] = voiced_sq;
+                    psq[u] = presence_sq;
+                }
+                store_tile(w1 + (size_t)t0 * stride, stride, valid, lsq);
+                store_tile(w2 + (size_t)t0 * stride, stride, valid, vsq);
+                store_tile(w3 + (size_t)t0 * stride, stride, valid, psq);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) det[u] = (double)xin[u];
+            }
+            store_tile(w0 + (size_t)t0 * stride, stride, valid, det);
+        }
+    }
+
+    // M2: detector weight in dB and instantaneous peak in dB.  w1 <- wdb, w2 <- ipk
+    AF_HD void map_m2(const double* w0, double* w1, double* w2, const double* w3, size_t stride, int valid) const {
+        double det[kGroup], lsq[kGroup], vsq[kGroup], psq[kGroup], wdb[kGroup], ipk[kGroup];
+        load_tile(w0, stride, valid, det);
+        if (sidechain) {
+            load_tile((const double*)w1, stride, valid, lsq);
+            load_tile((const double*)w2, stride, valid, vsq);
+            load_tile(w3, stride, valid, psq);
+        }
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            if (sidechain) {
+                const double low_rms = sqrt(lsq[u]);
+                const double voiced_rms = fmax(sqrt(vsq[u]), 1e-8);
+                const double presence_rms = sqrt(psq[u]);
+                const double plosive = clampd(low_rms / voiced_rms, 0.0, 32.0);
+                const double amount = clampd((plosive - 1.25) / (5.0 - 1.25), 0.0, 1.0);
+                const double penalty = 1.0 - amount * (1.0 - 0.35);
+                const double presence_ratio = clampd(presence_rms / voiced_rms, 0.0, 4.0);
+                const double pw = 1.0 + 0.18 * clampd(presence_ratio - 0.75, 0.0, 1.0);
+                wdb[u] = lin_to_db(clampd(penalty * pw, 0.35, 1.15), 1e-10);
+            } else {
+                wdb[u] = 0.0;
+            }
+            ipk[u] = lin_to_db(fabs(det[u]), 1e-10);
+        }
+        store_tile(w1, stride, valid, wdb);
+        store_tile(w2, stride, valid, ipk);
+    }
+
+    // R3: peak (dB domain) and RMS envelopes.  (w0 det, w2 ipk) -> w2 = peak_env, w3 = rms_env
+    AF_HD void run_r3(const double* w0, double* w2, double* w3, size_t stride, int len) {
+        constexpr int U = kGroup;
+        for (int t0 = 0; t0 < len; t0 += U) {
+            const int valid = len - t0 < U ? len - t0 : U;
+            double det[U], ipk[U], pk[U], rms[U];
+            load_tile(w0 + (size_t)t0 * stride, stride, valid, det);
+            load_tile((const double*)(w2 + (size_t)t0 * stride), stride, valid, ipk);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < valid) {
+                    const bool up = ipk[u] > peak_env;
+                    peak_env = (up ? attack : det_release) * peak_env + (up ? one_m_attack : one_m_det_release) * ipk[u];
+                    rms_env = rms_c * rms_env + one_m_rms * (det[u] * det[u]);
+                }
+                pk[u] = peak_env;
+                rms[u] = rms_env;
+            }
+            store_tile(w2 + (size_t)t0 * stride, stride, valid, pk);
+            store_tile(w3 + (size_t)t0 * stride, stride, valid, rms);
+        }
+    }
+
+    // M4: blended detector (:681-686) + gain computer (:657-678).  (w2 pk, w3 rms, w1 wdb) -> w1 = target GR
+    AF_HD void map_m4(double* w1, const double* w2, const double* w3, size_t stride, int valid) const {
+        double pk[kGroup], rms[kGroup], wdb[kGroup], tgt[kGroup];
+        load_tile(w2, stride, valid, pk);
+        load_tile(w3, stride, valid, rms);
+        load_tile((const double*)w1, stride, valid, wdb);
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            const double rms_db = lin_to_db(sqrt(rms[u]), 1e-10);
+            const double blended = 0.6 * db_to_lin(pk[u]) + 0.4 * db_to_lin(rms_db);
+            tgt[u] = gain_computer(lin_to_db(blended, 1e-10) + wdb[u]);
+        }
+        store_tile(w1, stride, valid, tgt);
+    }
+
+    // R5: gain-reduction smoothing (:468-505), in place on w1; block-end meter rows
+    AF_HD void run_r5(double* w1, size_t stride, int n0, int len, BlockClock clk, float* rows_comp) {
+        constexpr int U = kGroup;
+        for (int t0 = 0; t0 < len; t0 += U) {
+            const int valid = len - t0 < U ? len - t0 : U;
+            double tgt[U], grv[U];
+            load_tile((const double*)(w1 + (size_t)t0 * stride), stride, valid, tgt);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < valid) {
+                    const double target = tgt[u];
+                    if (!adaptive) {
+                        const bool up = target > gr;
+                        gr = (up ? attack : release) * gr + (up ? one_m_attack : one_m_release) * target;
+                    } else {
+                        if (target > gr)
+                            fast_env = attack * gr + one_m_attack * target;
+                        else
+                            fast_env = fast_c * fast_env + one_m_fast * target;
+                        if (target > 3.0)
+                            slow_env = charge_c * slow_env + one_m_charge * target;
+                        else
+                            slow_env *= slow_c;
+                        gr = fmax(fast_env, slow_env);
+                    }
+                    if (clk.at_end(n0 + t0 + u)) {
+                        rows_comp[(size_t)clk.blk * stride] = (float)gr;
+                        clk.advance();
+                    }
+                }
+                grv[u] = gr;
+            }
+            store_tile(w1 + (size_t)t0 * stride, stride, valid, grv);
+        }
+    }
+
+    // M6: apply gain.  (w1 gr, x) -> x
+    AF_HD void map_m6(const double* w1, float* x, size_t stride, int valid) const {
+        double grv[kGroup];
+        float xin[kGroup], y[kGroup];
+        load_tile(w1, stride, valid, grv);
+        load_tile((const float*)x, stride, valid, xin);
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+            const double gain = db_to_lin(-grv[u]) * makeup_lin;
+            y[u] = (float)((double)xin[u] * gain);
+        }
+        store_tile(x, stride, valid, y);
+    }
+};
+
+// ---- lookahead limiter (dsp/limiter.rs:246-284) -----------------------------------------------------------------
+// M: target gain of samples n..n+7 from the sliding maximum of |x| over [n-L, n] (exact: max is order
+// independent).  The 8 windows share [n+7-L, n]; each adds a few samples on the left and on the right.
+AF_HD void limiter_targets(const float* in_ring, size_t stride, int ring_rows, int row0, int t0, int n_first, int valid,
+                           int L, double ceil_lin, double* target_out /* column at t0 */) {
+    constexpr int G = kGroup;
+    float win[G];
+    if (L >= G - 1) {
+        // common part [n+G-1-L, n]
+        float common = 0.0f;
+        for (int m = G - 1 - L; m <= 0; ++m) {
+            if (n_first + m >= 0) common = fmaxf(common, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
+        }
+        // left extensions: window j additionally covers [n+j-L, n+G-2-L]
+        float left[G];
+        float run = 0.0f;
+        left[G - 1] = 0.0f;
+#pragma unroll
+        for (int j = G - 2; j >= 0; --j) {
+            const int m = j - L;
+            if (n_first + m >= 0) run = fmaxf(run, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
+            left[j] = run;
+        }
+        // right extensions: window j additionally covers [n+1, n+j]
+        float right = 0.0f;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (j > 0 && j < valid) right = fmaxf(right, fabsf(in_ring[(size_t)(row0 + t0 + j) * stride]));
+            win[j] = fmaxf(fmaxf(common, left[j]), right);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            float w = 0.0f;
+            if (j < valid) {
+                for (int m = j - L; m <= j; ++m)
+                    if (n_first + m >= 0) w = fmaxf(w, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
+            }
+            win[j] = w;
+        }
+    }
+    double tgt[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const double peak = (double)win[j];
+        tgt[j] = peak > ceil_lin ? ceil_lin / peak : 1.0;
+    }
+    store_tile(target_out, stride, valid, tgt);
+}
+
+struct LimiterR {
+    double g, min_g;
+    AF_HD void init() {
+        g = 1.0;
+        min_g = 1.0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+        io.f64(g);
+        io.f64(min_g);
+    }
+    // target (w0 column at chunk start), delayed input from the ring, output column at chunk start
+    AF_HD void run(const double* target, const float* in_ring, float* out, size_t stride, int ring_rows, int row0, int n0,
+                   int len, int L, double ceil_lin, double rel) {
+        constexpr int U = kGroup;
+        const double one_m_rel = 1.0 - rel;
+        for (int t0 = 0; t0 < len; t0 += U) {
+            const int valid = len - t0 < U ? len - t0 : U;
+            double tgt[U];
+            float delayed[U], y[U];
+            load_tile(target + (size_t)t0 * stride, stride, valid, tgt);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                delayed[u] = (u < valid && n0 + t0 + u >= L) ? in_ring[(size_t)ring_row(row0, t0 + u - L, ring_rows) * stride] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < valid) {
+                    if (tgt[u] < g)
+                        g = tgt[u];
+                    else
+                        g = rel * g + one_m_rel * tgt[u];
+                    min_g = fmin(min_g, g);
+                }
+                y[u] = (float)clampd((double)delayed[u] * g, -ceil_lin, ceil_lin);
+            }
+            store_tile(out + (size_t)t0 * stride, stride, valid, y);
+        }
+    }
+    AF_HD float peak_reduction_db() const { return min_g < 1.0 ? (float)(-lin_to_db(min_g, 1e-10)) : 0.0f; }
+};
+
+// ---- 4x true-peak FIR as a map: peaks of samples n..n+7 of a ring column ------------------------------------------
+template <typename FIR>
+AF_HD void fir_group_peaks(const float* ring, size_t stride, int ring_rows, int row0, int t0, int n_first, int valid,
+                           const FIR& fir, float (&peak)[kFirChunk]) {
+    float win[kFirWin];
+#pragma unroll
+    for (int i = 0; i < kFirWin; ++i) {
+        const int m = i - 31;  // sample n_first + m
+        float v = 0.0f;
+        if (n_first + m >= 0 && m < valid) v = ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride];
+        win[i] = af_finite(v) ? v : 0.0f;  // dsp/true_peak.rs:211,343 sanitise
+    }
+    fir8_peaks(win, fir, peak);
+}
+
+// ---- true-peak limiter gain recurrence + output statistics (dsp/true_peak.rs:337-378, python_api.rs:529-575) -------
+struct TpR {
+    float g, min_g, peak_pre;
+    uint32_t events;
+    bool limited;
+    double sum_out, blk_out;
+    float peak_out;
+    bool non_finite;
+
+    AF_HD void init() {
+        g = 1.0f;
+        min_g = 1.0f;
+        peak_pre = 0.0f;
+        events = 0;
+        limited = false;
+        sum_out = blk_out = 0.0;
+        peak_out = 0.0f;
+        non_finite = false;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+        io.f32(g);
+        io.f32(min_g);
+        io.f32(peak_pre);
+        io.u32(events);
+        io.flag(limited);
+        io.f64(sum_out);
+        io.f64(blk_out);
+        io.f32(peak_out);
+        io.flag(non_finite);
+    }
+    // itp: input true peaks (column at chunk start); in_ring: limiter output ring (the 20-sample delay
+    // reads it); out: column at chunk start; audio: nullable
+    AF_HD void run(const float* itp, const float* in_ring, float* out, float* audio, size_t stride, int ring_rows, int row0,
+                   int n0, int len, float ceil_lin, float rel, BlockClock clk, float* rows_out) {
+        constexpr int U = kGroup;
+        const float one_m_rel = 1.0f - rel;
+        for (int t0 = 0; t0 < len; t0 += U) {
+            const int valid = len - t0 < U ? len - t0 : U;
+            float pk[U], delayed[U], y[U];
+            load_tile(itp + (size_t)t0 * stride, stride, valid, pk);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float v = 0.0f;
+                if (u < valid && n0 + t0 + u >= kTpDelay) v = in_ring[(size_t)ring_row(row0, t0 + u - kTpDelay, ring_rows) * stride];
+                delayed[u] = af_finite(v) ? v : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                y[u] = 0.0f;
+                if (u < valid) {
+                    peak_pre = fmaxf(peak_pre, pk[u]);
+                    const float target = pk[u] > ceil_lin ? clampf((ceil_lin * 0.999f) / pk[u], 0.0f, 1.0f) : 1.0f;
+                    if (target < g) {
+                        g = target;
+                        limited = true;
+                    } else {
+                        g = rel * g + one_m_rel * target;
+                    }
+                    min_g = fminf(min_g, g);
+                    float o = clampf(delayed[u] * g, -ceil_lin, ceil_lin);
+                    if (!af_finite(o)) o = 0.0f;
+                    y[u] = o;
+                    // output statistics (python_api.rs:529-575)
+                    peak_out = fmaxf(peak_out, fabsf(o));
+                    const double sq = (double)o * (double)o;
+                    sum_out += sq;
+                    blk_out += sq;
+                    if (clk.at_end(n0 + t0 + u)) {
+                        events += limited ? 1u : 0u;
+                        limited = false;
+                        const float rms = (float)sqrt(blk_out / (double)clk.block_len(n0 + t0 + u));
+                        rows_out[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                        blk_out = 0.0;
+                        clk.advance();
+                    }
+                }
+            }
+            store_tile(out + (size_t)t0 * stride, stride, valid, y);
+            if (audio) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (u < valid) audio[t0 + u] = y[u];
+            }
+        }
+    }
+    AF_HD float peak_reduction_db() const { return min_g >= 1.0f ? 0.0f : -20.0f * af_log10_f32(fmaxf(min_g, 1e-10f)); }
+};
+
+}  // namespace afsim

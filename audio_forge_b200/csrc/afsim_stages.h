@@ -203,8 +203,7 @@ struct InputStage {
 };
 
 // ---- EQ: K consecutive sections of the cascade (dsp/eq.rs:317-322, dsp/biquad.rs) -------------------------
-// Steady state runs the sections as a software pipeline over time (section j works on sample
-// it-j), so the K section updates of one iteration are independent and overlap in the FP64 pipe.
+constexpr int kEqTile = 8;
 template <int K>
 struct EqStage {
     Bq c[K];
@@ -232,35 +231,53 @@ struct EqStage {
         }
     }
 
-    template <bool GUARD>
-    AF_HD void pipe_step(const Col& io, int it, int len, float (&v)[K + 1]) {
-#pragma unroll
-        for (int j = K - 1; j >= 0; --j) {
-            const int t = it - j;
-            if (!GUARD || (t >= 0 && t < len)) {
-                const float xin = (j == 0) ? io.get(t) : v[j];
-                const float yy = (float)bq_step((double)xin, c[j], z[j][0], z[j][1]);
-                const float y = j < lane_cnt ? yy : xin;
-                if (j == K - 1)
-                    io.set(t, y);
-                else
-                    v[j + 1] = y;
-            }
-        }
-    }
-
-    // samples [t_begin, len) of the chunk
+    // samples [t_begin, len) of the chunk, in register tiles of kEqTile samples: the next tile's
+    // loads are issued before the current tile is computed (the in-place stores would otherwise pin
+    // every load behind them), and the fully unrolled tile x section block of DF2T updates exposes
+    // the (sample, section) wavefront parallelism to the instruction scheduler.
     AF_HD void run(const Col& io_chunk, int t_begin, int len) {
+        constexpr int U = kEqTile;
         const Col io{io_chunk.base + (size_t)t_begin * io_chunk.stride, io_chunk.stride};
         const int m = len - t_begin;
         if (m <= 0) return;
-        float v[K + 1];
+        float nxt[U];
 #pragma unroll
-        for (int j = 0; j <= K; ++j) v[j] = 0.0f;
-        int it = 0;
-        for (; it < K - 1 && it < m + K - 1; ++it) pipe_step<true>(io, it, m, v);
-        for (; it < m; ++it) pipe_step<false>(io, it, m, v);
-        for (; it < m + K - 1; ++it) pipe_step<true>(io, it, m, v);
+        for (int u = 0; u < U; ++u) nxt[u] = u < m ? io.get(u) : 0.0f;
+        for (int t0 = 0; t0 < m; t0 += U) {
+            float x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = nxt[u];
+            if (t0 + U < m) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = t0 + U + u < m ? io.get(t0 + U + u) : 0.0f;
+            }
+            if (t0 + U <= m) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float yy = (float)bq_step((double)x[u], c[j], z[j][0], z[j][1]);
+                        x[u] = j < lane_cnt ? yy : x[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) io.set(t0 + u, x[u]);
+            } else {  // ragged tail: only the real samples may touch the state
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (t0 + u < m) {
+                            const float yy = (float)bq_step((double)x[u], c[j], z[j][0], z[j][1]);
+                            x[u] = j < lane_cnt ? yy : x[u];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (t0 + u < m) io.set(t0 + u, x[u]);
+            }
+        }
     }
 
     // Head of a legacy render (samples n < F of chunk 0): each section runs the constructor's filter

@@ -26,7 +26,9 @@ EXPORTS = (
     "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
     "afsim_sweep_profile_stages", "afsim_measure_issue_peak",
 )
-STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize")
+STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
+               "comp_r1", "comp_m2", "comp_r3", "comp_m4", "comp_r5", "comp_m6", "lim_m", "lim_r", "tp_fir_in", "tp_r",
+               "tp_fir_out")
 
 
 class AfsimError(RuntimeError):

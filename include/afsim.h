@@ -265,7 +265,10 @@ typedef enum AfStageKind {
     AF_STAGE_COMPRESSOR = 4,
     AF_STAGE_LIMITER = 5,
     AF_STAGE_OUTPUT = 6, /* true-peak limiter + detector + output statistics */
-    AF_STAGE_FINALIZE = 7
+    AF_STAGE_FINALIZE = 7,
+    /* split (serial recurrence R / parallel map M) kernels of few-stream batches, in chain order:
+     * compressor R1 M2 R3 M4 R5 M6, limiter M R, true-peak FIR-in R FIR-out */
+    AF_STAGE_SPLIT_BASE = 8
 } AfStageKind;
 
 /* Runs the first batch of the sweep once with the stage kernels SERIALISED on the handle's stream

@@ -29,7 +29,7 @@ def lib() -> C.CDLL:
         L.hostsim_last_error.restype = C.c_char_p
         L.hostsim_chain_sweep.argtypes = [C.POINTER(f32p), C.POINTER(C.c_size_t), C.c_size_t, C.c_double,
                                           C.POINTER(abi.AfCandidate), C.c_size_t, u32p, u32p, C.c_size_t, C.c_int,
-                                          C.c_int, C.c_int, C.POINTER(abi.AfChainMetrics), f32p, f32p]
+                                          C.c_int, C.c_int, C.c_int, C.POINTER(abi.AfChainMetrics), f32p, f32p]
         _lib = L
     return _lib
 
@@ -38,7 +38,7 @@ class HostsimError(ValueError):
     pass
 
 
-def chain_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate, *, chunk=1024, slots=2, eq_k=5,
+def chain_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate, *, chunk=1024, slots=2, eq_k=5, split=0,
                 want_audio=False, want_rows=False):
     """-> (AfChainMetrics array, audio [n_pairs, T] | None, rows [4, n_rows, n_pairs] | None)."""
     passages = [np.ascontiguousarray(p, dtype=np.float32) for p in passages]
@@ -56,7 +56,7 @@ def chain_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate,
     rows = np.zeros((4, n_rows, n_pairs), dtype=np.float32) if want_rows else None
     rc = lib().hostsim_chain_sweep(ptrs, lens, len(passages), float(sample_rate), candidates, len(candidates),
                                    pp.ctypes.data_as(C.POINTER(C.c_uint32)), pc.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                   n_pairs, int(chunk), int(slots), int(eq_k), out,
+                                   n_pairs, int(chunk), int(slots), int(eq_k), int(split), out,
                                    audio.ctypes.data_as(f32p) if audio is not None else None,
                                    rows.ctypes.data_as(f32p) if rows is not None else None)
     if rc != abi.AFSIM_OK:

@@ -33,7 +33,7 @@ const char* hostsim_last_error() { return g_error.c_str(); }
 // schedule to exercise.  out_audio: nullptr or [n_pairs][T].
 int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len, size_t n_passages, double fs,
                         const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
-                        const uint32_t* pair_candidate, size_t n_pairs, int chunk, int slots, int eq_k,
+                        const uint32_t* pair_candidate, size_t n_pairs, int chunk, int slots, int eq_k, int split,
                         AfChainMetrics* out_metrics, float* out_audio, float* out_rows /* [4][n_rows][n_pairs] or null */) {
     g_error.clear();
     std::vector<CandidatePlan> plans(n_candidates);
@@ -95,6 +95,14 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     std::vector<float> lim_sfx(static_cast<size_t>(a.lookahead + 1) * sp), rows(static_cast<size_t>(4) * std::max(a.n_rows, 1) * sp, 0.0f);
     std::vector<double> st_input(kStateInput * sp), st_de(kStateDeEsser * sp), st_eq(kStateEqPerSection * kMaxSections * sp),
         st_comp(kStateCompressor * sp), st_lim(kStateLimiter * sp), st_tp(kStateTruePeak * sp), de_tab(DE_FIELDS * sp);
+    std::vector<double> w0(static_cast<size_t>(a.ring_rows) * sp), w1(w0.size()), w2(w0.size()), w3(w0.size());
+    std::vector<float> buf_c(static_cast<size_t>(a.ring_rows) * sp), buf_p(buf_c.size());
+    a.w[0] = w0.data();
+    a.w[1] = w1.data();
+    a.w[2] = w2.data();
+    a.w[3] = w3.data();
+    a.buf_c = buf_c.data();
+    a.buf_p = buf_p.data();
     std::vector<StreamAccum> accum(sp);
     std::memset(accum.data(), 0, sp * sizeof(StreamAccum));
     std::vector<AfChainMetrics> metrics(n_pairs);
@@ -147,11 +155,39 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
                 for (int s = 0; s < S; ++s) body_deesser(a, ck, s);
             run_eq(ck);
         }
-        if (a.structure & ST_COMPRESSOR)
-            for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
+        const int n_groups = (ck.len + kGroup - 1) / kGroup + 1;  // one empty group past the end on purpose
+        if (a.structure & ST_COMPRESSOR) {
+            if (split & 1) {
+                for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s);
+                for (int g = n_groups - 1; g >= 0; --g)  // any order: the maps are independent
+                    for (int s = 0; s < S; ++s) body_comp_m2(a, ck, s, g);
+                for (int s = 0; s < S; ++s) body_comp_r3(a, ck, s);
+                for (int g = 0; g < n_groups; ++g)
+                    for (int s = 0; s < S; ++s) body_comp_m4(a, ck, s, g);
+                for (int s = 0; s < S; ++s) body_comp_r5(a, ck, s);
+                for (int g = n_groups - 1; g >= 0; --g)
+                    for (int s = 0; s < S; ++s) body_comp_m6(a, ck, s, g);
+            } else {
+                for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
+            }
+        }
         if (a.structure & ST_LIMITER) {
-            for (int s = 0; s < S; ++s) body_limiter(a, ck, s);
-            for (int s = 0; s < S; ++s) body_output<true>(a, ck, s, kFir);
+            if (split & 2) {
+                for (int g = n_groups - 1; g >= 0; --g)
+                    for (int s = 0; s < S; ++s) body_lim_m(a, ck, s, g);
+                for (int s = 0; s < S; ++s) body_lim_r(a, ck, s);
+            } else {
+                for (int s = 0; s < S; ++s) body_limiter(a, ck, s);
+            }
+            if (split & 4) {
+                for (int g = n_groups - 1; g >= 0; --g)
+                    for (int s = 0; s < S; ++s) body_tp_fir_in(a, ck, s, g, kFir);
+                for (int s = 0; s < S; ++s) body_tp_r(a, ck, s);
+                for (int g = n_groups - 1; g >= 0; --g)
+                    for (int s = 0; s < S; ++s) body_tp_fir_out(a, ck, s, g, kFir);
+            } else {
+                for (int s = 0; s < S; ++s) body_output<true>(a, ck, s, kFir);
+            }
         } else {
             for (int s = 0; s < S; ++s) body_output<false>(a, ck, s, kFir);
         }

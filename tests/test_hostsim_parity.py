@@ -19,15 +19,16 @@ X = golden_chain_input(blocks=60)  # 28 800 samples, the reference golden test's
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-@pytest.mark.parametrize("schedule", [(1024, 2, 5), (264, 3, 10), (40000, 2, 5)])
+@pytest.mark.parametrize("schedule", [(1024, 2, 5, 0), (264, 3, 10, 0), (40000, 2, 5, 0), (1024, 2, 5, 7), (264, 3, 10, 7),
+                                      (2048, 4, 5, 5), (512, 2, 5, 2)])
 def test_stage_bodies_bit_exact_with_oracle(name, schedule):
     bands, overrides = CASES[name]
     settings = abi.make_settings(**overrides)
     m0, a0, r0 = pyoracle.chain_render(X, FS, bands, settings, return_audio=True, return_rows=True)
-    chunk, slots, eq_k = schedule
+    chunk, slots, eq_k, split = schedule
     cands = candidate_array([candidate(bands, **overrides)])
-    m1, a1, r1 = hostsim.chain_sweep([X], FS, cands, [0], [0], chunk=chunk, slots=slots, eq_k=eq_k, want_audio=True,
-                                     want_rows=True)
+    m1, a1, r1 = hostsim.chain_sweep([X], FS, cands, [0], [0], chunk=chunk, slots=slots, eq_k=eq_k, split=split,
+                                     want_audio=True, want_rows=True)
     assert np.array_equal(a0, a1[0])
     assert np.array_equal(r0, r1[:, :, 0].T)
     assert metric_mismatches(m0, m1[0]) == {}
@@ -43,7 +44,12 @@ def test_multi_stream_batch_and_ragged_tail():
     cands = candidate_array(cand_list)
     pp = np.array([p for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
     pc = np.array([c for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
-    got, audio, _ = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=512, slots=2, want_audio=True)
+    for split in (0, 7):
+        got, audio, _ = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=512, slots=2, split=split, want_audio=True)
+        _check_pairs(passages, cand_list, pp, pc, got, audio)
+
+
+def _check_pairs(passages, cand_list, pp, pc, got, audio):
     for i in range(pp.size):
         m0, a0, _ = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings,
                                           return_audio=True)
@@ -58,10 +64,11 @@ def test_tiny_inputs(n):
     for name in ("legacy_eq", "golden_like"):
         bands, overrides = CASES[name]
         m0, a0, _ = pyoracle.chain_render(x, FS, bands, abi.make_settings(**overrides), return_audio=True)
-        m1, a1, _ = hostsim.chain_sweep([x], FS, candidate_array([candidate(bands, **overrides)]), [0], [0],
-                                        want_audio=True)
-        assert np.array_equal(a0, a1[0])
-        assert metric_mismatches(m0, m1[0]) == {}
+        for split in (0, 7):
+            m1, a1, _ = hostsim.chain_sweep([x], FS, candidate_array([candidate(bands, **overrides)]), [0], [0],
+                                            split=split, want_audio=True)
+            assert np.array_equal(a0, a1[0])
+            assert metric_mismatches(m0, m1[0]) == {}
 
 
 def test_non_finite_input_is_zeroed():
