@@ -68,10 +68,13 @@ __global__ void __launch_bounds__(128) k_input_true_peak(BatchArgs a, ChunkArgs 
 }
 
 // ---- split (R/M) path: serial recurrences, one thread per stream --------------------------------------------
-#define AF_R_KERNEL(name, body)                                              \
-    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) { \
-        AF_STREAM_INDEX();                                                   \
-        body(a, ck, s);                                                      \
+// Each thread stages its inputs through shared memory with cp.async (Staging, afsim_split.h).
+extern __shared__ __align__(16) unsigned char stage_smem[];
+#define AF_R_KERNEL(name, body)                                                         \
+    __global__ void __launch_bounds__(kRBlock) name(BatchArgs a, ChunkArgs ck) {        \
+        AF_STREAM_INDEX();                                                              \
+        const Staging stg{stage_smem, (int)blockDim.x, (int)threadIdx.x, 0};            \
+        body(a, ck, s, stg);                                                            \
     }
 AF_R_KERNEL(k_comp_r1, body_comp_r1)
 AF_R_KERNEL(k_comp_r3, body_comp_r3)
@@ -93,7 +96,7 @@ AF_M_KERNEL(k_lim_m, body_lim_m(a, ck, s, g))
 AF_M_KERNEL(k_tp_fir_in, body_tp_fir_in(a, ck, s, g, c_fir))
 AF_M_KERNEL(k_tp_fir_out, body_tp_fir_out(a, ck, s, g, c_fir))
 
-extern __shared__ float fin_smem[];
+extern __shared__ __align__(16) float fin_smem[];
 
 // One thread block per stream: sorts and percentiles of the per-block rows.
 __global__ void __launch_bounds__(kFinalizeThreads) k_finalize(BatchArgs a, int use_global) {
@@ -259,21 +262,22 @@ cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cuda
 }
 
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
-    const int rb = pick_block(a);
+    const int rb = kRBlock;
     const dim3 rgrid = stream_grid(a, rb);
+    const size_t rsm = kStagingBytesPerLane * kRBlock;
     const int mb = a.n_streams >= 128 ? 128 : 32;
     const dim3 mgrid((unsigned)((a.n_streams + mb - 1) / mb), (unsigned)((ck.len + kGroup - 1) / kGroup));
     switch (op) {
-        case SP_COMP_R1: k_comp_r1<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_R1: k_comp_r1<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_COMP_M2: k_comp_m2<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_COMP_R3: k_comp_r3<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_R3: k_comp_r3<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_COMP_M4: k_comp_m4<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_COMP_R5: k_comp_r5<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_COMP_R5: k_comp_r5<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_COMP_M6: k_comp_m6<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_LIM_M: k_lim_m<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_LIM_R: k_lim_r<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_LIM_R: k_lim_r<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_TP_FIR_IN: k_tp_fir_in<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_TP_R: k_tp_r<<<rgrid, rb, 0, st>>>(a, ck); break;
+        case SP_TP_R: k_tp_r<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_TP_FIR_OUT: k_tp_fir_out<<<mgrid, mb, 0, st>>>(a, ck); break;
         default: return cudaErrorInvalidValue;
     }

@@ -9,6 +9,7 @@ namespace afsim {
 struct ChunkArgs;
 
 constexpr int kFinalizeThreads = 128;
+constexpr int kRBlock = 32;  // threads per block of the serial (R) kernels: one warp, so few-stream batches reach every SM
 constexpr size_t kFinalizeSmemLimit = 200 * 1024;
 
 cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);

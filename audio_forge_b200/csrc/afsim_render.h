@@ -239,7 +239,7 @@ AF_HD T* col_at(T* ring, const BatchArgs& a, const ChunkArgs& ck, int s, int t0 
     return ring + (size_t)(ck.row0 + t0) * (size_t)a.stride + s;
 }
 
-AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s) {
+AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     CompSplit st;
     st.init(stream_params(a, s));
@@ -248,7 +248,7 @@ AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s) {
         st.sync_r1(io);
     }
     st.run_r1(col_at(a.buf_a, a, ck, s), col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s),
-              col_at(a.w[3], a, ck, s), stride, ck.len);
+              col_at(a.w[3], a, ck, s), stride, ck.len, stg);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{a.st_comp + s, stride};
         st.sync_r1(io);
@@ -262,7 +262,7 @@ AF_HD void body_comp_m2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     st.map_m2(col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
               col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
 }
-AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s) {
+AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     CompSplit st;
     st.init(stream_params(a, s));
@@ -271,7 +271,7 @@ AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s) {
         StateIO<false> io{table, stride};
         st.sync_r3(io);
     }
-    st.run_r3(col_at(a.w[0], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride, ck.len);
+    st.run_r3(col_at(a.w[0], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride, ck.len, stg);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync_r3(io);
@@ -284,7 +284,7 @@ AF_HD void body_comp_m4(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     st.init(stream_params(a, s));
     st.map_m4(col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
 }
-AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s) {
+AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     CompSplit st;
     st.init(stream_params(a, s));
@@ -295,7 +295,7 @@ AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s) {
     }
     BlockClock clk;
     clk.init(a.block_samples, a.n_samples, ck.n0);
-    st.run_r5(col_at(a.w[1], a, ck, s), stride, ck.n0, ck.len, clk, a.rows + (size_t)2 * a.n_rows * stride + s);
+    st.run_r5(col_at(a.w[1], a, ck, s), stride, ck.n0, ck.len, clk, a.rows + (size_t)2 * a.n_rows * stride + s, stg);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync_r5(io);
@@ -315,7 +315,7 @@ AF_HD void body_lim_m(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     limiter_targets(a.buf_a + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, a.lookahead,
                     stream_params(a, s).l_ceil, col_at(a.w[0], a, ck, s, t0));
 }
-AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
+AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     const CandidateParams& p = stream_params(a, s);
     LimiterR st;
@@ -326,7 +326,7 @@ AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
         st.sync(io);
     }
     st.run(col_at(a.w[0], a, ck, s), a.buf_a + s, col_at(a.buf_b, a, ck, s), stride, a.ring_rows, ck.row0, ck.n0, ck.len,
-           a.lookahead, p.l_ceil, p.l_release);
+           a.lookahead, p.l_ceil, p.l_release, stg);
     if (ck.n0 + ck.len >= a.n_samples) {
         a.accum[s].limiter_gr_db = st.peak_reduction_db();
     } else {
@@ -352,7 +352,7 @@ AF_HD void body_tp_fir_in(const BatchArgs& a, const ChunkArgs& ck, int s, int g,
     fir_group_peaks(a.buf_b + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, fir, pk);
     store_tile(col_at(a.buf_p, a, ck, s, t0), (size_t)a.stride, valid, pk);
 }
-AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
+AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     const CandidateParams& p = stream_params(a, s);
     TpR st;
@@ -366,7 +366,7 @@ AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s) {
     clk.init(a.block_samples, a.n_samples, ck.n0);
     float* audio = a.audio ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
     st.run(col_at(a.buf_p, a, ck, s), a.buf_b + s, col_at(a.buf_c, a, ck, s), audio, stride, a.ring_rows, ck.row0, ck.n0,
-           ck.len, p.tp_ceil, p.tp_release, clk, a.rows + (size_t)1 * a.n_rows * stride + s);
+           ck.len, p.tp_ceil, p.tp_release, clk, a.rows + (size_t)1 * a.n_rows * stride + s, stg);
     if (ck.n0 + ck.len >= a.n_samples) {
         StreamAccum& acc = a.accum[s];
         acc.sum_out = st.sum_out;

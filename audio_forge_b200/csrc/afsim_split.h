@@ -15,6 +15,9 @@
 //
 // Reference citations are relative to rust-core/src/.
 #pragma once
+#if defined(__CUDACC__)
+#include <cuda_pipeline.h>
+#endif
 #include "afsim_stages.h"
 
 namespace afsim {
@@ -25,6 +28,78 @@ AF_HD int ring_row(int row0, int t, int ring_rows) {
     int r = row0 + t;
     if (r < 0) r += ring_rows;
     return r;
+}
+
+// ---- asynchronous staging of the serial kernels' inputs --------------------------------------------------------
+// A thread that walks a recurrence reads a few bytes per sample from hand-off rings that live in HBM
+// (a chunk of every ring is tens of MB, far more than L2 holds across the ~25 stages in flight), and
+// with one warp per SM nothing hides that ~1 us latency.  So each R thread streams its inputs through a
+// private ring in shared memory with cp.async (LDGSTS): kPipeDepth tiles of kGroup samples are in
+// flight while the current tile is walked.  On the host the copies complete immediately, so
+// tests/hostsim exercises the same pipeline logic.
+constexpr int kPipeDepth = 8;
+
+AF_HD void async_copy(float* dst, const float* src) {
+#if defined(__CUDA_ARCH__)
+    __pipeline_memcpy_async(dst, src, 4);
+#else
+    *dst = *src;
+#endif
+}
+AF_HD void async_copy(double* dst, const double* src) {
+#if defined(__CUDA_ARCH__)
+    __pipeline_memcpy_async(dst, src, 8);
+#else
+    *dst = *src;
+#endif
+}
+AF_HD void async_commit() {
+#if defined(__CUDA_ARCH__)
+    __pipeline_commit();
+#endif
+}
+template <int N>
+AF_HD void async_wait_prior() {
+#if defined(__CUDA_ARCH__)
+    __pipeline_wait_prior(N);
+#endif
+}
+
+template <typename T>
+struct StageRing {  // one staged input stream of one thread
+    T* p;           // this thread's element of (tile slot 0, sample 0)
+    int lanes;      // threads sharing the staging area (element pitch)
+    AF_HD T* at(int tile, int u) const { return p + (size_t)((tile % kPipeDepth) * kGroup + u) * lanes; }
+};
+struct Staging {  // the staging area of a block (shared memory) / of one call (host)
+    unsigned char* base;
+    int lanes, lane;
+    size_t used;
+    template <typename T>
+    AF_HD StageRing<T> ring() {
+        StageRing<T> r;
+        r.p = reinterpret_cast<T*>(base + used) + lane;
+        r.lanes = lanes;
+        used += sizeof(T) * (size_t)kPipeDepth * kGroup * (size_t)lanes;
+        return r;
+    }
+};
+constexpr size_t kStagingBytesPerLane = (size_t)kPipeDepth * 8 * 16;  // widest user: two f64 streams (kGroup = 8)
+
+// issue(k) queues the copies of tile k; body(k) runs once tile k has landed.
+template <class Issue, class Body>
+AF_HD void pipelined_tiles(int len, Issue issue, Body body) {
+    const int n_tiles = (len + 8 - 1) / 8;
+    for (int k = 0; k < kPipeDepth - 1; ++k) {
+        if (k < n_tiles) issue(k);
+        async_commit();
+    }
+    for (int k = 0; k < n_tiles; ++k) {
+        if (k + kPipeDepth - 1 < n_tiles) issue(k + kPipeDepth - 1);
+        async_commit();
+        async_wait_prior<kPipeDepth - 1>();
+        body(k);
+    }
 }
 
 template <typename T, int U>
@@ -64,12 +139,21 @@ struct CompSplit : CompressorStage {
     }
 
     // R1: sidechain high-pass + band envelopes (:407-450).  x -> w0 = det, w1..w3 = band envelopes^2
-    AF_HD void run_r1(const float* x, double* w0, double* w1, double* w2, double* w3, size_t stride, int len) {
+    AF_HD void run_r1(const float* x, double* w0, double* w1, double* w2, double* w3, size_t stride, int len, Staging stg) {
         constexpr int U = kGroup;
-        for (int t0 = 0; t0 < len; t0 += U) {
+        const StageRing<float> sx = stg.ring<float>();
+        auto issue = [&](int k) {
+            const int t0 = k * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (t0 + u < len) async_copy(sx.at(k, u), x + (size_t)(t0 + u) * stride);
+        };
+        auto body = [&](int k) {
+            const int t0 = k * U;
             const int valid = len - t0 < U ? len - t0 : U;
             float xin[U];
-            load_tile(x + (size_t)t0 * stride, stride, valid, xin);
+#pragma unroll
+            for (int u = 0; u < U; ++u) xin[u] = u < valid ? *sx.at(k, u) : 0.0f;
             double det[U], lsq[U], vsq[U], psq[U];
             if (sidechain) {
 #pragma unroll
@@ -100,7 +184,8 @@ struct CompSplit : CompressorStage {
                 for (int u = 0; u < U; ++u) det[u] = (double)xin[u];
             }
             store_tile(w0 + (size_t)t0 * stride, stride, valid, det);
-        }
+        };
+        pipelined_tiles(len, issue, body);
     }
 
     // M2: detector weight in dB and instantaneous peak in dB.  w1 <- wdb, w2 <- ipk
@@ -134,13 +219,29 @@ struct CompSplit : CompressorStage {
     }
 
     // R3: peak (dB domain) and RMS envelopes.  (w0 det, w2 ipk) -> w2 = peak_env, w3 = rms_env
-    AF_HD void run_r3(const double* w0, double* w2, double* w3, size_t stride, int len) {
+    AF_HD void run_r3(const double* w0, double* w2, double* w3, size_t stride, int len, Staging stg) {
         constexpr int U = kGroup;
-        for (int t0 = 0; t0 < len; t0 += U) {
+        const StageRing<double> sdet = stg.ring<double>();
+        const StageRing<double> sipk = stg.ring<double>();
+        auto issue = [&](int k) {
+            const int t0 = k * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (t0 + u < len) {
+                    async_copy(sdet.at(k, u), w0 + (size_t)(t0 + u) * stride);
+                    async_copy(sipk.at(k, u), (const double*)w2 + (size_t)(t0 + u) * stride);
+                }
+            }
+        };
+        auto body = [&](int k) {
+            const int t0 = k * U;
             const int valid = len - t0 < U ? len - t0 : U;
             double det[U], ipk[U], pk[U], rms[U];
-            load_tile(w0 + (size_t)t0 * stride, stride, valid, det);
-            load_tile((const double*)(w2 + (size_t)t0 * stride), stride, valid, ipk);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                det[u] = u < valid ? *sdet.at(k, u) : 0.0;
+                ipk[u] = u < valid ? *sipk.at(k, u) : 0.0;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (u < valid) {
@@ -153,7 +254,8 @@ struct CompSplit : CompressorStage {
             }
             store_tile(w2 + (size_t)t0 * stride, stride, valid, pk);
             store_tile(w3 + (size_t)t0 * stride, stride, valid, rms);
-        }
+        };
+        pipelined_tiles(len, issue, body);
     }
 
     // M4: blended detector (:681-686) + gain computer (:657-678).  (w2 pk, w3 rms, w1 wdb) -> w1 = target GR
@@ -172,12 +274,21 @@ struct CompSplit : CompressorStage {
     }
 
     // R5: gain-reduction smoothing (:468-505), in place on w1; block-end meter rows
-    AF_HD void run_r5(double* w1, size_t stride, int n0, int len, BlockClock clk, float* rows_comp) {
+    AF_HD void run_r5(double* w1, size_t stride, int n0, int len, BlockClock clk, float* rows_comp, Staging stg) {
         constexpr int U = kGroup;
-        for (int t0 = 0; t0 < len; t0 += U) {
+        const StageRing<double> stgt = stg.ring<double>();
+        auto issue = [&](int k) {
+            const int t0 = k * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (t0 + u < len) async_copy(stgt.at(k, u), (const double*)w1 + (size_t)(t0 + u) * stride);
+        };
+        auto body = [&](int k) {
+            const int t0 = k * U;
             const int valid = len - t0 < U ? len - t0 : U;
             double tgt[U], grv[U];
-            load_tile((const double*)(w1 + (size_t)t0 * stride), stride, valid, tgt);
+#pragma unroll
+            for (int u = 0; u < U; ++u) tgt[u] = u < valid ? *stgt.at(k, u) : 0.0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (u < valid) {
@@ -204,7 +315,8 @@ struct CompSplit : CompressorStage {
                 grv[u] = gr;
             }
             store_tile(w1 + (size_t)t0 * stride, stride, valid, grv);
-        }
+        };
+        pipelined_tiles(len, issue, body);
     }
 
     // M6: apply gain.  (w1 gr, x) -> x
@@ -285,17 +397,34 @@ struct LimiterR {
     }
     // target (w0 column at chunk start), delayed input from the ring, output column at chunk start
     AF_HD void run(const double* target, const float* in_ring, float* out, size_t stride, int ring_rows, int row0, int n0,
-                   int len, int L, double ceil_lin, double rel) {
+                   int len, int L, double ceil_lin, double rel, Staging stg) {
         constexpr int U = kGroup;
         const double one_m_rel = 1.0 - rel;
-        for (int t0 = 0; t0 < len; t0 += U) {
+        const StageRing<double> stgt = stg.ring<double>();
+        const StageRing<float> sdel = stg.ring<float>();
+        auto issue = [&](int k) {
+            const int t0 = k * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (t0 + u < len) {
+                    async_copy(stgt.at(k, u), target + (size_t)(t0 + u) * stride);
+                    if (n0 + t0 + u >= L)
+                        async_copy(sdel.at(k, u), in_ring + (size_t)ring_row(row0, t0 + u - L, ring_rows) * stride);
+                    else
+                        *sdel.at(k, u) = 0.0f;
+                }
+            }
+        };
+        auto body = [&](int k) {
+            const int t0 = k * U;
             const int valid = len - t0 < U ? len - t0 : U;
             double tgt[U];
             float delayed[U], y[U];
-            load_tile(target + (size_t)t0 * stride, stride, valid, tgt);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                delayed[u] = (u < valid && n0 + t0 + u >= L) ? in_ring[(size_t)ring_row(row0, t0 + u - L, ring_rows) * stride] : 0.0f;
+            for (int u = 0; u < U; ++u) {
+                tgt[u] = u < valid ? *stgt.at(k, u) : 1.0;
+                delayed[u] = u < valid ? *sdel.at(k, u) : 0.0f;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (u < valid) {
@@ -308,7 +437,8 @@ struct LimiterR {
                 y[u] = (float)clampd((double)delayed[u] * g, -ceil_lin, ceil_lin);
             }
             store_tile(out + (size_t)t0 * stride, stride, valid, y);
-        }
+        };
+        pipelined_tiles(len, issue, body);
     }
     AF_HD float peak_reduction_db() const { return min_g < 1.0 ? (float)(-lin_to_db(min_g, 1e-10)) : 0.0f; }
 };
@@ -362,17 +492,32 @@ struct TpR {
     // itp: input true peaks (column at chunk start); in_ring: limiter output ring (the 20-sample delay
     // reads it); out: column at chunk start; audio: nullable
     AF_HD void run(const float* itp, const float* in_ring, float* out, float* audio, size_t stride, int ring_rows, int row0,
-                   int n0, int len, float ceil_lin, float rel, BlockClock clk, float* rows_out) {
+                   int n0, int len, float ceil_lin, float rel, BlockClock clk, float* rows_out, Staging stg) {
         constexpr int U = kGroup;
         const float one_m_rel = 1.0f - rel;
-        for (int t0 = 0; t0 < len; t0 += U) {
-            const int valid = len - t0 < U ? len - t0 : U;
-            float pk[U], delayed[U], y[U];
-            load_tile(itp + (size_t)t0 * stride, stride, valid, pk);
+        const StageRing<float> spk = stg.ring<float>();
+        const StageRing<float> sdel = stg.ring<float>();
+        auto issue = [&](int k) {
+            const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                float v = 0.0f;
-                if (u < valid && n0 + t0 + u >= kTpDelay) v = in_ring[(size_t)ring_row(row0, t0 + u - kTpDelay, ring_rows) * stride];
+                if (t0 + u < len) {
+                    async_copy(spk.at(k, u), itp + (size_t)(t0 + u) * stride);
+                    if (n0 + t0 + u >= kTpDelay)
+                        async_copy(sdel.at(k, u), in_ring + (size_t)ring_row(row0, t0 + u - kTpDelay, ring_rows) * stride);
+                    else
+                        *sdel.at(k, u) = 0.0f;
+                }
+            }
+        };
+        auto body = [&](int k) {
+            const int t0 = k * U;
+            const int valid = len - t0 < U ? len - t0 : U;
+            float pk[U], delayed[U], y[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                pk[u] = u < valid ? *spk.at(k, u) : 0.0f;
+                const float v = u < valid ? *sdel.at(k, u) : 0.0f;
                 delayed[u] = af_finite(v) ? v : 0.0f;
             }
 #pragma unroll
@@ -412,7 +557,8 @@ struct TpR {
                 for (int u = 0; u < U; ++u)
                     if (u < valid) audio[t0 + u] = y[u];
             }
-        }
+        };
+        pipelined_tiles(len, issue, body);
     }
     AF_HD float peak_reduction_db() const { return min_g >= 1.0f ? 0.0f : -20.0f * af_log10_f32(fmaxf(min_g, 1e-10f)); }
 };

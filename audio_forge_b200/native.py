@@ -14,6 +14,10 @@ import numpy as np
 
 from . import abi
 
+# The chunk x stage wavefront runs every stage on its own CUDA stream; the default of 8 hardware work
+# queues would serialise most of them.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libafsim.so"
 _lib = None

@@ -31,6 +31,8 @@ from pathlib import Path
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per stage stream (before CUDA init)
+
 ROOT = Path(__file__).resolve().parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
@@ -43,7 +45,9 @@ FS = workloads.FS
 
 # Algorithmic work per stream-sample of each stage: bytes = f32 read + f32 write
 # of the hand-off buffers; fp64 / fp32 = warp-lane arithmetic instructions of the loop body.
-STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20, "output": 4}
+STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20, "output": 4,
+               "comp_r1": 36, "comp_m2": 48, "comp_r3": 32, "comp_m4": 32, "comp_r5": 16, "comp_m6": 16,
+               "lim_m": 12, "lim_r": 16, "tp_fir_in": 8, "tp_r": 12, "tp_fir_out": 4}
 
 
 def parse_args():

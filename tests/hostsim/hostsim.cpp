@@ -130,6 +130,8 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
 
     if (a.structure & ST_DEESSER)
         for (int s = 0; s < S; ++s) body_expand_deesser(a, s);
+    std::vector<unsigned char> staging_bytes(kStagingBytesPerLane + 64);
+    const Staging stg{staging_bytes.data(), 1, 0, 0};
     const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
     auto run_eq = [&](const ChunkArgs& ck) {
         for (uint32_t f = 0; f < max_sections; f += eq_k)
@@ -158,13 +160,13 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         const int n_groups = (ck.len + kGroup - 1) / kGroup + 1;  // one empty group past the end on purpose
         if (a.structure & ST_COMPRESSOR) {
             if (split & 1) {
-                for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s);
+                for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s, stg);
                 for (int g = n_groups - 1; g >= 0; --g)  // any order: the maps are independent
                     for (int s = 0; s < S; ++s) body_comp_m2(a, ck, s, g);
-                for (int s = 0; s < S; ++s) body_comp_r3(a, ck, s);
+                for (int s = 0; s < S; ++s) body_comp_r3(a, ck, s, stg);
                 for (int g = 0; g < n_groups; ++g)
                     for (int s = 0; s < S; ++s) body_comp_m4(a, ck, s, g);
-                for (int s = 0; s < S; ++s) body_comp_r5(a, ck, s);
+                for (int s = 0; s < S; ++s) body_comp_r5(a, ck, s, stg);
                 for (int g = n_groups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_comp_m6(a, ck, s, g);
             } else {
@@ -175,14 +177,14 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
             if (split & 2) {
                 for (int g = n_groups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_lim_m(a, ck, s, g);
-                for (int s = 0; s < S; ++s) body_lim_r(a, ck, s);
+                for (int s = 0; s < S; ++s) body_lim_r(a, ck, s, stg);
             } else {
                 for (int s = 0; s < S; ++s) body_limiter(a, ck, s);
             }
             if (split & 4) {
                 for (int g = n_groups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_tp_fir_in(a, ck, s, g, kFir);
-                for (int s = 0; s < S; ++s) body_tp_r(a, ck, s);
+                for (int s = 0; s < S; ++s) body_tp_r(a, ck, s, stg);
                 for (int g = n_groups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_tp_fir_out(a, ck, s, g, kFir);
             } else {

@@ -29,8 +29,11 @@ def sim():
 X = golden_chain_input(blocks=100)  # 48 000 samples = 47 chunks of 1024
 
 
+@pytest.mark.parametrize("path", ["fused", "split"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_chain_render_matches_oracle(sim, name):
+def test_chain_render_matches_oracle(sim, name, path, monkeypatch):
+    """Both kernel paths: one-thread-per-stream fused stages (large sweeps) and the R/M split (few streams)."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
     bands, overrides = CASES[name]
     settings = abi.make_settings(**overrides)
     m0, a0, _ = pyoracle.chain_render(X, FS, bands, settings, return_audio=True)
@@ -60,8 +63,10 @@ def test_default_eq_is_bit_exact_passthrough(sim):
     assert st.output_sample_peak == st.input_sample_peak
 
 
-def test_sweep_mixed_structures_and_lengths(sim):
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_sweep_mixed_structures_and_lengths(sim, path, monkeypatch):
     """One call, several batches: candidates with different stage sets x passages of different lengths."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
     passages = [speech_like(20000 + 777 * k, seed=k, level=0.5 + 0.1 * k) for k in range(3)]
     names = ["default_legacy", "golden_like", "typed_pass", "no_limiter", "dc_hp", "long_lookahead"]
     cand_list = [candidate(CASES[n][0], **CASES[n][1]) for n in names]
@@ -75,8 +80,10 @@ def test_sweep_mixed_structures_and_lengths(sim):
             assert metric_mismatches(m0, metrics[i], tol_db=TOL_DB) == {}, (names[c], p)
 
 
-def test_sweep_many_streams_against_threaded_oracle(sim):
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_sweep_many_streams_against_threaded_oracle(sim, path, monkeypatch):
     """A 24 x 4 compressor grid (ragged last warp: 96 streams + explicit pair lists)."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
     passages = [speech_like(14400, seed=20 + k, level=0.8) for k in range(4)]
     bands, overrides = CASES["legacy_eq"]
     grid = [(thr, ratio, att) for thr in (-40.0, -30.0, -20.0, -12.0) for ratio in (1.5, 3.0, 6.0) for att in (3.0, 25.0)]
@@ -106,8 +113,10 @@ def test_resident_sweep_relaunch_is_deterministic(sim):
     assert first == second
 
 
+@pytest.mark.parametrize("path", ["fused", "split"])
 @pytest.mark.parametrize("n", [0, 1, 71, 72, 73, 960, 961])
-def test_tiny_and_empty_inputs(sim, n):
+def test_tiny_and_empty_inputs(sim, n, path, monkeypatch):
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
     x = speech_like(2000, seed=5, level=0.9)[:n].copy()
     bands, overrides = CASES["golden_like"]
     settings = abi.make_settings(**overrides)
