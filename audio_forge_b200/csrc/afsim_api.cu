@@ -31,7 +31,8 @@ struct AfsimHandle {
     int device = 0;
     cudaStream_t stream = nullptr;   // caller-visible stream: every call starts and ends on it
     bool own_stream = false;
-    cudaStream_t stage_stream[kMaxStages] = {};
+    cudaStream_t stage_stream[kMaxStages] = {};      // high priority: serial (latency-critical) stage kernels
+    cudaStream_t stage_stream_map[kMaxStages] = {};  // low priority: map kernels that fill every SM
     cudaEvent_t ev_fork = nullptr;
     std::string error;
 };
@@ -388,7 +389,13 @@ int run_batch(AfsimHandle* h, Batch& b) {
     if (a.structure & ST_DEESSER) AF_CUDA(h, launch_expand_deesser(a, h->stream));
     if (T > 0) {
         AF_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-        for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(h->stage_stream[i], h->ev_fork, 0));
+        auto stream_of = [&](int i) {
+            const StageDesc& sd = b.stages[i];
+            const bool is_map = sd.kind == SK_SPLIT && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
+                                                        sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT);
+            return is_map ? h->stage_stream_map[i] : h->stage_stream[i];
+        };
+        for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(stream_of(i), h->ev_fork, 0));
         const int n_chunks = (T + b.chunk - 1) / b.chunk;
         for (int c = 0; c < n_chunks; ++c) {
             ChunkArgs ck;
@@ -397,7 +404,7 @@ int run_batch(AfsimHandle* h, Batch& b) {
             const int slot = c % b.slots;
             ck.row0 = slot * b.chunk;
             for (int i = 0; i < n_stages; ++i) {
-                cudaStream_t st = h->stage_stream[i];
+                cudaStream_t st = stream_of(i);
                 if (i > 0) AF_CUDA(h, cudaStreamWaitEvent(st, b.events[static_cast<size_t>(i - 1) * b.slots + slot], 0));
                 if (i == 0 && c - b.slots + 1 >= 0) {
                     const int old_slot = (c - b.slots + 1) % b.slots;
@@ -470,8 +477,11 @@ int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle
         }
         h->own_stream = true;
     }
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     for (int i = 0; i < kMaxStages; ++i) {
-        err = cudaStreamCreateWithFlags(&h->stage_stream[i], cudaStreamNonBlocking);
+        err = cudaStreamCreateWithPriority(&h->stage_stream[i], cudaStreamNonBlocking, prio_greatest);
+        if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&h->stage_stream_map[i], cudaStreamNonBlocking, prio_least);
         if (err != cudaSuccess) {
             g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(err);
             return AFSIM_CUDA_ERROR;
@@ -490,8 +500,10 @@ void afsim_destroy(AfsimHandle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < kMaxStages; ++i)
+    for (int i = 0; i < kMaxStages; ++i) {
         if (h->stage_stream[i]) cudaStreamDestroy(h->stage_stream[i]);
+        if (h->stage_stream_map[i]) cudaStreamDestroy(h->stage_stream_map[i]);
+    }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -596,7 +608,10 @@ void afsim_sweep_release(AfsimHandle* h, AfsimSweep* sweep) {
     if (h) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
-        for (int i = 0; i < kMaxStages; ++i) cudaStreamSynchronize(h->stage_stream[i]);
+        for (int i = 0; i < kMaxStages; ++i) {
+            cudaStreamSynchronize(h->stage_stream[i]);
+            cudaStreamSynchronize(h->stage_stream_map[i]);
+        }
     }
     delete sweep;
 }

@@ -86,19 +86,34 @@ struct Staging {  // the staging area of a block (shared memory) / of one call (
 };
 constexpr size_t kStagingBytesPerLane = (size_t)kPipeDepth * 8 * 16;  // widest user: two f64 streams (kGroup = 8)
 
-// issue(k) queues the copies of tile k; body(k) runs once tile k has landed.
+// issue(k, full) queues the copies of tile k; body(k, full) runs once tile k has landed.  `full` is a
+// compile-time flag (TileFull / TileRagged): all tiles but the last one of a render hold kGroup samples, and
+// their code carries no per-sample bounds predicates.
+struct TileFull { static constexpr bool value = true; };
+struct TileRagged { static constexpr bool value = false; };
 template <class Issue, class Body>
 AF_HD void pipelined_tiles(int len, Issue issue, Body body) {
     const int n_tiles = (len + 8 - 1) / 8;
+    const int n_full = len / 8;
     for (int k = 0; k < kPipeDepth - 1; ++k) {
-        if (k < n_tiles) issue(k);
+        if (k < n_full)
+            issue(k, TileFull());
+        else if (k < n_tiles)
+            issue(k, TileRagged());
         async_commit();
     }
     for (int k = 0; k < n_tiles; ++k) {
-        if (k + kPipeDepth - 1 < n_tiles) issue(k + kPipeDepth - 1);
+        const int ahead = k + kPipeDepth - 1;
+        if (ahead < n_full)
+            issue(ahead, TileFull());
+        else if (ahead < n_tiles)
+            issue(ahead, TileRagged());
         async_commit();
         async_wait_prior<kPipeDepth - 1>();
-        body(k);
+        if (k < n_full)
+            body(k, TileFull());
+        else
+            body(k, TileRagged());
     }
 }
 
@@ -142,23 +157,25 @@ struct CompSplit : CompressorStage {
     AF_HD void run_r1(const float* x, double* w0, double* w1, double* w2, double* w3, size_t stride, int len, Staging stg) {
         constexpr int U = kGroup;
         const StageRing<float> sx = stg.ring<float>();
-        auto issue = [&](int k) {
+        auto issue = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (t0 + u < len) async_copy(sx.at(k, u), x + (size_t)(t0 + u) * stride);
+                if (FULL || t0 + u < len) async_copy(sx.at(k, u), x + (size_t)(t0 + u) * stride);
         };
-        auto body = [&](int k) {
+        auto body = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
-            const int valid = len - t0 < U ? len - t0 : U;
+            const int valid = FULL ? U : len - t0;
             float xin[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) xin[u] = u < valid ? *sx.at(k, u) : 0.0f;
+            for (int u = 0; u < U; ++u) xin[u] = (FULL || u < valid) ? *sx.at(k, u) : 0.0f;
             double det[U], lsq[U], vsq[U], psq[U];
             if (sidechain) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (u < valid) {
+                    if (FULL || u < valid) {
                         const double xv = (double)xin[u];
                         const double d = sc_c * (prev_out + xv - prev_in);
                         prev_in = xv;
@@ -223,28 +240,30 @@ struct CompSplit : CompressorStage {
         constexpr int U = kGroup;
         const StageRing<double> sdet = stg.ring<double>();
         const StageRing<double> sipk = stg.ring<double>();
-        auto issue = [&](int k) {
+        auto issue = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (t0 + u < len) {
+                if (FULL || t0 + u < len) {
                     async_copy(sdet.at(k, u), w0 + (size_t)(t0 + u) * stride);
                     async_copy(sipk.at(k, u), (const double*)w2 + (size_t)(t0 + u) * stride);
                 }
             }
         };
-        auto body = [&](int k) {
+        auto body = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
-            const int valid = len - t0 < U ? len - t0 : U;
+            const int valid = FULL ? U : len - t0;
             double det[U], ipk[U], pk[U], rms[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                det[u] = u < valid ? *sdet.at(k, u) : 0.0;
-                ipk[u] = u < valid ? *sipk.at(k, u) : 0.0;
+                det[u] = (FULL || u < valid) ? *sdet.at(k, u) : 0.0;
+                ipk[u] = (FULL || u < valid) ? *sipk.at(k, u) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (u < valid) {
+                if (FULL || u < valid) {
                     const bool up = ipk[u] > peak_env;
                     peak_env = (up ? attack : det_release) * peak_env + (up ? one_m_attack : one_m_det_release) * ipk[u];
                     rms_env = rms_c * rms_env + one_m_rms * (det[u] * det[u]);
@@ -277,43 +296,52 @@ struct CompSplit : CompressorStage {
     AF_HD void run_r5(double* w1, size_t stride, int n0, int len, BlockClock clk, float* rows_comp, Staging stg) {
         constexpr int U = kGroup;
         const StageRing<double> stgt = stg.ring<double>();
-        auto issue = [&](int k) {
+        auto issue = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (t0 + u < len) async_copy(stgt.at(k, u), (const double*)w1 + (size_t)(t0 + u) * stride);
+                if (FULL || t0 + u < len) async_copy(stgt.at(k, u), (const double*)w1 + (size_t)(t0 + u) * stride);
         };
-        auto body = [&](int k) {
+        auto body = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
-            const int valid = len - t0 < U ? len - t0 : U;
+            const int valid = FULL ? U : len - t0;
             double tgt[U], grv[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) tgt[u] = u < valid ? *stgt.at(k, u) : 0.0;
+            for (int u = 0; u < U; ++u) tgt[u] = (FULL || u < valid) ? *stgt.at(k, u) : 0.0;
+            auto walk = [&](auto may_end) {  // may_end: an analysis block can end inside this tile
+                constexpr bool CHECK = decltype(may_end)::value;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (u < valid) {
-                    const double target = tgt[u];
-                    if (!adaptive) {
-                        const bool up = target > gr;
-                        gr = (up ? attack : release) * gr + (up ? one_m_attack : one_m_release) * target;
-                    } else {
-                        if (target > gr)
-                            fast_env = attack * gr + one_m_attack * target;
-                        else
-                            fast_env = fast_c * fast_env + one_m_fast * target;
-                        if (target > 3.0)
-                            slow_env = charge_c * slow_env + one_m_charge * target;
-                        else
-                            slow_env *= slow_c;
-                        gr = fmax(fast_env, slow_env);
+                for (int u = 0; u < U; ++u) {
+                    if (FULL || u < valid) {
+                        const double target = tgt[u];
+                        if (!adaptive) {
+                            const bool up = target > gr;
+                            gr = (up ? attack : release) * gr + (up ? one_m_attack : one_m_release) * target;
+                        } else {
+                            if (target > gr)
+                                fast_env = attack * gr + one_m_attack * target;
+                            else
+                                fast_env = fast_c * fast_env + one_m_fast * target;
+                            if (target > 3.0)
+                                slow_env = charge_c * slow_env + one_m_charge * target;
+                            else
+                                slow_env *= slow_c;
+                            gr = fmax(fast_env, slow_env);
+                        }
+                        if (CHECK && clk.at_end(n0 + t0 + u)) {
+                            rows_comp[(size_t)clk.blk * stride] = (float)gr;
+                            clk.advance();
+                        }
                     }
-                    if (clk.at_end(n0 + t0 + u)) {
-                        rows_comp[(size_t)clk.blk * stride] = (float)gr;
-                        clk.advance();
-                    }
+                    grv[u] = gr;
                 }
-                grv[u] = gr;
-            }
+            };
+            if (FULL && clk.ends_after(n0 + t0, U))
+                walk(TileRagged());
+            else
+                walk(TileFull());
             store_tile(w1 + (size_t)t0 * stride, stride, valid, grv);
         };
         pipelined_tiles(len, issue, body);
@@ -402,11 +430,12 @@ struct LimiterR {
         const double one_m_rel = 1.0 - rel;
         const StageRing<double> stgt = stg.ring<double>();
         const StageRing<float> sdel = stg.ring<float>();
-        auto issue = [&](int k) {
+        auto issue = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (t0 + u < len) {
+                if (FULL || t0 + u < len) {
                     async_copy(stgt.at(k, u), target + (size_t)(t0 + u) * stride);
                     if (n0 + t0 + u >= L)
                         async_copy(sdel.at(k, u), in_ring + (size_t)ring_row(row0, t0 + u - L, ring_rows) * stride);
@@ -415,19 +444,20 @@ struct LimiterR {
                 }
             }
         };
-        auto body = [&](int k) {
+        auto body = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
-            const int valid = len - t0 < U ? len - t0 : U;
+            const int valid = FULL ? U : len - t0;
             double tgt[U];
             float delayed[U], y[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                tgt[u] = u < valid ? *stgt.at(k, u) : 1.0;
-                delayed[u] = u < valid ? *sdel.at(k, u) : 0.0f;
+                tgt[u] = (FULL || u < valid) ? *stgt.at(k, u) : 1.0;
+                delayed[u] = (FULL || u < valid) ? *sdel.at(k, u) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (u < valid) {
+                if (FULL || u < valid) {
                     if (tgt[u] < g)
                         g = tgt[u];
                     else
@@ -497,11 +527,12 @@ struct TpR {
         const float one_m_rel = 1.0f - rel;
         const StageRing<float> spk = stg.ring<float>();
         const StageRing<float> sdel = stg.ring<float>();
-        auto issue = [&](int k) {
+        auto issue = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (t0 + u < len) {
+                if (FULL || t0 + u < len) {
                     async_copy(spk.at(k, u), itp + (size_t)(t0 + u) * stride);
                     if (n0 + t0 + u >= kTpDelay)
                         async_copy(sdel.at(k, u), in_ring + (size_t)ring_row(row0, t0 + u - kTpDelay, ring_rows) * stride);
@@ -510,47 +541,55 @@ struct TpR {
                 }
             }
         };
-        auto body = [&](int k) {
+        auto body = [&](int k, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             const int t0 = k * U;
-            const int valid = len - t0 < U ? len - t0 : U;
+            const int valid = FULL ? U : len - t0;
             float pk[U], delayed[U], y[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                pk[u] = u < valid ? *spk.at(k, u) : 0.0f;
-                const float v = u < valid ? *sdel.at(k, u) : 0.0f;
+                pk[u] = (FULL || u < valid) ? *spk.at(k, u) : 0.0f;
+                const float v = (FULL || u < valid) ? *sdel.at(k, u) : 0.0f;
                 delayed[u] = af_finite(v) ? v : 0.0f;
             }
+            auto walk = [&](auto may_end) {  // may_end: an analysis block can end inside this tile
+                constexpr bool CHECK = decltype(may_end)::value;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                y[u] = 0.0f;
-                if (u < valid) {
-                    peak_pre = fmaxf(peak_pre, pk[u]);
-                    const float target = pk[u] > ceil_lin ? clampf((ceil_lin * 0.999f) / pk[u], 0.0f, 1.0f) : 1.0f;
-                    if (target < g) {
-                        g = target;
-                        limited = true;
-                    } else {
-                        g = rel * g + one_m_rel * target;
-                    }
-                    min_g = fminf(min_g, g);
-                    float o = clampf(delayed[u] * g, -ceil_lin, ceil_lin);
-                    if (!af_finite(o)) o = 0.0f;
-                    y[u] = o;
-                    // output statistics (python_api.rs:529-575)
-                    peak_out = fmaxf(peak_out, fabsf(o));
-                    const double sq = (double)o * (double)o;
-                    sum_out += sq;
-                    blk_out += sq;
-                    if (clk.at_end(n0 + t0 + u)) {
-                        events += limited ? 1u : 0u;
-                        limited = false;
-                        const float rms = (float)sqrt(blk_out / (double)clk.block_len(n0 + t0 + u));
-                        rows_out[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
-                        blk_out = 0.0;
-                        clk.advance();
+                for (int u = 0; u < U; ++u) {
+                    y[u] = 0.0f;
+                    if (FULL || u < valid) {
+                        peak_pre = fmaxf(peak_pre, pk[u]);
+                        const float target = pk[u] > ceil_lin ? clampf((ceil_lin * 0.999f) / pk[u], 0.0f, 1.0f) : 1.0f;
+                        if (target < g) {
+                            g = target;
+                            limited = true;
+                        } else {
+                            g = rel * g + one_m_rel * target;
+                        }
+                        min_g = fminf(min_g, g);
+                        float o = clampf(delayed[u] * g, -ceil_lin, ceil_lin);
+                        if (!af_finite(o)) o = 0.0f;
+                        y[u] = o;
+                        // output statistics (python_api.rs:529-575)
+                        peak_out = fmaxf(peak_out, fabsf(o));
+                        const double sq = (double)o * (double)o;
+                        sum_out += sq;
+                        blk_out += sq;
+                        if (CHECK && clk.at_end(n0 + t0 + u)) {
+                            events += limited ? 1u : 0u;
+                            limited = false;
+                            const float rms = (float)sqrt(blk_out / (double)clk.block_len(n0 + t0 + u));
+                            rows_out[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                            blk_out = 0.0;
+                            clk.advance();
+                        }
                     }
                 }
-            }
+            };
+            if (FULL && clk.ends_after(n0 + t0, U))
+                walk(TileRagged());
+            else
+                walk(TileFull());
             store_tile(out + (size_t)t0 * stride, stride, valid, y);
             if (audio) {
 #pragma unroll

@@ -105,6 +105,8 @@ struct BlockClock {
     }
     AF_HD bool at_end(int n) const { return n + 1 == next_end || n + 1 == total; }
     AF_HD int block_len(int n) const { return n + 1 - (next_end - block); }
+    // true when neither the current analysis block nor the signal ends within samples [n, n + count)
+    AF_HD bool ends_after(int n, int count) const { return next_end - n > count && total - n > count; }
     AF_HD void advance() {
         blk += 1;
         next_end += block;
