@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -27,8 +28,52 @@ thread_local std::string g_create_error;
 constexpr int kMaxStages = 32;
 }  // namespace
 
+// Device allocations are recycled through the handle: a sweep's work rings are GBs, and cudaMalloc /
+// cudaFree of those on every call would dominate the host-buffer (end-to-end) path.
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = size_t(96) << 30;
+    cudaError_t take(size_t bytes, void** out) {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto it = free_blocks.find(bytes);
+            if (it != free_blocks.end()) {
+                *out = it->second;
+                cached_bytes -= bytes;
+                free_blocks.erase(it);
+                return cudaSuccess;
+            }
+        }
+        cudaError_t err = cudaMalloc(out, bytes);
+        if (err == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+            cudaGetLastError();
+            trim();
+            err = cudaMalloc(out, bytes);
+        }
+        return err;
+    }
+    void give(size_t bytes, void* p) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (cached_bytes + bytes > kMaxCached) {
+            cudaFree(p);
+            return;
+        }
+        free_blocks.emplace(bytes, p);
+        cached_bytes += bytes;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& kv : free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+
 struct AfsimHandle {
     int device = 0;
+    DevicePool pool;
     cudaStream_t stream = nullptr;   // caller-visible stream: every call starts and ends on it
     bool own_stream = false;
     cudaStream_t stage_stream[kMaxStages] = {};      // high priority: serial (latency-critical) stage kernels
@@ -39,17 +84,24 @@ struct AfsimHandle {
 
 namespace {
 
-struct DeviceBuffers {  // frees what it allocated
-    std::vector<void*> ptrs;
+struct DeviceBuffers {  // returns what it allocated to the handle's pool
+    DevicePool* pool = nullptr;
+    std::vector<std::pair<size_t, void*>> blocks;
     ~DeviceBuffers() {
-        for (void* p : ptrs) cudaFree(p);
+        for (auto& b : blocks) {
+            if (pool)
+                pool->give(b.first, b.second);
+            else
+                cudaFree(b.second);
+        }
     }
     template <typename T>
     cudaError_t alloc(T** out, size_t count) {
         void* p = nullptr;
-        const cudaError_t err = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+        const cudaError_t err = pool ? pool->take(bytes, &p) : cudaMalloc(&p, bytes);
         if (err != cudaSuccess) return err;
-        ptrs.push_back(p);
+        blocks.emplace_back(bytes, p);
         *out = static_cast<T*>(p);
         return cudaSuccess;
     }
@@ -154,6 +206,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
     const RateConstants rate = rate_constants(fs);
 
     auto sweep = std::make_unique<AfsimSweep>();
+    sweep->mem.pool = &h->pool;
     sweep->n_pairs = n_pairs;
 
     // passages -> one device pool
@@ -505,6 +558,7 @@ void afsim_destroy(AfsimHandle* h) {
         if (h->stage_stream_map[i]) cudaStreamDestroy(h->stage_stream_map[i]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    h->pool.trim();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -787,6 +841,7 @@ int afsim_eq_response(AfsimHandle* h, const double* frequencies_hz, size_t n_fre
         plan_eq_sections(bands + s * AFSIM_NUM_BANDS, typed != 0, sample_rate,
                          reinterpret_cast<double(*)[5]>(coeffs.data() + s * kMaxSections * 5), sections.data() + s * AFSIM_NUM_BANDS);
     DeviceBuffers mem;
+    mem.pool = &h->pool;
     double *d_coeffs = nullptr, *d_freqs = nullptr, *d_out = nullptr;
     int* d_sections = nullptr;
     AF_CUDA(h, mem.alloc(&d_coeffs, coeffs.size()));

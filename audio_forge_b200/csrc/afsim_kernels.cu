@@ -83,11 +83,14 @@ AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
-#define AF_M_KERNEL(name, call)                                              \
-    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) { \
-        AF_STREAM_INDEX();                                                   \
-        const int g = (int)blockIdx.y;                                       \
-        call;                                                                \
+// A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping
+// rows that neighbouring groups read (31-sample FIR history, limiter window) hit in L1.
+#define AF_M_KERNEL(name, call)                                                          \
+    __global__ void __launch_bounds__(32 * kMapWarps) name(BatchArgs a, ChunkArgs ck) {  \
+        const int s = (int)(blockIdx.x * 32 + (threadIdx.x & 31));                       \
+        const int g = (int)(blockIdx.y * kMapWarps + (threadIdx.x >> 5));                \
+        if (s >= a.n_streams) return;                                                    \
+        call;                                                                            \
     }
 AF_M_KERNEL(k_comp_m2, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, body_comp_m4(a, ck, s, g))
@@ -265,8 +268,9 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     const int rb = kRBlock;
     const dim3 rgrid = stream_grid(a, rb);
     const size_t rsm = kStagingBytesPerLane * kRBlock;
-    const int mb = a.n_streams >= 128 ? 128 : 32;
-    const dim3 mgrid((unsigned)((a.n_streams + mb - 1) / mb), (unsigned)((ck.len + kGroup - 1) / kGroup));
+    const int mb = 32 * kMapWarps;
+    const int n_groups = (ck.len + kGroup - 1) / kGroup;
+    const dim3 mgrid((unsigned)((a.n_streams + 31) / 32), (unsigned)((n_groups + kMapWarps - 1) / kMapWarps));
     switch (op) {
         case SP_COMP_R1: k_comp_r1<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_COMP_M2: k_comp_m2<<<mgrid, mb, 0, st>>>(a, ck); break;

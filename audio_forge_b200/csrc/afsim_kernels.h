@@ -9,6 +9,7 @@ namespace afsim {
 struct ChunkArgs;
 
 constexpr int kFinalizeThreads = 128;
+constexpr int kMapWarps = 4;  // warps per block of the map (M) kernels
 constexpr int kRBlock = 32;  // threads per block of the serial (R) kernels: one warp, so few-stream batches reach every SM
 constexpr size_t kFinalizeSmemLimit = 200 * 1024;
 

@@ -285,9 +285,7 @@ struct CompSplit : CompressorStage {
         load_tile((const double*)w1, stride, valid, wdb);
 #pragma unroll
         for (int u = 0; u < kGroup; ++u) {
-            const double rms_db = lin_to_db(sqrt(rms[u]), 1e-10);
-            const double blended = 0.6 * db_to_lin(pk[u]) + 0.4 * db_to_lin(rms_db);
-            tgt[u] = gain_computer(lin_to_db(blended, 1e-10) + wdb[u]);
+            tgt[u] = gain_computer(lin_to_db(0.6 * db_to_lin(pk[u]) + 0.4 * rms_linear(rms[u]), 1e-10) + wdb[u]);
         }
         store_tile(w1, stride, valid, tgt);
     }

@@ -529,6 +529,19 @@ struct DeEsserStage {
     }
 };
 
+// The RMS leg of the blended detector (dsp/compressor.rs:681-686) is db_to_linear(linear_to_db(sqrt(e)))
+// = 10^(log10(max(sqrt(e), 1e-10))), i.e. max(sqrt(e), 1e-10) up to the rounding of the log / exp pair
+// (~2e-16 relative).  The device map evaluates the closed form -- the same size of deviation as the device
+// libm's ulp differences that the parity tolerance already covers -- and saves a log10 + exp10 per sample.
+// The host build (tests/hostsim) keeps the reference's round trip so that it stays bit-exact with the oracle.
+AF_HD double rms_linear(double env_sq) {
+#if defined(__CUDA_ARCH__)
+    return fmax(sqrt(env_sq), 1e-10);
+#else
+    return db_to_lin(lin_to_db(sqrt(env_sq), 1e-10));
+#endif
+}
+
 // ---- compressor (dsp/compressor.rs:725-774), auto-makeup off ---------------------------------------------
 // A chunk is processed in micro-tiles of M samples, phase by phase: the short recurrences (sidechain
 // high-pass, band / peak / RMS envelopes, gain-reduction smoothing) run serially, the transcendental
@@ -654,8 +667,7 @@ struct CompressorStage {
             // phase 4: blended detector (:681-686) + gain computer, independent per sample
 #pragma unroll
             for (int i = 0; i < M; ++i) {
-                const double rms_db = lin_to_db(sqrt(rms[i]), 1e-10);
-                const double blended = 0.6 * db_to_lin(pk[i]) + 0.4 * db_to_lin(rms_db);
+                const double blended = 0.6 * db_to_lin(pk[i]) + 0.4 * rms_linear(rms[i]);
                 tgt[i] = gain_computer(lin_to_db(blended, 1e-10) + wdb[i]);
             }
             // phase 5: gain-reduction smoothing (:468-505), serial
