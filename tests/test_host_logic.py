@@ -1,0 +1,162 @@
+"""Host-side logic that needs no GPU: C-ABI surface, batched headroom decisions, sharding + gloo gather."""
+import ctypes as C
+import os
+import re
+import socket
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from audio_forge_b200 import abi, headroom, native, sharding
+from oracle import pyoracle
+from tests.cases import FS, candidate, candidate_array, metric_mismatches
+from tests.signals import speech_like
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """Every function include/afsim.h declares is exported by libafsim.so (no compute calls here)."""
+    native.build()
+    header = (ROOT / "include" / "afsim.h").read_text()
+    declared = set(re.findall(r"\b(afsim_[a-z_0-9]+)\s*\(", header))
+    lib = C.CDLL(str(native.LIB_PATH))
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert missing == []
+    assert declared == set(native.EXPORTS)
+    lib.afsim_abi_version.restype = C.c_int
+    assert lib.afsim_abi_version() == 1
+
+
+def test_pod_layouts_match_the_header():
+    assert C.sizeof(abi.AfBand) == 32
+    assert C.sizeof(abi.AfChainSettings) == 16 + 18 * 8
+    assert C.sizeof(abi.AfCandidate) == 10 * 32 + 160
+    assert C.sizeof(abi.AfChainMetrics) == 136
+    lib = C.CDLL(str(native.LIB_PATH))
+    s = abi.AfChainSettings()
+    lib.afsim_chain_settings_default(C.byref(s))
+    ref = abi.make_settings()
+    assert bytes(s) == bytes(ref)
+    bands = (abi.AfBand * 10)()
+    lib.afsim_default_bands(bands)
+    assert bytes(bands) == bytes(abi.default_bands())
+
+
+def test_no_gpu_means_a_loud_failure_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(native.AfsimError, match="no CPU path"):
+        native.Simulator(0)
+
+
+def _oracle_batch(passages, fs, jobs):
+    """Stand-in for mic_eq_core.simulate_auto_eq_chain_batch built on the CPU oracle (tests only)."""
+    from audio_forge_b200 import mic_eq_core
+    out = []
+    for bands, settings in jobs:
+        st, _, _ = mic_eq_core.settings_from_mapping(settings)
+        m, _, _ = pyoracle.chain_render(passages[0], fs, abi.legacy_bands(bands), st)
+        out.append(abi.metrics_to_dict(m))
+    return out
+
+
+def _sequential_reference_walk(audio, fs, eq_settings, chain_settings):
+    """headroom.py:292-354 restated with one render per scale, stopping at the first safe one."""
+    flat = headroom.flatten_chain_settings(chain_settings)
+    flat.pop("return_output_audio")
+    sims = []
+    for cand in headroom.scaled_candidates(eq_settings):
+        sim = _oracle_batch([audio], fs, [(headroom.bands_from_settings(cand), flat)])[0]
+        sim["simulation_backend"] = "rust"
+        sims.append(sim)
+        if headroom.is_headroom_safe(sim):
+            break
+    return len(sims) - 1, sims
+
+
+def test_batched_headroom_validation_equals_the_sequential_walk():
+    """test_auto_eq.py:968-1001 shape: 0.62 sine at 5 kHz, +9 dB on band 6 -> scaled down, safe."""
+    x = (0.62 * np.sin(2 * np.pi * 5000.0 * np.arange(9600) / FS)).astype(np.float32)
+    base = {"band_freqs": list(abi.DEFAULT_FREQUENCIES), "band_qs": [1.41] * 10, "band_gains": [0.0] * 10}
+    hot = dict(base, band_gains=[0, 0, 0, 0, 0, 0, 9.0, 0, 0, 0])
+    flat_ok = dict(base)
+    broken = dict(base, band_gains=[1.0, 2.0])
+    chain = {"compressor": {"enabled": False}, "limiter": {"enabled": True, "ceiling_db": -0.5}}
+    results = headroom.apply_headroom_validation_batch(x, FS, [hot, flat_ok, broken], chain, simulate_batch=_oracle_batch)
+    index, sims = _sequential_reference_walk(x, FS, hot, chain)
+    r = results[0]
+    assert r["headroom_gain_scale"] == headroom.HEADROOM_SCALES[index] < 1.0
+    assert r["headroom_safe"] and r["headroom_validation"]["status"] == "safe"
+    assert r["headroom_validation"]["after"]["pre_limiter_true_peak_headroom_db"] >= 1.0
+    assert r["validation_confidence"] == 0.72
+    assert np.allclose(r["band_gains"], np.asarray(hot["band_gains"]) * headroom.HEADROOM_SCALES[index])
+    assert results[1]["headroom_gain_scale"] == 1.0 and results[1]["headroom_safe"]
+    assert results[2] == broken  # headroom.py:303-304: malformed settings pass through untouched
+
+
+def test_abstain_when_no_scale_is_safe():
+    x = (0.99 * np.sign(np.sin(2 * np.pi * 900.0 * np.arange(9600) / FS))).astype(np.float32)  # clipped square wave
+    base = {"band_freqs": list(abi.DEFAULT_FREQUENCIES), "band_qs": [1.41] * 10, "band_gains": [6.0] * 10}
+    r = headroom.apply_headroom_validation_batch(x, FS, [base], {"compressor": {"enabled": False}},
+                                                 simulate_batch=_oracle_batch)[0]
+    assert r["headroom_gain_scale"] == 0.0 and not r["headroom_safe"]
+    assert r["headroom_validation"]["status"] == "risk"
+    assert r["validation_confidence"] == 0.42 and r["analysis_confidence"] == 0.58
+
+
+def test_shard_streams_is_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    costs = rng.choice([50.0, 56.0, 80.0], size=1000) * 480000
+    shards = sharding.shard_streams(costs, 8)
+    assert np.array_equal(np.sort(np.concatenate(shards)), np.arange(1000))
+    loads = np.array([costs[s].sum() for s in shards])
+    assert loads.max() / loads.min() < 1.01
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, tmp: str):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        passages, cands, pp, pc = _sweep_problem()
+        costs = sharding.stream_costs(cands, pc, [passages[p].size for p in pp])
+        mine = sharding.shard_streams(costs, world)[rank]
+        local = pyoracle.chain_sweep(passages, FS, cands, pp[mine], pc[mine])  # stands in for the rank's GPU render
+        full = sharding.gather_metrics(local, mine, pp.size)
+        np.save(os.path.join(tmp, f"rank{rank}.npy"), sharding.metrics_to_bytes(full, pp.size))
+    finally:
+        dist.destroy_process_group()
+
+
+def _sweep_problem():
+    passages = [speech_like(4800, seed=k, level=0.8) for k in range(2)]
+    bands = abi.default_bands()
+    cand_list = [candidate(bands, compressor_threshold_db=t, compressor_ratio=r) for t in (-30.0, -20.0, -10.0) for r in (2.0, 5.0)]
+    cand_list.append(candidate(abi.typed_bands([("high_pass", 90, 0, 0.7, 48, True)] + [("bell", f, 1.0, 1.0, 12, True)
+                                                for f in abi.DEFAULT_FREQUENCIES[1:]]), use_typed_bands=True))
+    cands = candidate_array(cand_list)
+    pp = np.array([p for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+    pc = np.array([c for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+    return passages, cands, pp, pc
+
+
+def test_two_rank_gloo_gather_reassembles_the_single_process_result(tmp_path):
+    """world_size 2 on CPU: each rank renders its shard, the all-gather puts every struct back in caller order."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    passages, cands, pp, pc = _sweep_problem()
+    want = pyoracle.chain_sweep(passages, FS, cands, pp, pc)
+    for rank in range(2):
+        got = sharding.bytes_to_metrics(np.load(tmp_path / f"rank{rank}.npy"))
+        for i in range(pp.size):
+            assert metric_mismatches(want[i], got[i]) == {}, (rank, i)
