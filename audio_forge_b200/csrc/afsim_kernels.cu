@@ -12,6 +12,8 @@
 //        explicit __fmaf_rn).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "afsim_kernels.h"
 #include "afsim_render.h"
 
@@ -88,9 +90,12 @@ AF_R_KERNEL(k_tp_r, body_tp_r)
 #define AF_M_KERNEL(name, call)                                                          \
     __global__ void __launch_bounds__(32 * kMapWarps) name(BatchArgs a, ChunkArgs ck) {  \
         const int s = (int)(blockIdx.x * 32 + (threadIdx.x & 31));                       \
-        const int g = (int)(blockIdx.y * kMapWarps + (threadIdx.x >> 5));                \
         if (s >= a.n_streams) return;                                                    \
-        call;                                                                            \
+        const int n_groups = (ck.len + kGroup - 1) / kGroup;                             \
+        for (int g = (int)(blockIdx.y * kMapWarps + (threadIdx.x >> 5)); g < n_groups;   \
+             g += (int)gridDim.y * kMapWarps) {                                          \
+            call;                                                                        \
+        }                                                                                \
     }
 AF_M_KERNEL(k_comp_m2, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, body_comp_m4(a, ck, s, g))
@@ -264,13 +269,38 @@ cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cuda
     return cudaGetLastError();
 }
 
+static int env_blocks_per_sm() {
+    const char* v = getenv("AFSIM_MAP_BLOCKS_PER_SM");
+    return v && *v ? atoi(v) : 0;
+}
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int rb = kRBlock;
     const dim3 rgrid = stream_grid(a, rb);
     const size_t rsm = kStagingBytesPerLane * kRBlock;
     const int mb = 32 * kMapWarps;
     const int n_groups = (ck.len + kGroup - 1) / kGroup;
-    const dim3 mgrid((unsigned)((a.n_streams + 31) / 32), (unsigned)((n_groups + kMapWarps - 1) / kMapWarps));
+    // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
+    // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
+    // other wavefront stages.  AFSIM_MAP_BLOCKS_PER_SM = 0 removes the cap.
+    static const int blocks_per_sm = env_blocks_per_sm();
+    const unsigned gx = (unsigned)((a.n_streams + 31) / 32);
+    unsigned gy = (unsigned)((n_groups + kMapWarps - 1) / kMapWarps);
+    if (blocks_per_sm > 0) {
+        const unsigned cap = (unsigned)((blocks_per_sm * sm_count() + (int)gx - 1) / (int)gx);
+        if (gy > cap) gy = cap < 1 ? 1 : cap;
+    }
+    const dim3 mgrid(gx, gy);
     switch (op) {
         case SP_COMP_R1: k_comp_r1<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_COMP_M2: k_comp_m2<<<mgrid, mb, 0, st>>>(a, ck); break;
