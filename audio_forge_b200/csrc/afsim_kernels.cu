@@ -87,22 +87,22 @@ AF_R_KERNEL(k_tp_r, body_tp_r)
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
 // A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping
 // rows that neighbouring groups read (31-sample FIR history, limiter window) hit in L1.
-#define AF_M_KERNEL(name, call)                                                          \
+#define AF_M_KERNEL(name, GROUP, call)                                                         \
     __global__ void __launch_bounds__(32 * kMapWarps) name(BatchArgs a, ChunkArgs ck) {  \
         const int s = (int)(blockIdx.x * 32 + (threadIdx.x & 31));                       \
         if (s >= a.n_streams) return;                                                    \
-        const int n_groups = (ck.len + kGroup - 1) / kGroup;                             \
+        const int n_groups = (ck.len + (GROUP) - 1) / (GROUP);                           \
         for (int g = (int)(blockIdx.y * kMapWarps + (threadIdx.x >> 5)); g < n_groups;   \
              g += (int)gridDim.y * kMapWarps) {                                          \
             call;                                                                        \
         }                                                                                \
     }
-AF_M_KERNEL(k_comp_m2, body_comp_m2(a, ck, s, g))
-AF_M_KERNEL(k_comp_m4, body_comp_m4(a, ck, s, g))
-AF_M_KERNEL(k_comp_m6, body_comp_m6(a, ck, s, g))
-AF_M_KERNEL(k_lim_m, body_lim_m(a, ck, s, g))
-AF_M_KERNEL(k_tp_fir_in, body_tp_fir_in(a, ck, s, g, c_fir))
-AF_M_KERNEL(k_tp_fir_out, body_tp_fir_out(a, ck, s, g, c_fir))
+AF_M_KERNEL(k_comp_m2, kCompMapGroup, body_comp_m2(a, ck, s, g))
+AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
+AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
+AF_M_KERNEL(k_lim_m, kGroup, body_lim_m(a, ck, s, g))
+AF_M_KERNEL(k_tp_fir_in, kGroup, body_tp_fir_in(a, ck, s, g, c_fir))
+AF_M_KERNEL(k_tp_fir_out, kGroup, body_tp_fir_out(a, ck, s, g, c_fir))
 
 extern __shared__ __align__(16) float fin_smem[];
 
@@ -289,7 +289,8 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     const dim3 rgrid = stream_grid(a, rb);
     const size_t rsm = kStagingBytesPerLane * kRBlock;
     const int mb = 32 * kMapWarps;
-    const int n_groups = (ck.len + kGroup - 1) / kGroup;
+    const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup : kGroup;
+    const int n_groups = (ck.len + group - 1) / group;
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
     // other wavefront stages.  AFSIM_MAP_BLOCKS_PER_SM = 0 removes the cap.

@@ -229,9 +229,9 @@ AF_HD void body_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, int s, 
 // split (R/M) path: see afsim_split.h.  R bodies: one call per stream and chunk; M bodies: one call per
 // (stream, group of kGroup samples).
 // =====================================================================================================================
-AF_HD bool group_span(const ChunkArgs& ck, int g, int* t0, int* valid) {
-    *t0 = g * kGroup;
-    *valid = ck.len - *t0 < kGroup ? ck.len - *t0 : kGroup;
+AF_HD bool group_span(const ChunkArgs& ck, int g, int* t0, int* valid, int group = kGroup) {
+    *t0 = g * group;
+    *valid = ck.len - *t0 < group ? ck.len - *t0 : group;
     return *valid > 0;
 }
 template <typename T>
@@ -256,7 +256,7 @@ AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s, Staging 
 }
 AF_HD void body_comp_m2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
-    if (!group_span(ck, g, &t0, &valid)) return;
+    if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
     st.init(stream_params(a, s));
     st.map_m2(col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
@@ -279,7 +279,7 @@ AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s, Staging 
 }
 AF_HD void body_comp_m4(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
-    if (!group_span(ck, g, &t0, &valid)) return;
+    if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
     st.init(stream_params(a, s));
     st.map_m4(col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
@@ -303,7 +303,7 @@ AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s, Staging 
 }
 AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
-    if (!group_span(ck, g, &t0, &valid)) return;
+    if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
     st.init(stream_params(a, s));
     st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);

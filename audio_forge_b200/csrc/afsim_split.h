@@ -22,7 +22,9 @@
 
 namespace afsim {
 
-constexpr int kGroup = 8;  // samples per map thread; chunks are multiples of it
+constexpr int kGroup = 8;         // samples per tile of the serial kernels / per FIR and limiter map thread
+constexpr int kCompMapGroup = 2;  // samples per thread of the compressor maps: their transcendental chains need
+                                  // ~100+ registers per sample in flight, so occupancy (not unrolling) hides latency
 
 AF_HD int ring_row(int row0, int t, int ring_rows) {
     int r = row0 + t;
@@ -207,7 +209,7 @@ struct CompSplit : CompressorStage {
 
     // M2: detector weight in dB and instantaneous peak in dB.  w1 <- wdb, w2 <- ipk
     AF_HD void map_m2(const double* w0, double* w1, double* w2, const double* w3, size_t stride, int valid) const {
-        double det[kGroup], lsq[kGroup], vsq[kGroup], psq[kGroup], wdb[kGroup], ipk[kGroup];
+        double det[kCompMapGroup], lsq[kCompMapGroup], vsq[kCompMapGroup], psq[kCompMapGroup], wdb[kCompMapGroup], ipk[kCompMapGroup];
         load_tile(w0, stride, valid, det);
         if (sidechain) {
             load_tile((const double*)w1, stride, valid, lsq);
@@ -215,7 +217,7 @@ struct CompSplit : CompressorStage {
             load_tile(w3, stride, valid, psq);
         }
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
+        for (int u = 0; u < kCompMapGroup; ++u) {
             if (sidechain) {
                 const double low_rms = sqrt(lsq[u]);
                 const double voiced_rms = fmax(sqrt(vsq[u]), 1e-8);
@@ -279,12 +281,12 @@ struct CompSplit : CompressorStage {
 
     // M4: blended detector (:681-686) + gain computer (:657-678).  (w2 pk, w3 rms, w1 wdb) -> w1 = target GR
     AF_HD void map_m4(double* w1, const double* w2, const double* w3, size_t stride, int valid) const {
-        double pk[kGroup], rms[kGroup], wdb[kGroup], tgt[kGroup];
+        double pk[kCompMapGroup], rms[kCompMapGroup], wdb[kCompMapGroup], tgt[kCompMapGroup];
         load_tile(w2, stride, valid, pk);
         load_tile(w3, stride, valid, rms);
         load_tile((const double*)w1, stride, valid, wdb);
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
+        for (int u = 0; u < kCompMapGroup; ++u) {
             tgt[u] = gain_computer(lin_to_db(0.6 * db_to_lin(pk[u]) + 0.4 * rms_linear(rms[u]), 1e-10) + wdb[u]);
         }
         store_tile(w1, stride, valid, tgt);
@@ -347,12 +349,12 @@ struct CompSplit : CompressorStage {
 
     // M6: apply gain.  (w1 gr, x) -> x
     AF_HD void map_m6(const double* w1, float* x, size_t stride, int valid) const {
-        double grv[kGroup];
-        float xin[kGroup], y[kGroup];
+        double grv[kCompMapGroup];
+        float xin[kCompMapGroup], y[kCompMapGroup];
         load_tile(w1, stride, valid, grv);
         load_tile((const float*)x, stride, valid, xin);
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
+        for (int u = 0; u < kCompMapGroup; ++u) {
             const double gain = db_to_lin(-grv[u]) * makeup_lin;
             y[u] = (float)((double)xin[u] * gain);
         }

@@ -161,13 +161,14 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         if (a.structure & ST_COMPRESSOR) {
             if (split & 1) {
                 for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s, stg);
-                for (int g = n_groups - 1; g >= 0; --g)  // any order: the maps are independent
+                const int n_cgroups = (ck.len + kCompMapGroup - 1) / kCompMapGroup + 1;
+                for (int g = n_cgroups - 1; g >= 0; --g)  // any order: the maps are independent
                     for (int s = 0; s < S; ++s) body_comp_m2(a, ck, s, g);
                 for (int s = 0; s < S; ++s) body_comp_r3(a, ck, s, stg);
-                for (int g = 0; g < n_groups; ++g)
+                for (int g = 0; g < n_cgroups; ++g)
                     for (int s = 0; s < S; ++s) body_comp_m4(a, ck, s, g);
                 for (int s = 0; s < S; ++s) body_comp_r5(a, ck, s, stg);
-                for (int g = n_groups - 1; g >= 0; --g)
+                for (int g = n_cgroups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_comp_m6(a, ck, s, g);
             } else {
                 for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
