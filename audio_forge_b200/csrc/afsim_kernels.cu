@@ -100,7 +100,7 @@ AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_M_KERNEL(k_comp_m2, kCompMapGroup, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
 AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
-AF_M_KERNEL(k_lim_m, kGroup, body_lim_m(a, ck, s, g))
+AF_M_KERNEL(k_lim_m, kLimGroup, body_lim_m(a, ck, s, g))
 AF_M_KERNEL(k_tp_fir_in, kGroup, body_tp_fir_in(a, ck, s, g, c_fir))
 AF_M_KERNEL(k_tp_fir_out, kGroup, body_tp_fir_out(a, ck, s, g, c_fir))
 
@@ -289,7 +289,8 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     const dim3 rgrid = stream_grid(a, rb);
     const size_t rsm = kStagingBytesPerLane * kRBlock;
     const int mb = 32 * kMapWarps;
-    const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup : kGroup;
+    const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup
+                      : (op == SP_LIM_M ? kLimGroup : kGroup);
     const int n_groups = (ck.len + group - 1) / group;
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the

@@ -311,7 +311,7 @@ AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
 
 AF_HD void body_lim_m(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
-    if (!group_span(ck, g, &t0, &valid)) return;
+    if (!group_span(ck, g, &t0, &valid, kLimGroup)) return;
     limiter_targets(a.buf_a + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, a.lookahead,
                     stream_params(a, s).l_ceil, col_at(a.w[0], a, ck, s, t0));
 }

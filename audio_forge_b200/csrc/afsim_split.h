@@ -365,51 +365,70 @@ struct CompSplit : CompressorStage {
 // ---- lookahead limiter (dsp/limiter.rs:246-284) -----------------------------------------------------------------
 // M: target gain of samples n..n+7 from the sliding maximum of |x| over [n-L, n] (exact: max is order
 // independent).  The 8 windows share [n+7-L, n]; each adds a few samples on the left and on the right.
-AF_HD void limiter_targets(const float* in_ring, size_t stride, int ring_rows, int row0, int t0, int n_first, int valid,
-                           int L, double ceil_lin, double* target_out /* column at t0 */) {
-    constexpr int G = kGroup;
-    float win[G];
-    if (L >= G - 1) {
-        // common part [n+G-1-L, n]
-        float common = 0.0f;
-        for (int m = G - 1 - L; m <= 0; ++m) {
-            if (n_first + m >= 0) common = fmaxf(common, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
-        }
-        // left extensions: window j additionally covers [n+j-L, n+G-2-L]
-        float left[G];
+constexpr int kLimGroup = 32;  // outputs per limiter-map thread: L + 32 loads for 32 windows
+
+// x(m) = |input| of sample n_first + m, m in [-L, kLimGroup): FAST = the whole span is inside the ring slot
+// history (no wrap, no samples before the render's start, no ragged tail), so it is one pointer walk.
+template <bool FAST>
+struct LimiterSpan {
+    const float* ring;   // this stream's column of the ring
+    const float* first;  // FAST: &x(-L)
+    size_t stride;
+    int ring_rows, row0, t0, n_first, valid, L;
+    AF_HD float operator()(int m) const {
+        if (FAST) return fabsf(first[(size_t)(m + L) * stride]);
+        if (n_first + m < 0 || m >= valid) return 0.0f;
+        return fabsf(ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]);
+    }
+};
+
+template <bool FAST>
+AF_HD void limiter_windows(const LimiterSpan<FAST>& x, int L, float (&win)[kLimGroup]) {
+    constexpr int G = kLimGroup;
+    if (L >= G) {
+        // window j = [j-L, j] = (suffix of the samples before the group, from j-L) U (prefix of the group, to j)
         float run = 0.0f;
-        left[G - 1] = 0.0f;
+        for (int m = -1; m >= G - L; --m) run = fmaxf(run, x(m));
+        float left[G];
 #pragma unroll
-        for (int j = G - 2; j >= 0; --j) {
-            const int m = j - L;
-            if (n_first + m >= 0) run = fmaxf(run, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
+        for (int j = G - 1; j >= 0; --j) {
+            run = fmaxf(run, x(j - L));
             left[j] = run;
         }
-        // right extensions: window j additionally covers [n+1, n+j]
-        float right = 0.0f;
+        float prefix = 0.0f;
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-            if (j > 0 && j < valid) right = fmaxf(right, fabsf(in_ring[(size_t)(row0 + t0 + j) * stride]));
-            win[j] = fmaxf(fmaxf(common, left[j]), right);
+            prefix = fmaxf(prefix, x(j));
+            win[j] = fmaxf(left[j], prefix);
         }
     } else {
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < G; ++j) {
             float w = 0.0f;
-            if (j < valid) {
-                for (int m = j - L; m <= j; ++m)
-                    if (n_first + m >= 0) w = fmaxf(w, fabsf(in_ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]));
-            }
+            for (int m = j - L; m <= j; ++m) w = fmaxf(w, x(m));
             win[j] = w;
         }
     }
-    double tgt[G];
+}
+
+AF_HD void limiter_targets(const float* in_ring, size_t stride, int ring_rows, int row0, int t0, int n_first, int valid,
+                           int L, double ceil_lin, double* target_out /* column at t0 */) {
+    constexpr int G = kLimGroup;
+    float win[G];
+    if (valid == G && n_first - L >= 0 && row0 + t0 - L >= 0) {
+        LimiterSpan<true> x{in_ring, in_ring + (size_t)(row0 + t0 - L) * stride, stride, ring_rows, row0, t0, n_first, valid, L};
+        limiter_windows(x, L, win);
+    } else {
+        LimiterSpan<false> x{in_ring, in_ring, stride, ring_rows, row0, t0, n_first, valid, L};
+        limiter_windows(x, L, win);
+    }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        const double peak = (double)win[j];
-        tgt[j] = peak > ceil_lin ? ceil_lin / peak : 1.0;
+        if (j < valid) {
+            const double peak = (double)win[j];
+            target_out[(size_t)j * stride] = peak > ceil_lin ? ceil_lin / peak : 1.0;
+        }
     }
-    store_tile(target_out, stride, valid, tgt);
 }
 
 struct LimiterR {
@@ -478,12 +497,21 @@ template <typename FIR>
 AF_HD void fir_group_peaks(const float* ring, size_t stride, int ring_rows, int row0, int t0, int n_first, int valid,
                            const FIR& fir, float (&peak)[kFirChunk]) {
     float win[kFirWin];
+    if (valid == kFirChunk && n_first >= 31 && row0 + t0 >= 31) {  // whole 39-sample span inside the slot history
+        const float* first = ring + (size_t)(row0 + t0 - 31) * stride;
 #pragma unroll
-    for (int i = 0; i < kFirWin; ++i) {
-        const int m = i - 31;  // sample n_first + m
-        float v = 0.0f;
-        if (n_first + m >= 0 && m < valid) v = ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride];
-        win[i] = af_finite(v) ? v : 0.0f;  // dsp/true_peak.rs:211,343 sanitise
+        for (int i = 0; i < kFirWin; ++i) {
+            const float v = first[(size_t)i * stride];
+            win[i] = af_finite(v) ? v : 0.0f;  // dsp/true_peak.rs:211,343 sanitise
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kFirWin; ++i) {
+            const int m = i - 31;  // sample n_first + m
+            float v = 0.0f;
+            if (n_first + m >= 0 && m < valid) v = ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride];
+            win[i] = af_finite(v) ? v : 0.0f;
+        }
     }
     fir8_peaks(win, fir, peak);
 }

@@ -176,7 +176,7 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         }
         if (a.structure & ST_LIMITER) {
             if (split & 2) {
-                for (int g = n_groups - 1; g >= 0; --g)
+                for (int g = (ck.len + kLimGroup - 1) / kLimGroup; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_lim_m(a, ck, s, g);
                 for (int s = 0; s < S; ++s) body_lim_r(a, ck, s, stg);
             } else {
