@@ -269,7 +269,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         groups[Key(pl.structure, pl.lookahead, pl.input_stage, sweep->pair_len[i])].push_back(static_cast<uint32_t>(i));
     }
     for (auto& kv : groups) {
-        const std::vector<uint32_t>& members = kv.second;
+        // Streams with the same EQ section count share warps: an EQ slice past a warp's last section is skipped
+        // by the whole warp (body_eq returns early), instead of running as a predicated pass-through.
+        std::vector<uint32_t>& members = kv.second;
+        std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) {
+            return plans[candidate_of(x)].params.n_sections < plans[candidate_of(y)].params.n_sections;
+        });
         auto batch = std::make_unique<Batch>();
         BatchArgs& a = batch->args;
         const int S = static_cast<int>(members.size());

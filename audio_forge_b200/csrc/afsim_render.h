@@ -60,6 +60,7 @@ template <int K>
 AF_HD void body_eq(const BatchArgs& a, const ChunkArgs& ck, int s, int first) {
     const size_t stride = (size_t)a.stride;
     const CandidateParams& p = stream_params(a, s);
+    if ((int)p.n_sections <= first) return;  // nothing of this slice in the stream's cascade: samples pass through
     EqStage<K> st;
     st.init(p, first);
     double* table = a.st_eq + (size_t)(kStateEqPerSection * first) * stride + s;
@@ -239,6 +240,15 @@ AF_HD T* col_at(T* ring, const BatchArgs& a, const ChunkArgs& ck, int s, int t0 
     return ring + (size_t)(ck.row0 + t0) * (size_t)a.stride + s;
 }
 
+AF_HD void atomic_max_nonneg(float* addr, float v) {
+    if (!(v == v)) return;  // f32::max ignores NaN
+#if defined(__CUDA_ARCH__)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+#else
+    if (v > *addr) *addr = v;
+#endif
+}
+
 AF_HD void body_comp_r1(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     CompSplit st;
@@ -335,14 +345,6 @@ AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging st
     }
 }
 
-AF_HD void atomic_max_nonneg(float* addr, float v) {
-    if (!(v == v)) return;  // f32::max ignores NaN
-#if defined(__CUDA_ARCH__)
-    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-#else
-    if (v > *addr) *addr = v;
-#endif
-}
 
 // input true peaks of the true-peak limiter: buf_b -> buf_p
 AF_HD void body_tp_fir_in(const BatchArgs& a, const ChunkArgs& ck, int s, int g, const FirTable& fir) {
@@ -350,7 +352,18 @@ AF_HD void body_tp_fir_in(const BatchArgs& a, const ChunkArgs& ck, int s, int g,
     if (!group_span(ck, g, &t0, &valid)) return;
     float pk[kFirChunk];
     fir_group_peaks(a.buf_b + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, fir, pk);
-    store_tile(col_at(a.buf_p, a, ck, s, t0), (size_t)a.stride, valid, pk);
+    // feed-forward part of dsp/true_peak.rs:349-354: the target gain of every sample, and the running
+    // maximum of the input true peak (order independent -> atomic)
+    const float ceil_lin = stream_params(a, s).tp_ceil;
+    float tgt[kFirChunk];
+    float m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kFirChunk; ++j) {
+        tgt[j] = pk[j] > ceil_lin ? clampf((ceil_lin * 0.999f) / pk[j], 0.0f, 1.0f) : 1.0f;
+        if (j < valid) m = fmaxf(m, pk[j]);
+    }
+    store_tile(col_at(a.buf_p, a, ck, s, t0), (size_t)a.stride, valid, tgt);
+    atomic_max_nonneg(&a.accum[s].peak_pre_tp, m);
 }
 AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
@@ -372,7 +385,6 @@ AF_HD void body_tp_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg
         acc.sum_out = st.sum_out;
         acc.peak_out = st.peak_out;
         acc.non_finite = st.non_finite ? 1u : 0u;
-        acc.peak_pre_tp = st.peak_pre;
         acc.tp_gr_db = st.peak_reduction_db();
         acc.events = st.events;
     } else {

@@ -518,7 +518,7 @@ AF_HD void fir_group_peaks(const float* ring, size_t stride, int ring_rows, int 
 
 // ---- true-peak limiter gain recurrence + output statistics (dsp/true_peak.rs:337-378, python_api.rs:529-575) -------
 struct TpR {
-    float g, min_g, peak_pre;
+    float g, min_g;
     uint32_t events;
     bool limited;
     double sum_out, blk_out;
@@ -528,7 +528,6 @@ struct TpR {
     AF_HD void init() {
         g = 1.0f;
         min_g = 1.0f;
-        peak_pre = 0.0f;
         events = 0;
         limited = false;
         sum_out = blk_out = 0.0;
@@ -539,7 +538,6 @@ struct TpR {
     AF_HD void sync(IO& io) {
         io.f32(g);
         io.f32(min_g);
-        io.f32(peak_pre);
         io.u32(events);
         io.flag(limited);
         io.f64(sum_out);
@@ -547,7 +545,7 @@ struct TpR {
         io.f32(peak_out);
         io.flag(non_finite);
     }
-    // itp: input true peaks (column at chunk start); in_ring: limiter output ring (the 20-sample delay
+    // itp: target gains from the input true peaks (column at chunk start); in_ring: limiter output ring (the 20-sample delay
     // reads it); out: column at chunk start; audio: nullable
     AF_HD void run(const float* itp, const float* in_ring, float* out, float* audio, size_t stride, int ring_rows, int row0,
                    int n0, int len, float ceil_lin, float rel, BlockClock clk, float* rows_out, Staging stg) {
@@ -586,8 +584,7 @@ struct TpR {
                 for (int u = 0; u < U; ++u) {
                     y[u] = 0.0f;
                     if (FULL || u < valid) {
-                        peak_pre = fmaxf(peak_pre, pk[u]);
-                        const float target = pk[u] > ceil_lin ? clampf((ceil_lin * 0.999f) / pk[u], 0.0f, 1.0f) : 1.0f;
+                        const float target = pk[u];
                         if (target < g) {
                             g = target;
                             limited = true;
