@@ -134,9 +134,16 @@ int design_eq(const AfBand bands[AFSIM_NUM_BANDS], bool typed, double fs, double
                 }
             } else {
                 const double gain = b.filter_type == AF_NOTCH ? 0.0 : b.gain_db;  // dsp/eq.rs:270-274
-                const int slot = band_major_slots ? static_cast<int>(i) * 4 : n;
-                store(out[slot], design_biquad(kind_of(b.filter_type), b.frequency_hz, gain, b.q, fs));
-                count = 1;
+                const BiquadCoeffs c = design_biquad(kind_of(b.filter_type), b.frequency_hz, gain, b.q, fs);
+                // A flat band (0 dB bell / shelf) designs to b0 == 1, b1 == a1, b2 == a2: DF2T then returns
+                // its input bit for bit and keeps z1 = z2 = 0 for every finite sample, so the render cascade
+                // drops the section (the typed path has no coefficient crossfade that could tell the difference).
+                const bool identity = c.b0 == 1.0 && c.b1 == c.a1 && c.b2 == c.a2;
+                if (band_major_slots || !identity) {
+                    const int slot = band_major_slots ? static_cast<int>(i) * 4 : n;
+                    store(out[slot], c);
+                    count = 1;
+                }
             }
         }
         if (band_sections) band_sections[i] = count;

@@ -69,24 +69,67 @@ def headroom_candidates(n_candidates: int = 4096, seed: int = 1234, **settings_o
     return cands
 
 
-def compressor_grid_candidates(n_thr: int = 16, n_ratio: int = 16, n_attack: int = 8, n_release: int = 8):
-    """C3 (compressor calibration grid) over the search bounds of voice_setup.py:700-705."""
-    total = n_thr * n_ratio * n_attack * n_release
-    cands = (abi.AfCandidate * total)()
+def _grid_shape(n: int) -> tuple[int, int, int, int]:
+    """Threshold x ratio x attack x release counts whose product is n (n a power of two): 16384 -> 16x16x8x8."""
+    dims = [1, 1, 1, 1]
+    k = 0
+    while dims[0] * dims[1] * dims[2] * dims[3] < n:
+        dims[k % 4] *= 2
+        k += 1
+    return tuple(dims)  # type: ignore[return-value]
+
+
+def compressor_grid_candidates(n_candidates: int = 16384, seed: int = 0):
+    """C3 (compressor calibration grid) over the search bounds of voice_setup.py:700-705: threshold [-55,-6] dB,
+    ratio [1.5,6], attack [3,25] ms, release [60,320] ms; adaptive release on; limiter as the search renders it
+    (-1.5 dB, 80 ms, careful; voice_setup.py:802-816); auto-makeup off (voice_setup.py:798-801)."""
+    n_thr, n_ratio, n_attack, n_release = _grid_shape(n_candidates)
+    cands = (abi.AfCandidate * n_candidates)()
     bands = abi.default_bands()
+    rng = np.random.default_rng(seed)
+    jitter = rng.uniform(-0.01, 0.01)
     i = 0
     for thr in np.linspace(-55.0, -6.0, n_thr):
         for ratio in np.linspace(1.5, 6.0, n_ratio):
             for attack in np.linspace(3.0, 25.0, n_attack):
                 for release in np.linspace(60.0, 320.0, n_release):
+                    if i >= n_candidates:
+                        break
                     c = cands[i]
                     for b in range(10):
                         c.bands[b] = bands[b]
-                    c.settings = abi.make_settings(compressor_threshold_db=thr, compressor_ratio=ratio,
-                                                   compressor_attack_ms=attack, compressor_release_ms=release,
+                    c.settings = abi.make_settings(compressor_threshold_db=float(thr) + jitter, compressor_ratio=float(ratio),
+                                                   compressor_attack_ms=float(attack), compressor_release_ms=float(release),
                                                    compressor_adaptive_release=True, limiter_ceiling_db=-1.5,
                                                    limiter_release_ms=80.0)
                     i += 1
+    return cands
+
+
+def true_peak_candidates(n_candidates: int = 1):
+    """C4 (batch true-peak detection + lookahead limiting): flat typed EQ, compressor off, limiter -1.5 dB /
+    50 ms / 2 ms lookahead + true-peak limiter + detector."""
+    cands = (abi.AfCandidate * n_candidates)()
+    bands = abi.default_bands()
+    for i in range(n_candidates):
+        for b in range(10):
+            cands[i].bands[b] = bands[b]
+        cands[i].settings = abi.make_settings(use_typed_bands=True, compressor_enabled=False, limiter_ceiling_db=-1.5,
+                                              limiter_release_ms=50.0, limiter_lookahead_ms=2.0)
+    return cands
+
+
+def full_chain_candidates(n_candidates: int = 8192, seed: int = 0):
+    """C5 (full chain): DC block + 80 Hz high-pass, auto de-esser, typed EQ, compressor, limiter, true peak.
+    (The adaptive hum / harmonic notch cleanup of the live loop is not on the GPU path yet: DESIGN.md section 8.)"""
+    rng = np.random.default_rng(seed)
+    cands = headroom_candidates(n_candidates, seed=seed + 7)
+    for i in range(n_candidates):
+        cands[i].settings = abi.make_settings(
+            use_typed_bands=True, input_stage=1, deesser_enabled=True, deesser_auto_enabled=True,
+            deesser_auto_amount=float(rng.uniform(0.2, 0.9)), deesser_max_reduction_db=float(rng.uniform(4.0, 10.0)),
+            compressor_threshold_db=float(rng.uniform(-35.0, -12.0)), compressor_ratio=float(rng.uniform(2.0, 6.0)),
+            compressor_adaptive_release=bool(i % 2))
     return cands
 
 
@@ -94,3 +137,19 @@ def is_headroom_safe(m: dict) -> bool:
     """headroom.py:278-289."""
     return (m["pre_limiter_true_peak_headroom_db"] >= 1.0 and m["limiter_gain_reduction_db"] <= 1.0
             and m["true_peak_limiter_gain_reduction_db"] <= 0.5)
+
+
+def synthetic_noise_host(passage: int, n: int) -> np.ndarray:
+    """Host copy of the device generator `k_synth` kind 1 (hot white noise, csrc/afsim_kernels.cu): a counter
+    hash per (passage, sample), so any stream of a device-generated batch can be rebuilt for the oracle."""
+    mask = (1 << 64) - 1
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (np.uint64(0x6A09E667F3BCC909) + np.uint64((passage * 0x9E3779B97F4A7C15) & mask)
+             + idx * np.uint64(0xBF58476D1CE4E5B9))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    bits = ((z >> np.uint64(40)) & np.uint64(0xFFFFFF)).astype(np.float32)
+    u = bits / np.float32(16777215.0) * np.float32(2.0) - np.float32(1.0)
+    return (u * np.float32(0.88)).astype(np.float32)

@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- chain-simulator throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
-Workload (N = 1): BASELINE config 2, Auto-EQ headroom validation -- 4096 candidate 10-band typed EQ
-settings (25 % with 48 dB/oct Butterworth pass bands) x one 30 s 48 kHz passage through the full
-chain (EQ -> compressor -> lookahead limiter -> 4x true-peak limiter -> true-peak detector + fused
-score reductions).  A "step" is one pass of that sweep.  N > 1: every rank renders its own 4096
-candidates (weak scaling, candidates x passages sharded, no data-path collective) and the
-per-candidate metric structs are all-gathered with NCCL for the final first-safe-scale pick.
+Workload at N = 1 (default `--workload c2`): BASELINE config 2, Auto-EQ headroom validation -- 4096
+candidate 10-band typed EQ settings (25 % with 48 dB/oct Butterworth pass bands) x one 30 s 48 kHz
+passage through the full chain (EQ -> compressor -> lookahead limiter -> 4x true-peak limiter ->
+true-peak detector + fused score reductions).  A "step" is one pass of that sweep.  N > 1: every rank
+renders its own 4096 candidates (weak scaling; candidates x passages are sharded with no data-path
+collective) and the per-candidate metric structs are all-gathered with NCCL for the final
+first-safe-scale pick.
 
   value      Msamples/s (stream-samples), inputs resident in HBM, CUDA events on the launching stream
   e2e        same metric through the public API with HOST buffers (plan + H2D + render + D2H per step)
-  roofline   dominant stage kernel: algorithmic bytes / its mean launch duration vs measured HBM peak,
-             plus `issue`: its FP64 warp-lane instruction rate vs the DMUL+DADD issue peak measured here
+  roofline   dominant stage kernel: algorithmic bytes / its mean launch duration vs the measured HBM peak,
+             plus `issue`: the FP64 / FP32 issue peaks measured in this run (the chain is issue bound)
   cpu_baseline  the CPU oracle port (the reference's Rust simulator cannot be built here) on all host
-             cores, on a bounded sample of the same workload
+             threads, on a bounded sample of the same workload
 
-`--impl reference` times that CPU port alone (rank 0 only).
+`--impl reference` times that CPU port alone (rank 0 only).  `--workload c3|c4|c5` runs the other
+BASELINE shapes (optionally scaled with --candidates / --passages / --seconds).
 """
 from __future__ import annotations
 
@@ -43,8 +45,20 @@ METRIC = "chain-sim throughput (candidate x passage stream-samples rendered per 
 UNIT = "Msamples/s"
 FS = workloads.FS
 
-# Algorithmic work per stream-sample of each stage: bytes = f32 read + f32 write
-# of the hand-off buffers; fp64 / fp32 = warp-lane arithmetic instructions of the loop body.
+# BASELINE.json configs.  c2 is the one the metric is quoted on at N = 1; the others are parity / scaling shapes.
+WORKLOADS = {
+    "c2": dict(kind="headroom", candidates=4096, passages=1, seconds=30.0, level=0.5,
+               name="C2 auto-eq headroom validation", chain="typed EQ -> compressor -> limiter -> true-peak"),
+    "c3": dict(kind="compressor_grid", candidates=16384, passages=8, seconds=20.0, level=0.6,
+               name="C3 compressor calibration grid", chain="EQ -> compressor (adaptive release) -> limiter -> true-peak"),
+    "c4": dict(kind="true_peak", candidates=1, passages=8192, seconds=60.0, level=1.05,
+               name="C4 batch true-peak detection + lookahead limiting", chain="limiter -> true-peak limiter -> detector"),
+    "c5": dict(kind="full_chain", candidates=8192, passages=8, seconds=10.0, level=0.6,
+               name="C5 full chain with de-esser", chain="DC+HP -> de-esser -> EQ -> compressor -> limiter -> true-peak"),
+}
+
+# Algorithmic bytes per stream-sample of each stage kernel: the f32 / f64 hand-off
+# values it must read and write.
 STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20, "output": 4,
                "comp_r1": 36, "comp_m2": 48, "comp_r3": 32, "comp_m4": 32, "comp_r5": 16, "comp_m6": 16,
                "lim_m": 12, "lim_r": 16, "tp_fir_in": 8, "tp_r": 12, "tp_fir_out": 4}
@@ -56,9 +70,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--candidates", type=int, default=4096)
-    ap.add_argument("--seconds", type=float, default=30.0)
-    ap.add_argument("--cpu-sample-candidates", type=int, default=0, help="0 = 4 per host thread")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config; c2 (the headline, default) fits one GPU")
+    ap.add_argument("--candidates", type=int, default=0, help="override the workload's candidate count")
+    ap.add_argument("--passages", type=int, default=0, help="override the workload's passage count")
+    ap.add_argument("--seconds", type=float, default=0.0, help="override the workload's passage length")
+    ap.add_argument("--cpu-sample-streams", type=int, default=0, help="0 = 4 per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the serialised per-stage timing pass")
     return ap.parse_args()
@@ -95,63 +112,92 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [x for x in (num(r[0]) for r in self.rows if r) if x is not None]
+        mx = [x for x in (num(r[1]) for r in self.rows if len(r) > 1) if x is not None]
+        pw = [x for x in (num(r[2]) for r in self.rows if len(r) > 2) if x is not None]
         reasons = set()
         for r in self.rows:
             for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 def make_workload(args, rank: int):
+    """-> (passages, candidates); the sweep is the full cross product, candidate-major."""
+    spec = WORKLOADS[args.workload]
+    args.candidates = args.candidates or spec["candidates"]
+    args.passages = args.passages or spec["passages"]
+    args.seconds = args.seconds or spec["seconds"]
     n = int(round(args.seconds * FS))
-    passage = workloads.speech_like(n, seed=100 + rank, level=0.5)
-    cands = workloads.headroom_candidates(args.candidates, seed=1234 + rank)
-    return passage, cands
+    passages = [workloads.speech_like(n, seed=100 + 17 * rank + k, level=spec["level"]) for k in range(args.passages)]
+    kind = spec["kind"]
+    if kind == "headroom":
+        cands = workloads.headroom_candidates(args.candidates, seed=1234 + rank)
+    elif kind == "compressor_grid":
+        cands = workloads.compressor_grid_candidates(args.candidates, seed=1234 + rank)
+    elif kind == "true_peak":
+        cands = workloads.true_peak_candidates(args.candidates)
+    else:
+        cands = workloads.full_chain_candidates(args.candidates, seed=1234 + rank)
+    return passages, cands
 
 
-def cpu_port_run(passage, cands, n_sample: int, threads: int):
-    """The oracle port on `threads` host threads over the first n_sample candidates -> (Msamples/s, seconds)."""
+def config_of(args, world: int) -> dict:
+    spec = WORKLOADS[args.workload]
+    return {"workload": spec["name"], "candidates_per_gpu": args.candidates, "passages": args.passages,
+            "seconds": args.seconds, "sample_rate": FS, "chain": spec["chain"],
+            "l2": "the f32/f64 hand-off rings are rewritten every chunk and exceed L2 (tens of MB per chunk per "
+                  "ring); the shared passage is read through L2 by design",
+            "parallelism": (f"candidate x passage streams sharded x{world}, NCCL all-gather of the metric structs"
+                            if world > 1 else "single GPU")}
+
+
+def cpu_port_run(passages, cands, n_sample: int, threads: int):
+    """The oracle port on `threads` host threads over n_sample streams spread over the sweep -> (Msamples/s, s, n)."""
     from oracle import pyoracle
-    sample = (abi.AfCandidate * n_sample).from_buffer(cands)
-    pp = np.zeros(n_sample, dtype=np.uint32)
-    pc = np.arange(n_sample, dtype=np.uint32)
+    n_pass, n_cand = len(passages), len(cands)
+    total = n_pass * n_cand
+    picks = np.unique(np.linspace(0, total - 1, n_sample).astype(np.int64))
+    pp = (picks % n_pass).astype(np.uint32)
+    pc = (picks // n_pass).astype(np.uint32)
     t0 = time.perf_counter()
-    pyoracle.chain_sweep([passage], FS, sample, pp, pc, n_threads=threads)
+    pyoracle.chain_sweep(passages, FS, cands, pp, pc, n_threads=threads)
     dt = time.perf_counter() - t0
-    return n_sample * passage.size / dt / 1e6, dt
+    return picks.size * passages[0].size / dt / 1e6, dt, int(picks.size)
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    passage, cands = make_workload(args, 0)
+    passages, cands = make_workload(args, 0)
     threads = os.cpu_count() or 1
-    n_sample = args.cpu_sample_candidates or min(args.candidates, 2 * threads)
+    n_sample = args.cpu_sample_streams or min(len(passages) * len(cands), 2 * threads)
     for _ in range(min(args.warmup, 1)):
-        cpu_port_run(passage[: int(FS)], cands, min(n_sample, threads), threads)
-    times = []
+        cpu_port_run([p[: int(FS)] for p in passages], cands, min(n_sample, threads), threads)
+    total_s, streams = 0.0, 0
     for _ in range(args.steps):
-        _, dt = cpu_port_run(passage, cands, n_sample, threads)
-        times.append(dt)
-    total = sum(times)
-    value = args.steps * n_sample * passage.size / total / 1e6
-    sample = f"{n_sample} of {args.candidates} candidates x the full {args.seconds:g} s passage per step"
+        _, dt, streams = cpu_port_run(passages, cands, n_sample, threads)
+        total_s += dt
+    value = args.steps * streams * passages[0].size / total_s / 1e6
+    sample = f"{streams} of {len(passages) * len(cands)} streams x the full {args.seconds:g} s passage per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 auto-eq headroom validation", "candidates": args.candidates,
-                   "passages": 1, "seconds": args.seconds, "sample_rate": FS},
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "candidates_per_s": value * 1e6 / passage.size,
-        "note": "CPU oracle port of the reference's Rust chain simulator (no Rust toolchain in the image), one stream per host thread",
+        "candidates_per_s": value * 1e6 / passages[0].size,
+        "note": "CPU oracle port of the reference's Rust chain simulator (no Rust toolchain in the image), one "
+                "stream per host thread",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, rank: int, world: int, local_rank: int):
@@ -166,9 +212,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stream = torch.cuda.Stream(device=local_rank)  # the library launches on it, so torch's events see the work
     torch.cuda.set_stream(stream)
     sim = native.Simulator(local_rank, cuda_stream=stream.cuda_stream)
-    passage, cands = make_workload(args, rank)
-    n_pairs = args.candidates
-    stream_samples = n_pairs * passage.size
+    passages, cands = make_workload(args, rank)
+    n_pairs = len(cands) * len(passages)
+    n_samples = passages[0].size
+    stream_samples = n_pairs * n_samples
 
     def barrier():
         if world > 1:
@@ -176,9 +223,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     # ---- resident sweep: value ------------------------------------------------------------------------
-    sweep = sim.prepare_sweep([passage], FS, cands)
+    sweep = sim.prepare_sweep(passages, FS, cands)
     metrics_bytes = n_pairs * abi.ctypes_sizeof_metrics()
-    gathered = None
+    local = gathered = None
     if world > 1:
         class _DevBytes:  # zero-copy view of the sweep's device metrics (AfChainMetrics[n_pairs])
             __cuda_array_interface__ = {"shape": (metrics_bytes,), "typestr": "|u1", "version": 2,
@@ -188,7 +235,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     def step_resident():
         sweep.launch()
-        if world > 1:  # the only collective on the path: gather of the per-candidate metric structs
+        if world > 1:  # the only collective on the path: gather of the per-stream metric structs
             dist.all_gather_into_tensor(gathered, local)
 
     for _ in range(args.warmup):
@@ -206,16 +253,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     metrics = sweep.collect()
 
     # ---- end to end through the public API with host buffers --------------------------------------------
-    pinned = torch.from_numpy(passage).pin_memory()
-    host_passage = pinned.numpy()
-    h2d = passage.nbytes + len(cands) * abi.ctypes_sizeof_candidate_params()
+    host_passages = [torch.from_numpy(p).pin_memory().numpy() for p in passages]
+    h2d = sum(p.nbytes for p in passages) + len(cands) * abi.ctypes_sizeof_candidate_params()
     d2h = metrics_bytes
-    sim.chain_sweep([host_passage], FS, cands)  # warm-up
+    sim.chain_sweep(host_passages, FS, cands)  # warm-up
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
-        e2e_metrics, _ = sim.chain_sweep([host_passage], FS, cands)
+        sim.chain_sweep(host_passages, FS, cands)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -243,13 +289,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         value = world * stream_samples * args.steps / (ms_total * 1e-3) / 1e6
         e2e_value = world * stream_samples * e2e_steps / e2e_s / 1e6
-        roofline = None
-        stage_table = []
+        roofline, stage_table = None, []
         if stages:
             chunk = int(os.environ.get("AFSIM_CHUNK", "1024"))
-            total_ms = sum(ms for _, ms, _ in stages if _ != "finalize") or 1.0
             render = [(name, ms, n) for name, ms, n in stages if name != "finalize"]
-            merged = {}
+            total_ms = sum(ms for _, ms, _ in render) or 1.0
+            merged: dict = {}
             for name, ms, n in render:
                 m = merged.setdefault(name, [0.0, 0])
                 m[0] += ms
@@ -263,40 +308,51 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             roofline = {"bound": "hbm", "achieved": dominant["GBps"], "peak": hbm_peak, "unit": "GB/s",
                         "frac": dominant["GBps"] / hbm_peak if dominant["GBps"] else None, "traffic": None,
                         "kernel": dominant["stage"], "peak_source": peak_src,
-                        "note": "recurrence kernels are FP64-issue bound, not HBM bound (SURVEY 8(d)); see `issue`",
+                        "timing": "mean launch duration of the stage in a serialised pass (CUDA events around every "
+                                  "launch of 64 chunks); in the timed wavefront the stage kernels overlap",
+                        "note": "the chain is FP64 / FP32 issue bound, not HBM bound (SURVEY 8(d)); see `issue` and profiles/",
                         "issue": {"fp64_peak_ginstr_s": fp64_peak, "fp32_fma_peak_ginstr_s": fp32_peak,
                                   "unit": "1e9 warp-lane instructions/s, measured in this run"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 auto-eq headroom validation", "candidates_per_gpu": args.candidates, "passages": 1,
-                       "seconds": args.seconds, "sample_rate": FS, "chain": "typed EQ -> compressor -> limiter -> true-peak",
-                       "l2": "work buffers are rewritten every chunk (ring of chunks); 5.8 MB passage stays L2 resident by design",
-                       "parallelism": f"candidates sharded x{world}, NCCL all-gather of metric structs" if world > 1 else "single GPU"},
-            "candidates_per_s": value * 1e6 / passage.size,
+            "dtype": "f64", "data": "synthetic", "config": config_of(args, world),
+            "candidates_per_s": value * 1e6 / n_samples,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": roofline,
             "stages": stage_table,
-            "decisions": {"safe_candidates": int(sum(workloads.is_headroom_safe(abi.metrics_to_dict(metrics[i]))
-                                                     for i in range(n_pairs)))},
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if WORKLOADS[args.workload]["kind"] == "headroom":
+            line["decisions"] = {"safe_candidates": int(sum(workloads.is_headroom_safe(abi.metrics_to_dict(metrics[i]))
+                                                            for i in range(n_pairs)))}
+        if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n_sample = args.cpu_sample_candidates or min(args.candidates, 4 * threads)
-            cpu_value, cpu_s = cpu_port_run(passage, cands, n_sample, threads)
+            n_sample = args.cpu_sample_streams or min(n_pairs, 4 * threads)
+            cpu_value, cpu_s, streams = cpu_port_run(passages, cands, n_sample, threads)
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n_sample} of {args.candidates} candidates x the full passage, {cpu_s:.1f} s"}
-        print(json.dumps(line), flush=True)
+                                    "sample": f"{streams} of {n_pairs} streams x the full passage, {cpu_s:.1f} s"}
+        emit(line)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line of the contract, on the real stdout (libraries such as NCCL print banners on fd 1)."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # anything else written to fd 1 from here on goes to stderr
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
