@@ -243,6 +243,9 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
     double* d_eq_default = nullptr;
     AF_CUDA(h, sweep->mem.alloc(&d_eq_default, 50));
     AF_CUDA(h, cudaMemcpyAsync(d_eq_default, rate.eq_default, sizeof rate.eq_default, cudaMemcpyHostToDevice, h->stream));
+    CleanupConst* d_cleanup = nullptr;
+    AF_CUDA(h, sweep->mem.alloc(&d_cleanup, 1));
+    AF_CUDA(h, cudaMemcpyAsync(d_cleanup, &rate.cleanup, sizeof rate.cleanup, cudaMemcpyHostToDevice, h->stream));
     AF_CUDA(h, cudaStreamSynchronize(h->stream));
 
     AF_CUDA(h, sweep->mem.alloc(&sweep->d_metrics, n_pairs));
@@ -295,6 +298,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         a.signals = d_signals;
         a.audio = sweep->d_audio;
         a.eq_default = d_eq_default;
+        a.cleanup = d_cleanup;
         a.metrics = sweep->d_metrics;
 
         // chunking: a multiple of 8 (true-peak FIR groups) and of the compressor micro-tile, long
@@ -302,6 +306,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         int chunk = env_int("AFSIM_CHUNK", 1024);
         chunk = std::max(chunk, std::max(rate.fade_samples, a.lookahead + 1));
         chunk = round_up(chunk, 8);
+        if (a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG)
+            chunk = round_up(chunk, kInputBlock);  // the cleanup stage works in whole 480-sample blocks
         batch->chunk = chunk;
         const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
         // ring slots = chunks in flight + 1; few-stream batches need the stage wavefront to fill the GPU

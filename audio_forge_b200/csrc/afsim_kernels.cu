@@ -37,6 +37,13 @@ __global__ void __launch_bounds__(128) k_input(BatchArgs a, ChunkArgs ck) {
     body_input(a, ck, s);
 }
 
+// Input stage with the adaptive hum / rumble cleanup (afsim_cleanup.h): its own kernel, because its 26 phasor
+// bins want ~250 registers and must not cost the plain input kernel its occupancy.
+__global__ void __launch_bounds__(128) k_input_cleanup(BatchArgs a, ChunkArgs ck) {
+    AF_STREAM_INDEX();
+    body_input_cleanup(a, ck, s);
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) k_eq(BatchArgs a, ChunkArgs ck, int first) {
     AF_STREAM_INDEX();
@@ -227,7 +234,10 @@ cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int b = pick_block(a);
-    k_input<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    if (input_uses_cleanup(a))
+        k_input_cleanup<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    else
+        k_input<<<stream_grid(a, b), b, 0, st>>>(a, ck);
     return cudaGetLastError();
 }
 cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first, int k, cudaStream_t st) {

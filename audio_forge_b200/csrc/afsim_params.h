@@ -108,7 +108,7 @@ struct StreamAccum {
 };
 
 // Slots (doubles per stream) of the per-stage state tables.
-constexpr int kStateInput = 48;
+constexpr int kStateInput = 256;  // 7 (sanitize / DC / statistics) + the adaptive cleanup stage (afsim_cleanup.h)
 constexpr int kStateDeEsser = 96;
 constexpr int kStateEqPerSection = 2;
 constexpr int kStateCompressor = 12;
@@ -140,6 +140,7 @@ struct BatchArgs {
     StreamAccum* accum;           // [S_pad]
     const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
     const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)
+    const struct CleanupConst* cleanup;  // sample-rate constants of the adaptive input cleanup (afsim_cleanup.h)
     void* metrics;                // AfChainMetrics[n_pairs of the sweep], indexed by pair[s]
     float* fin_scratch;           // per-block finalize workspace when it does not fit shared memory
     int n_streams;                // S

@@ -325,6 +325,45 @@ RateConstants rate_constants(double fs) {
     rc.fade_samples = std::isfinite(fade) ? static_cast<int>(std::clamp<size_t>(as_usize(fade), 1, 4096)) : 1;
     for (size_t i = 0; i < 10; ++i)
         store(rc.eq_default[i], design_biquad(default_kind(i), kDefaultFrequencies[i], 0.0, kDefaultQ, fs));
+    // adaptive input cleanup (audio/processor/routing.rs): everything below is f32 like the reference
+    CleanupConst& k = rc.cleanup;
+    const float pi = 3.14159265358979323846f;
+    const float fsf = static_cast<float>(fs);
+    k.fs = fsf;
+    k.lowpass_coeff = rclampf(2.0f * pi * 150.0f / fsf, 0.0f, 1.0f);                 // routing.rs:341
+    for (int i = 0; i < kHumBins; ++i) {
+        for (int h = 0; h < 2; ++h) {                                                // HumBin::new, routing.rs:64-76
+            const float f = (h == 0 ? 1.0f : 2.0f) * (49.0f + static_cast<float>(i) * 1.0f);
+            const float omega = 2.0f * pi * f / std::fmax(fsf, 1.0f);
+            k.bin_cos[h * kHumBins + i] = std::cos(omega);
+            k.bin_sin[h * kHumBins + i] = std::sin(omega);
+        }
+    }
+    for (int h = 0; h < 2; ++h) {                                                    // NotchFilter::new, routing.rs:117-140
+        const float f = h == 0 ? 55.0f : 110.0f;
+        const float omega = 2.0f * pi * f / std::fmax(fsf, 1.0f);
+        const float sn = std::sin(omega), cs = std::cos(omega);
+        const float alpha = sn / (2.0f * std::fmax(36.0f, 1.0f));
+        const float a0 = 1.0f + alpha;
+        k.notch0[h][0] = 1.0f / a0;
+        k.notch0[h][1] = -2.0f * cs / a0;
+        k.notch0[h][2] = 1.0f / a0;
+        k.notch0[h][3] = -2.0f * cs / a0;
+        k.notch0[h][4] = (1.0f - alpha) / a0;
+    }
+    const double hp_hz[3] = {80.0, 100.0, 120.0};                                    // routing.rs:539-547
+    for (int i = 0; i < 3; ++i) store(k.hp[i], design_biquad(BqKind::HighPass, hp_hz[i], 0.0, 0.707, static_cast<double>(fsf)));
+    auto as_u32 = [](float v) -> uint32_t {
+        if (!(v > 0.0f)) return 0;
+        if (v >= 4294967296.0f) return 0xffffffffu;
+        return static_cast<uint32_t>(v);
+    };
+    k.window_samples = static_cast<int>(as_usize(static_cast<double>(std::fmax(std::round(fsf * 0.25f), 1.0f))));
+    k.notch_fade_total = static_cast<int>(as_usize(static_cast<double>(std::fmax(std::round(fsf * 0.020f), 1.0f))));
+    k.hp_fade_total = rc.fade_samples;
+    k.rumble_hold_gentle = as_u32(std::round(fsf * 0.18f));
+    k.rumble_hold_strong = as_u32(std::round(fsf * 0.30f));
+    k.hum_hold = as_u32(std::round(fsf * 0.75f));
     return rc;
 }
 
@@ -378,8 +417,6 @@ int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& s
         if (rc != AFSIM_OK) return rc;
     }
     if (s.input_stage > AF_INPUT_CLEANUP_STRONG) return fail(error, AFSIM_INVALID_ARGUMENT, "unknown input_stage");
-    if (s.input_stage == AF_INPUT_CLEANUP_GENTLE || s.input_stage == AF_INPUT_CLEANUP_STRONG)
-        return fail(error, AFSIM_UNSUPPORTED, "adaptive input cleanup (hum / rumble) is not available on the GPU path yet");
     if (s.compressor_enabled && s.compressor_auto_makeup_enabled && loudness_meter_supports(fs))
         return fail(error, AFSIM_UNSUPPORTED,
                     "compressor auto makeup (ebur128 momentary loudness) is not available on the GPU path yet");

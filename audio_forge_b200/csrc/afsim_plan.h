@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/afsim.h"
+#include "afsim_cleanup.h"
 #include "afsim_params.h"
 
 namespace afsim {
@@ -32,6 +33,7 @@ struct RateConstants {
     int block_samples;            // python_api.rs:512-513
     int fade_samples;             // dsp/biquad.rs:12-19
     double eq_default[10][5];     // constructor coefficients of the 10 default bands (dsp/eq.rs:125-140)
+    CleanupConst cleanup;         // adaptive input cleanup constants (audio/processor/routing.rs:55-330)
 };
 
 // Fills `out`; returns AFSIM_OK or a status with the reference's message in *error.

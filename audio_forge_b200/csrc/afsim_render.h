@@ -8,6 +8,7 @@
 // Reference citations are relative to rust-core/src/.
 #pragma once
 #include "../../include/afsim.h"
+#include "afsim_cleanup.h"
 #include "afsim_split.h"
 
 namespace afsim {
@@ -23,6 +24,72 @@ typedef float FirTable[4][32];
 AF_HD const CandidateParams& stream_params(const BatchArgs& a, int s) { return a.params[a.cand[s]]; }
 
 // ---- input -------------------------------------------------------------------------------------------------
+// Adaptive cleanup (AF_INPUT_CLEANUP_*): per 480-sample block, analyse the raw block, then DC block + notches
+// + adaptive high-pass (processor/tests.rs:500-549).  Chunks are multiples of 480 in this mode.
+AF_HD void body_input_cleanup(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride;
+    const CleanupConst& k = *a.cleanup;
+    const bool gentle = a.input_stage == AF_INPUT_CLEANUP_GENTLE;
+    InputStage st;
+    CleanupStage cl;
+    if (ck.n0 == 0) {
+        st.init();
+        cl.init(k);
+    } else {
+        StateIO<false> io{a.st_input + s, stride};
+        st.sync(io);
+        cl.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const Col out{a.buf_a + (size_t)ck.row0 * stride + s, stride};
+    const float* src = a.signals + a.src_off[s];
+    float* rows_in = a.rows + s;
+    for (int b0 = 0; b0 < ck.len; b0 += kInputBlock) {
+        const int blen = ck.len - b0 < kInputBlock ? ck.len - b0 : kInputBlock;
+        for (int t = 0; t < blen; ++t) {  // analyze_input on the raw (sanitised) block
+            float v = src[ck.n0 + b0 + t];
+            if (!af_finite(v)) v = 0.0f;
+            out.set(b0 + t, v);
+            cl.analyze(v, k, gentle);
+        }
+        bool hum_detected;
+        cl.begin_block(k, gentle, &hum_detected);
+        for (int t = 0; t < blen; ++t) {
+            const int n = ck.n0 + b0 + t;
+            const float in = out.get(b0 + t);
+            const float dc = in - st.x1 + 0.995f * st.y1;  // routing.rs:832-836 (no fixed high-pass in this mode)
+            st.x1 = in;
+            st.y1 = dc;
+            float v = cl.process(dc, k);
+            if (!af_finite(v)) v = 0.0f;
+            const double sq = (double)v * (double)v;
+            st.sum_in += sq;
+            st.blk_in += sq;
+            st.peak_in = fmaxf(st.peak_in, fabsf(v));
+            out.set(b0 + t, v);
+            if (clk.at_end(n)) {
+                const float rms = (float)sqrt(st.blk_in / (double)clk.block_len(n));
+                rows_in[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                st.blk_in = 0.0;
+                clk.advance();
+            }
+        }
+    }
+    if (ck.n0 + ck.len >= a.n_samples) {
+        a.accum[s].sum_in = st.sum_in;
+        a.accum[s].peak_in = st.peak_in;
+    } else {
+        StateIO<true> io{a.st_input + s, stride};
+        st.sync(io);
+        cl.sync(io);
+    }
+}
+
+AF_HD bool input_uses_cleanup(const BatchArgs& a) {
+    return a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG;
+}
+
 AF_HD void body_input(const BatchArgs& a, const ChunkArgs& ck, int s) {
     const size_t stride = (size_t)a.stride;
     InputStage st;

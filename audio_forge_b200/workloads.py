@@ -120,13 +120,13 @@ def true_peak_candidates(n_candidates: int = 1):
 
 
 def full_chain_candidates(n_candidates: int = 8192, seed: int = 0):
-    """C5 (full chain): DC block + 80 Hz high-pass, auto de-esser, typed EQ, compressor, limiter, true peak.
-    (The adaptive hum / harmonic notch cleanup of the live loop is not on the GPU path yet: DESIGN.md section 8.)"""
+    """C5 (full chain): adaptive input cleanup (49-61 Hz hum / harmonic notches, Strong), auto de-esser, typed EQ,
+    compressor, limiter, true peak."""
     rng = np.random.default_rng(seed)
     cands = headroom_candidates(n_candidates, seed=seed + 7)
     for i in range(n_candidates):
         cands[i].settings = abi.make_settings(
-            use_typed_bands=True, input_stage=1, deesser_enabled=True, deesser_auto_enabled=True,
+            use_typed_bands=True, input_stage=3, deesser_enabled=True, deesser_auto_enabled=True,
             deesser_auto_amount=float(rng.uniform(0.2, 0.9)), deesser_max_reduction_db=float(rng.uniform(4.0, 10.0)),
             compressor_threshold_db=float(rng.uniform(-35.0, -12.0)), compressor_ratio=float(rng.uniform(2.0, 6.0)),
             compressor_adaptive_release=bool(i % 2))
@@ -137,6 +137,14 @@ def is_headroom_safe(m: dict) -> bool:
     """headroom.py:278-289."""
     return (m["pre_limiter_true_peak_headroom_db"] >= 1.0 and m["limiter_gain_reduction_db"] <= 1.0
             and m["true_peak_limiter_gain_reduction_db"] <= 0.5)
+
+
+def add_hum(x: np.ndarray, hum_hz: float = 50.37, level_db: float = -26.0, fs: float = FS) -> np.ndarray:
+    """Mains hum + second harmonic injected at level_db dBFS."""
+    t = np.arange(x.size, dtype=np.float64) / fs
+    a = 10.0 ** (level_db / 20.0)
+    y = x.astype(np.float64) + a * np.sin(2.0 * np.pi * hum_hz * t) + 0.5 * a * np.sin(2.0 * np.pi * 2.0 * hum_hz * t + 0.3)
+    return y.astype(np.float32)
 
 
 def synthetic_noise_host(passage: int, n: int) -> np.ndarray:

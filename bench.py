@@ -54,7 +54,7 @@ WORKLOADS = {
     "c4": dict(kind="true_peak", candidates=1, passages=8192, seconds=60.0, level=1.05,
                name="C4 batch true-peak detection + lookahead limiting", chain="limiter -> true-peak limiter -> detector"),
     "c5": dict(kind="full_chain", candidates=8192, passages=8, seconds=10.0, level=0.6,
-               name="C5 full chain with de-esser", chain="DC+HP -> de-esser -> EQ -> compressor -> limiter -> true-peak"),
+               name="C5 full chain with de-esser", chain="hum/harmonic notch cleanup -> de-esser -> EQ -> compressor -> limiter -> true-peak"),
 }
 
 # Algorithmic bytes per stream-sample of each stage kernel: the f32 / f64 hand-off
@@ -138,6 +138,8 @@ def make_workload(args, rank: int):
     n = int(round(args.seconds * FS))
     passages = [workloads.speech_like(n, seed=100 + 17 * rank + k, level=spec["level"]) for k in range(args.passages)]
     kind = spec["kind"]
+    if kind == "full_chain":  # config 5: mains hum + harmonic injected at -26 dBFS
+        passages = [workloads.add_hum(p, 50.37 + 0.11 * k) for k, p in enumerate(passages)]
     if kind == "headroom":
         cands = workloads.headroom_candidates(args.candidates, seed=1234 + rank)
     elif kind == "compressor_grid":

@@ -78,6 +78,8 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     while (a.n_pad < a.n_rows) a.n_pad <<= 1;
     chunk = std::max(chunk, std::max(rate.fade_samples, a.lookahead + 1));
     chunk = (chunk + 7) / 8 * 8;
+    if (a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG)
+        chunk = (chunk + kInputBlock - 1) / kInputBlock * kInputBlock;
     slots = std::max(slots, 2);
     a.ring_rows = slots * chunk;
 
@@ -125,6 +127,7 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     a.rows = rows.data();
     a.accum = accum.data();
     a.eq_default = &rate.eq_default[0][0];
+    a.cleanup = &rate.cleanup;
     a.de_tab = de_tab.data();
     a.metrics = metrics.data();
 
@@ -147,7 +150,12 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         ck.n0 = c * chunk;
         ck.len = std::min(chunk, T - ck.n0);
         ck.row0 = (c % slots) * chunk;
-        for (int s = 0; s < S; ++s) body_input(a, ck, s);
+        for (int s = 0; s < S; ++s) {
+            if (input_uses_cleanup(a))
+                body_input_cleanup(a, ck, s);
+            else
+                body_input(a, ck, s);
+        }
         if (a.structure & ST_EQ_BEFORE_DEESSER) {
             run_eq(ck);
             if (a.structure & ST_DEESSER)

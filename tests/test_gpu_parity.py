@@ -180,3 +180,29 @@ def test_reference_python_door(sim):
     for key in ("pre_limiter_true_peak_headroom_db", "limiter_gain_reduction_db", "true_peak_limiter_gain_reduction_db"):
         assert abs(want[key] - result[key]) <= TOL_DB
     assert result["limiter_gain_reduction_db"] > 1.0  # +9 dB at 5 kHz on a 0.62 sine engages the limiter
+
+
+def _hum_signal(n, hum_hz=50.37, level=0.1, seed=9):
+    """Speech-like passage + mains hum and its second harmonic + a rumble burst."""
+    x = speech_like(n, seed=seed, level=0.5).astype(np.float64)
+    t = np.arange(n) / FS
+    x += level * np.sin(2 * np.pi * hum_hz * t) + 0.5 * level * np.sin(2 * np.pi * 2 * hum_hz * t + 0.3)
+    burst = (t > 1.6) & (t < 1.9)
+    x += burst * 0.6 * np.sin(2 * np.pi * 31.0 * t)
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("path", ["fused", "split"])
+@pytest.mark.parametrize("mode", ["gentle", "strong"])
+def test_adaptive_input_cleanup_matches_oracle(sim, mode, path, monkeypatch):
+    """49-61 Hz hum tracker + hum / harmonic notches + rumble-adaptive high-pass (routing.rs:55-648) in front of
+    the chain.  f32 throughout; only atan2f / logf at window ends and sinf / cosf at notch retunes use the device
+    libm, so the render stays inside the sample tolerance."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
+    x = _hum_signal(3 * 48000)
+    bands, overrides = CASES["golden_like"]
+    settings = abi.make_settings(**dict(overrides, input_stage=mode))
+    m0, a0, _ = pyoracle.chain_render(x, FS, bands, settings, return_audio=True)
+    m1, a1 = sim.chain_render(x, FS, bands, settings, return_audio=True)
+    assert audio_within_tolerance(a0, a1) <= 0.0
+    assert metric_mismatches(m0, m1, tol_db=TOL_DB) == {}

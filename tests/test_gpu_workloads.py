@@ -80,8 +80,9 @@ def test_c4_batch_true_peak_device_generated(sim):
 
 
 def test_c5_full_chain_with_deesser_fused_path(sim):
-    """2560 candidates x 8 passages = 20480 streams x 0.5 s: DC+HP -> de-esser -> typed EQ -> compressor -> limiter -> TP."""
-    passages = [workloads.speech_like(24000, seed=500 + k, level=0.6) for k in range(8)]
+    """2560 candidates x 8 passages = 20480 streams x 1 s: hum cleanup -> de-esser -> typed EQ -> compressor -> limiter -> TP."""
+    passages = [workloads.add_hum(workloads.speech_like(48000, seed=500 + k, level=0.6), 50.37 + 0.11 * k, level_db=-20.0)
+                for k in range(8)]
     cands = workloads.full_chain_candidates(2560)
     metrics, _ = sim.chain_sweep(passages, FS, cands)
     _check_sample(passages, cands, metrics, 24, seed=2)

@@ -95,3 +95,34 @@ def test_other_sample_rates():
                                         want_audio=True)
         assert np.array_equal(a0, a1[0]), fs
         assert metric_mismatches(m0, m1[0]) == {}, fs
+
+
+def _hum_signal(n, hum_hz=50.37, level=0.1, seed=9):
+    """Speech-like passage + mains hum and its second harmonic at -26 dBFS + a rumble burst."""
+    x = speech_like(n, seed=seed, level=0.5).astype(np.float64)
+    t = np.arange(n) / FS
+    x += level * np.sin(2 * np.pi * hum_hz * t) + 0.5 * level * np.sin(2 * np.pi * 2 * hum_hz * t + 0.3)
+    burst = (t > 1.6) & (t < 1.9)
+    x += burst * 0.6 * np.sin(2 * np.pi * 31.0 * t)
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["gentle", "strong"])
+@pytest.mark.parametrize("schedule", [(960, 2, 0), (2000, 3, 7)])
+def test_adaptive_input_cleanup_bit_exact_with_oracle(mode, schedule):
+    """Hum tracker + notches + rumble-adaptive high-pass (routing.rs:55-648) in front of the chain."""
+    x = _hum_signal(3 * 48000)
+    bands, overrides = CASES["legacy_eq"]
+    overrides = dict(overrides, input_stage=mode)
+    m0, a0, r0 = pyoracle.chain_render(x, FS, bands, abi.make_settings(**overrides), return_audio=True, return_rows=True)
+    chunk, slots, split = schedule
+    m1, a1, r1 = hostsim.chain_sweep([x], FS, candidate_array([candidate(bands, **overrides)]), [0], [0], chunk=chunk,
+                                     slots=slots, split=split, want_audio=True, want_rows=True)
+    assert np.array_equal(a0, a1[0])
+    assert np.array_equal(r0, r1[:, :, 0].T)
+    assert metric_mismatches(m0, m1[0]) == {}
+    # the stage really engaged on this signal: the oracle's tracker locked onto the 50.37 Hz line
+    info = np.zeros(4, dtype=np.float32)
+    y = x.copy()
+    pyoracle.lib().orc_input_stage_process(2 if mode == "gentle" else 3, FS, pyoracle.fptr(y), y.size, pyoracle.fptr(info))
+    assert info[1] == 1.0 and abs(float(info[0]) - 50.37) < 0.8  # routing.rs:616-641 tolerance
