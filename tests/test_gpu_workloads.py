@@ -76,7 +76,7 @@ def test_c4_batch_true_peak_device_generated(sim):
     limited = np.array([metrics[i].limiter_gain_reduction_db for i in range(n_streams)])
     sample_peaks = np.array([metrics[i].output_sample_peak_db for i in range(n_streams)])
     assert np.all(np.isfinite(peaks)) and np.all(sample_peaks <= -1.5 + 1e-3)  # the hard ceiling clamp always holds
-    assert np.all(limited > 0.5)             # ~5 % of the samples exceed the ceiling: every stream is limited
+    assert np.all(limited > 0.3)             # noise peaks at 0.88 vs the 0.841 ceiling: every stream is limited by ~0.39 dB
 
 
 def test_c5_full_chain_with_deesser_fused_path(sim):
