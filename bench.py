@@ -136,8 +136,12 @@ def make_workload(args, rank: int):
     args.passages = args.passages or spec["passages"]
     args.seconds = args.seconds or spec["seconds"]
     n = int(round(args.seconds * FS))
-    passages = [workloads.speech_like(n, seed=100 + 17 * rank + k, level=spec["level"]) for k in range(args.passages)]
     kind = spec["kind"]
+    if kind == "true_peak" and args.passages * n * 4 > (8 << 30):
+        # config 4 at full size is 94 GB of input: generated on the device (afsim_sweep_prepare_synthetic); only the
+        # few streams the CPU checks are rebuilt on the host from the same counter hash
+        return DeviceNoise(args.passages, n), workloads.true_peak_candidates(args.candidates)
+    passages = [workloads.speech_like(n, seed=100 + 17 * rank + k, level=spec["level"]) for k in range(args.passages)]
     if kind == "full_chain":  # config 5: mains hum + harmonic injected at -26 dBFS
         passages = [workloads.add_hum(p, 50.37 + 0.11 * k) for k, p in enumerate(passages)]
     if kind == "headroom":
@@ -149,6 +153,19 @@ def make_workload(args, rank: int):
     else:
         cands = workloads.full_chain_candidates(args.candidates, seed=1234 + rank)
     return passages, cands
+
+
+class DeviceNoise:
+    """Stand-in for a list of passages that only exist on the device (hot white noise, workloads.synthetic_noise_host)."""
+
+    def __init__(self, n_passages: int, n_samples: int):
+        self.n_passages, self.n_samples = n_passages, n_samples
+
+    def __len__(self):
+        return self.n_passages
+
+    def __getitem__(self, i):
+        return workloads.synthetic_noise_host(i, self.n_samples)
 
 
 def config_of(args, world: int) -> dict:
@@ -167,12 +184,15 @@ def cpu_port_run(passages, cands, n_sample: int, threads: int):
     n_pass, n_cand = len(passages), len(cands)
     total = n_pass * n_cand
     picks = np.unique(np.linspace(0, total - 1, n_sample).astype(np.int64))
-    pp = (picks % n_pass).astype(np.uint32)
+    used = sorted({int(i % n_pass) for i in picks})  # materialise only the passages the sample touches
+    local = {p: k for k, p in enumerate(used)}
+    host = [passages[p] for p in used]
+    pp = np.array([local[int(i % n_pass)] for i in picks], dtype=np.uint32)
     pc = (picks // n_pass).astype(np.uint32)
     t0 = time.perf_counter()
-    pyoracle.chain_sweep(passages, FS, cands, pp, pc, n_threads=threads)
+    pyoracle.chain_sweep(host, FS, cands, pp, pc, n_threads=threads)
     dt = time.perf_counter() - t0
-    return picks.size * passages[0].size / dt / 1e6, dt, int(picks.size)
+    return picks.size * host[0].size / dt / 1e6, dt, int(picks.size)
 
 
 def run_reference(args, rank: int):
@@ -182,12 +202,13 @@ def run_reference(args, rank: int):
     threads = os.cpu_count() or 1
     n_sample = args.cpu_sample_streams or min(len(passages) * len(cands), 2 * threads)
     for _ in range(min(args.warmup, 1)):
-        cpu_port_run([p[: int(FS)] for p in passages], cands, min(n_sample, threads), threads)
+        cpu_port_run([passages[i][: int(FS)] for i in range(min(len(passages), 4))], cands, min(n_sample, threads), threads)
     total_s, streams = 0.0, 0
     for _ in range(args.steps):
         _, dt, streams = cpu_port_run(passages, cands, n_sample, threads)
         total_s += dt
-    value = args.steps * streams * passages[0].size / total_s / 1e6
+    n_samples = passages.n_samples if isinstance(passages, DeviceNoise) else passages[0].size
+    value = args.steps * streams * n_samples / total_s / 1e6
     sample = f"{streams} of {len(passages) * len(cands)} streams x the full {args.seconds:g} s passage per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -195,7 +216,7 @@ def run_reference(args, rank: int):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "candidates_per_s": value * 1e6 / passages[0].size,
+        "candidates_per_s": value * 1e6 / n_samples,
         "note": "CPU oracle port of the reference's Rust chain simulator (no Rust toolchain in the image), one "
                 "stream per host thread",
     }
@@ -215,8 +236,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_stream(stream)
     sim = native.Simulator(local_rank, cuda_stream=stream.cuda_stream)
     passages, cands = make_workload(args, rank)
+    on_device = isinstance(passages, DeviceNoise)
     n_pairs = len(cands) * len(passages)
-    n_samples = passages[0].size
+    n_samples = passages.n_samples if on_device else passages[0].size
     stream_samples = n_pairs * n_samples
 
     def barrier():
@@ -225,7 +247,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     # ---- resident sweep: value ------------------------------------------------------------------------
-    sweep = sim.prepare_sweep(passages, FS, cands)
+    if on_device:
+        sweep = sim.prepare_synthetic_sweep(1, len(passages), n_samples, FS, cands)
+    else:
+        sweep = sim.prepare_sweep(passages, FS, cands)
     metrics_bytes = n_pairs * abi.ctypes_sizeof_metrics()
     local = gathered = None
     if world > 1:
@@ -255,17 +280,30 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     metrics = sweep.collect()
 
     # ---- end to end through the public API with host buffers --------------------------------------------
-    host_passages = [torch.from_numpy(p).pin_memory().numpy() for p in passages]
-    h2d = sum(p.nbytes for p in passages) + len(cands) * abi.ctypes_sizeof_candidate_params()
-    d2h = metrics_bytes
-    sim.chain_sweep(host_passages, FS, cands)  # warm-up
-    barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        sim.chain_sweep(host_passages, FS, cands)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    d2h = metrics_bytes
+    if on_device:
+        # no host copy of a 94 GB batch exists: the end-to-end leg covers generate-on-device + render + D2H metrics
+        h2d = len(cands) * abi.ctypes_sizeof_candidate_params()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            s2 = sim.prepare_synthetic_sweep(1, len(passages), n_samples, FS, cands)
+            s2.launch()
+            s2.collect()
+            s2.release()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    else:
+        host_passages = [torch.from_numpy(p).pin_memory().numpy() for p in passages]
+        h2d = sum(p.nbytes for p in passages) + len(cands) * abi.ctypes_sizeof_candidate_params()
+        sim.chain_sweep(host_passages, FS, cands)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sim.chain_sweep(host_passages, FS, cands)
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     # ---- per-stage timing (serialised pass) + issue peaks --------------------------------------------------
     stages, fp64_peak, fp32_peak = [], None, None
