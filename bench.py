@@ -279,6 +279,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     launches = sweep.kernel_count * args.steps
     metrics = sweep.collect()
 
+    # ---- per-stage timing (serialised pass) + issue peaks --------------------------------------------------
+    stages, fp64_peak, fp32_peak = [], None, None
+    if rank == 0 and not args.no_profile:
+        stages = sweep.profile_stages(max_chunks=64)
+        fp64_peak = sim.issue_peak(0)
+        fp32_peak = sim.issue_peak(1)
+    sweep.release()
+
     # ---- end to end through the public API with host buffers --------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     d2h = metrics_bytes
@@ -304,14 +312,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             sim.chain_sweep(host_passages, FS, cands)
         barrier()
         e2e_s = time.perf_counter() - t0
-
-    # ---- per-stage timing (serialised pass) + issue peaks --------------------------------------------------
-    stages, fp64_peak, fp32_peak = [], None, None
-    if rank == 0 and not args.no_profile:
-        stages = sweep.profile_stages(max_chunks=64)
-        fp64_peak = sim.issue_peak(0)
-        fp32_peak = sim.issue_peak(1)
-    sweep.release()
 
     # ---- reductions over ranks ----------------------------------------------------------------------------
     t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
