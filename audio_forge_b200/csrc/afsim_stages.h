@@ -176,31 +176,57 @@ struct InputStage {
     }
     // rows_in: row.0 table of this stream, element b at rows_in[b * stride]
     template <bool DC_HP>
+    AF_HD void step(float v, int t, int n, const Col& out, const Bq& hp, BlockClock& clk, float* rows_in, size_t stride,
+                    bool may_end) {
+        if (!af_finite(v)) v = 0.0f;
+        if (DC_HP) {
+            const float dc = v - x1 + 0.995f * y1;
+            x1 = v;
+            y1 = dc;
+            v = (float)bq_step((double)dc, hp, z1, z2);
+            if (!af_finite(v)) v = 0.0f;  // python_api.rs:517-520 runs after the input stage
+        }
+        const double sq = (double)v * (double)v;
+        sum_in += sq;
+        blk_in += sq;
+        peak_in = fmaxf(peak_in, fabsf(v));
+        out.set(t, v);
+        if (may_end && clk.at_end(n)) {
+            const float rms = (float)sqrt(blk_in / (double)clk.block_len(n));
+            rows_in[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+            blk_in = 0.0;
+            clk.advance();
+        }
+    }
+
+    // Register tiles of 8 samples with the next tile's loads issued first: the source is read straight from HBM
+    // (a stream's own 32-byte sector per tile when every stream has its own passage, a broadcast line when the
+    // streams share one), and with one warp per SM only loads in flight hide that latency.
+    template <bool DC_HP>
     AF_HD void run(const float* src, const Col& out, int n0, int len, const Bq& hp, BlockClock clk, float* rows_in,
                    size_t stride) {
-        for (int t = 0; t < len; ++t) {
-            const int n = n0 + t;
-            float v = src[n];
-            if (!af_finite(v)) v = 0.0f;
-            if (DC_HP) {
-                const float dc = v - x1 + 0.995f * y1;
-                x1 = v;
-                y1 = dc;
-                v = (float)bq_step((double)dc, hp, z1, z2);
-                if (!af_finite(v)) v = 0.0f;  // python_api.rs:517-520 runs after the input stage
+        constexpr int U = 8;
+        const float* p = src + n0;
+        float nxt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) nxt[u] = u < len ? p[u] : 0.0f;
+        int t0 = 0;
+        for (; t0 + U <= len; t0 += U) {
+            float x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = nxt[u];
+            if (t0 + 2 * U <= len) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = p[t0 + U + u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = t0 + U + u < len ? p[t0 + U + u] : 0.0f;
             }
-            const double sq = (double)v * (double)v;
-            sum_in += sq;
-            blk_in += sq;
-            peak_in = fmaxf(peak_in, fabsf(v));
-            out.set(t, v);
-            if (clk.at_end(n)) {
-                const float rms = (float)sqrt(blk_in / (double)clk.block_len(n));
-                rows_in[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
-                blk_in = 0.0;
-                clk.advance();
-            }
+            const bool may_end = !clk.ends_after(n0 + t0, U);
+#pragma unroll
+            for (int u = 0; u < U; ++u) step<DC_HP>(x[u], t0 + u, n0 + t0 + u, out, hp, clk, rows_in, stride, may_end);
         }
+        for (int u = 0; t0 + u < len; ++u) step<DC_HP>(nxt[u], t0 + u, n0 + t0 + u, out, hp, clk, rows_in, stride, true);
     }
 };
 
