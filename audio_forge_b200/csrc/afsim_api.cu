@@ -363,8 +363,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
             }
         }
-        if (split && (a.structure & (ST_LIMITER | ST_COMPRESSOR))) {
-            const int n_w = (a.structure & ST_COMPRESSOR) ? 4 : 1;
+        a.stage_inputs = split ? 1 : 0;
+        {
+            int n_w = 0;
+            if (split && (a.structure & ST_LIMITER)) n_w = 1;
+            if (split && (a.structure & ST_COMPRESSOR)) n_w = 4;
+            if (a.structure & ST_DEESSER) n_w = 7;  // the de-esser is always R/M split (afsim_deesser.h)
             for (int k = 0; k < n_w; ++k) AF_CUDA(h, sweep->mem.alloc(&a.w[k], ring_elems));
         }
         AF_CUDA(h, sweep->mem.alloc(&a.st_input, kStateInput * sp));
@@ -392,13 +396,17 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             for (uint32_t first = 0; first < max_sections; first += batch->eq_k)
                 batch->stages.push_back({SK_EQ, static_cast<int>(first)});
         };
+        auto push_deesser = [&]() {
+            if (!(a.structure & ST_DEESSER)) return;
+            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC}) batch->stages.push_back({SK_SPLIT, op});
+        };
         batch->stages.push_back({SK_INPUT, 0});
         if (a.structure & ST_INPUT_TRUE_PEAK) batch->stages.push_back({SK_INPUT_TP, 0});
         if (a.structure & ST_EQ_BEFORE_DEESSER) {
             push_eq();
-            if (a.structure & ST_DEESSER) batch->stages.push_back({SK_DEESSER, 0});
+            push_deesser();
         } else {
-            if (a.structure & ST_DEESSER) batch->stages.push_back({SK_DEESSER, 0});
+            push_deesser();
             push_eq();
         }
         if (a.structure & ST_COMPRESSOR) {
@@ -432,7 +440,6 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
     switch (st.kind) {
         case SK_INPUT: return launch_input(b.args, ck, stream);
         case SK_INPUT_TP: return launch_input_true_peak(b.args, ck, stream);
-        case SK_DEESSER: return launch_deesser(b.args, ck, stream);
         case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
         case SK_LIMITER: return launch_limiter(b.args, ck, stream);
@@ -456,7 +463,8 @@ int run_batch(AfsimHandle* h, Batch& b) {
         auto stream_of = [&](int i) {
             const StageDesc& sd = b.stages[i];
             const bool is_map = sd.kind == SK_SPLIT && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
-                                                        sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT);
+                                                        sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT ||
+                                                        sd.arg == SP_DE_MB);
             return is_map ? h->stage_stream_map[i] : h->stage_stream[i];
         };
         for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(stream_of(i), h->ev_fork, 0));

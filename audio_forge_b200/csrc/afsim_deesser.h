@@ -1,0 +1,368 @@
+// afsim_deesser.h -- the dynamic-EQ de-esser (rust-core/src/dsp/deesser.rs:405-547) cut into two serial
+// recurrence kernels and one map kernel:
+//     R_a  detector biquads (3 bands x high-pass + low-pass), band / broadband envelopes
+//     M_b  levels in dB, voice level, narrowness, dominance, confidence targets   (4 log10, 3 sqrt, ~20 divisions)
+//     R_c  confidence / baseline / reduction smoothing, the target logic, the dynamic-EQ gain hysteresis with
+//          its coefficient rebuilds, and the three time-varying peaking biquads
+// The map holds most of the arithmetic and runs one thread per (stream, 2 samples); the serial kernels keep
+// ~16 / ~37 state values per stream in registers.  Per sample the operations and their order are those of
+// DeEsser::process_sample, so the result is the same as a fused walk (tests/hostsim: bit-exact vs the oracle).
+//
+// Hand-off rings (f64, [row][stream]): R_a writes w0 = broadband envelope, w1..w3 = band envelopes; M_b
+// overwrites w0 = voice dB, w1..w3 = band level dB and writes w4..w6 = clamped confidence targets.
+#pragma once
+#include "afsim_split.h"
+
+namespace afsim {
+
+constexpr int kDeMapGroup = 2;    // samples per thread of the de-esser map
+constexpr int kDeRcDepth = 3;     // staging depth of R_c (8 staged streams: keep the shared-memory footprint small)
+constexpr int kStateDeDetect = 16;  // state slots of R_a; R_c's follow
+
+// ---- R_a ------------------------------------------------------------------------------------------------------
+struct DeEsserDetect {
+    double dz[3][4];  // detector hp z1,z2, lp z1,z2
+    double env[3];
+    double broadband;
+
+    AF_HD void init() {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dz[b][i] = 0.0;
+            env[b] = 0.0;
+        }
+        broadband = 0.0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) io.f64(dz[b][i]);
+            io.f64(env[b]);
+        }
+        io.f64(broadband);
+    }
+
+    // x: chunk column (f32); w: ring columns at chunk start.  The first F samples of a render cross-fade the
+    // detector biquads from their constructor coefficients (deesser.rs:64-73 -> dsp/biquad.rs:249-327).
+    AF_HD void run(const float* x, double* w0, double* w1, double* w2, double* w3, size_t stride, int n0, int len,
+                   int fade_total, const DeConst& k, const CandidateParams* p, Staging stg) {
+        constexpr int U = kGroup;
+        const double det_attack = k(DE_DET_ATTACK), det_release = k(DE_DET_RELEASE);
+        Bq hp[3], lp[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            hp[b] = k.bq(DE_DET + 10 * b);
+            lp[b] = k.bq(DE_DET + 10 * b + 5);
+        }
+        int t_head = 0;
+        if (n0 < fade_total) {  // head of the render, sample by sample
+            double pdz[3][4];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pdz[b][i] = 0.0;
+            // (the crossfade always starts at n = 0 and chunks are at least F long: n0 == 0 here)
+            for (; t_head < len && n0 + t_head < fade_total; ++t_head) {
+                const int n = n0 + t_head;
+                const float in = x[(size_t)t_head * stride];
+                broadband = smooth_ar(broadband, (double)fabsf(in), det_attack, det_release);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const Bq hp0 = bq_from(p->de_det0[2 * b]);
+                    const Bq lp0 = bq_from(p->de_det0[2 * b + 1]);
+                    const float hp_out = (float)bq_step_fading((double)in, hp0, hp[b], dz[b][0], dz[b][1], pdz[b][0],
+                                                               pdz[b][1], n, fade_total);
+                    const float sc = (float)bq_step_fading((double)hp_out, lp0, lp[b], dz[b][2], dz[b][3], pdz[b][2],
+                                                           pdz[b][3], n, fade_total);
+                    if (n + 1 == fade_total) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dz[b][i] = pdz[b][i];
+                    }
+                    env[b] = smooth_ar(env[b], (double)fabsf(sc), det_attack, det_release);
+                }
+                w0[(size_t)t_head * stride] = broadband;
+                w1[(size_t)t_head * stride] = env[0];
+                w2[(size_t)t_head * stride] = env[1];
+                w3[(size_t)t_head * stride] = env[2];
+            }
+        }
+        // steady state: staged tiles
+        const float* xs = x + (size_t)t_head * stride;
+        double* o0 = w0 + (size_t)t_head * stride;
+        double* o1 = w1 + (size_t)t_head * stride;
+        double* o2 = w2 + (size_t)t_head * stride;
+        double* o3 = w3 + (size_t)t_head * stride;
+        const int m = len - t_head;
+        const StageRing<float> sx = stg.ring<float>();
+        auto issue = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (FULL || t0 + u < m) sx.fetch(kt, u, xs + (size_t)(t0 + u) * stride);
+        };
+        auto body = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+            const int valid = FULL ? U : m - t0;
+            float xin[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xin[u] = (FULL || u < valid) ? sx.get(kt, u, xs + (size_t)(t0 + u) * stride) : 0.0f;
+            double ob[U], o_e0[U], o_e1[U], o_e2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || u < valid) {
+                    const float in = xin[u];
+                    broadband = smooth_ar(broadband, (double)fabsf(in), det_attack, det_release);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const float hp_out = (float)bq_step((double)in, hp[b], dz[b][0], dz[b][1]);
+                        const float sc = (float)bq_step((double)hp_out, lp[b], dz[b][2], dz[b][3]);
+                        env[b] = smooth_ar(env[b], (double)fabsf(sc), det_attack, det_release);
+                    }
+                }
+                ob[u] = broadband;
+                o_e0[u] = env[0];
+                o_e1[u] = env[1];
+                o_e2[u] = env[2];
+            }
+            store_tile(o0 + (size_t)t0 * stride, stride, valid, ob);
+            store_tile(o1 + (size_t)t0 * stride, stride, valid, o_e0);
+            store_tile(o2 + (size_t)t0 * stride, stride, valid, o_e1);
+            store_tile(o3 + (size_t)t0 * stride, stride, valid, o_e2);
+        };
+        pipelined_tiles(m, issue, body);
+    }
+};
+
+// ---- M_b ------------------------------------------------------------------------------------------------------
+AF_HD void deesser_levels(double* w0, double* w1, double* w2, double* w3, double* w4, double* w5, double* w6, size_t stride,
+                          int valid) {
+    constexpr int G = kDeMapGroup;
+    double bb[G], e0[G], e1[G], e2[G];
+    load_tile((const double*)w0, stride, valid, bb);
+    load_tile((const double*)w1, stride, valid, e0);
+    load_tile((const double*)w2, stride, valid, e1);
+    load_tile((const double*)w3, stride, valid, e2);
+    double voice[G], lv0[G], lv1[G], lv2[G], c0[G], c1[G], c2[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        const double env[3] = {e0[u], e1[u], e2[u]};
+        double level_db[3];
+        double total_env = 0.0, max_env = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            total_env += env[b];
+            max_env = fmax(max_env, env[b]);
+            level_db[b] = lin_to_db(env[b], 1e-10);
+        }
+        const double voice_level = fmax(bb[u] - total_env * 0.6, 1e-8);
+        const double voice_db = lin_to_db(voice_level, 1e-10);
+        const double narrowness = total_env > 1e-10 ? max_env / total_env : 0.0;
+        double conf[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double dominance = max_env > 1e-10 ? sqrt(env[b] / max_env) : 0.0;
+            conf[b] = clampd(de_confidence_target(level_db[b], voice_db, narrowness) * dominance, 0.0, 1.0);
+        }
+        voice[u] = voice_db;
+        lv0[u] = level_db[0];
+        lv1[u] = level_db[1];
+        lv2[u] = level_db[2];
+        c0[u] = conf[0];
+        c1[u] = conf[1];
+        c2[u] = conf[2];
+    }
+    store_tile(w0, stride, valid, voice);
+    store_tile(w1, stride, valid, lv0);
+    store_tile(w2, stride, valid, lv1);
+    store_tile(w3, stride, valid, lv2);
+    store_tile(w4, stride, valid, c0);
+    store_tile(w5, stride, valid, c1);
+    store_tile(w6, stride, valid, c2);
+}
+
+// ---- R_c ------------------------------------------------------------------------------------------------------
+struct DeEsserApply {
+    double conf[3], base[3], red[3], built_gain[3];
+    Bq dyn[3];        // live dynamic-EQ coefficients
+    double yz[3][2];  // dynamic-EQ state
+    double current;
+    bool cancel[3];   // set_gain_db_immediate cancelled the configuration crossfade
+    bool auto_mode;
+
+    AF_HD void init(const CandidateParams& p) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            conf[b] = base[b] = red[b] = built_gain[b] = 0.0;
+            dyn[b] = bq_from(p.de_dyn0[b]);
+            yz[b][0] = yz[b][1] = 0.0;
+            cancel[b] = false;
+        }
+        current = 0.0;
+        auto_mode = (p.flags & LF_DE_AUTO) != 0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            io.f64(conf[b]);
+            io.f64(base[b]);
+            io.f64(red[b]);
+            io.f64(built_gain[b]);
+            io.f64(dyn[b].b0);
+            io.f64(dyn[b].b1);
+            io.f64(dyn[b].b2);
+            io.f64(dyn[b].a1);
+            io.f64(dyn[b].a2);
+            io.f64(yz[b][0]);
+            io.f64(yz[b][1]);
+            io.flag(cancel[b]);
+        }
+        io.f64(current);
+    }
+
+    // One sample of the second half of DeEsser::process_sample (deesser.rs:452-547).
+    template <bool HEAD>
+    AF_HD float sample(float input, double voice_db, const double (&level_db)[3], const double (&conf_target)[3], int n,
+                       int fade_total, const DeConst& k, const CandidateParams* p, double (*pyz)[2]) {
+        const double det_attack = k(DE_DET_ATTACK), det_release = k(DE_DET_RELEASE);
+        const double max_red = k(DE_MAX_RED);
+        double target[3];
+        double target_sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double ratio_db = fmax(level_db[b] - voice_db, 0.0);
+            conf[b] = smooth_ar(conf[b], conf_target[b], det_attack, det_release);
+            double tr = 0.0;
+            if (auto_mode) {
+                const bool voice_active = voice_db > -55.0 || level_db[b] > -55.0;
+                if (voice_active) {
+                    const double base_target = clampd(ratio_db * 0.45, 0.0, 24.0);
+                    const double c = base_target < base[b] ? k(DE_BASE_FALL) : k(DE_BASE_RISE);
+                    base[b] = c * base[b] + (1.0 - c) * base_target;
+                } else {
+                    base[b] *= k(DE_BASE_INACTIVE);
+                }
+                const double conf_gain = norm_range(conf[b], k(DE_CONF_FLOOR), 1.0);
+                const double over_db = fmax(ratio_db - base[b] - k(DE_TRIGGER), 0.0);
+                tr = clampd(over_db * k(DE_SLOPE) * conf_gain, 0.0, k(DE_CAP));
+            } else if (level_db[b] > k(DE_THRESHOLD)) {
+                const double level_over = level_db[b] - k(DE_THRESHOLD);
+                const double ratio_over = ratio_db - k(DE_RATIO_THR);
+                if (ratio_over > 0.0) {
+                    const double over_db = fmin(level_over, ratio_over);
+                    const double conf_gain = norm_range(conf[b], 0.22, 1.0);
+                    tr = clampd(k(DE_RATIO_FACTOR) * over_db * conf_gain, 0.0, k(DE_MANUAL_CAP));
+                }
+            }
+            target[b] = tr;
+            target_sum += tr;
+        }
+        if (target_sum > max_red && target_sum > 0.0) {
+            const double scale = max_red / target_sum;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) target[b] *= scale;
+        }
+        const double attack = k(DE_ATTACK), release = k(DE_RELEASE);
+        float processed = input;
+        double total_red = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            red[b] = smooth_ar(red[b], target[b], attack, release);
+            total_red += red[b];
+            const double dyn_gain = -red[b];
+            if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate: cancels any fade, keeps z1/z2
+                built_gain[b] = dyn_gain;
+                dyn[b] = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), dyn_gain);
+                cancel[b] = true;
+            }
+            double y;
+            if (HEAD && n < fade_total && !cancel[b]) {
+                const Bq pend = bq_from(p->de_dyn1[b]);
+                y = bq_step_fading((double)processed, dyn[b], pend, yz[b][0], yz[b][1], pyz[b][0], pyz[b][1], n, fade_total);
+                if (n + 1 == fade_total) {
+                    dyn[b] = pend;
+                    yz[b][0] = pyz[b][0];
+                    yz[b][1] = pyz[b][1];
+                }
+            } else {
+                y = bq_step((double)processed, dyn[b], yz[b][0], yz[b][1]);
+            }
+            processed = (float)y;
+        }
+        current = fmin(total_red, max_red);
+        return processed;
+    }
+
+    // x: chunk column (in place); w[0..6]: ring columns at chunk start (voice dB, 3 level dB, 3 confidence targets)
+    AF_HD void run(float* x, double* const (&w)[7], size_t stride, int n0, int len, int fade_total, const DeConst& k,
+                   const CandidateParams* p, BlockClock clk, float* rows_de, Staging stg) {
+        constexpr int U = kGroup;
+        int t_head = 0;
+        if (n0 < fade_total) {
+            double pyz[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            for (; t_head < len && n0 + t_head < fade_total; ++t_head) {
+                const size_t o = (size_t)t_head * stride;
+                const double lv[3] = {w[1][o], w[2][o], w[3][o]};
+                const double ct[3] = {w[4][o], w[5][o], w[6][o]};
+                x[o] = sample<true>(x[o], w[0][o], lv, ct, n0 + t_head, fade_total, k, p, pyz);
+                if (clk.at_end(n0 + t_head)) {
+                    rows_de[(size_t)clk.blk * stride] = (float)current;
+                    clk.advance();
+                }
+            }
+        }
+        float* xs = x + (size_t)t_head * stride;
+        const double* ws[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) ws[i] = w[i] + (size_t)t_head * stride;
+        const int m = len - t_head;
+        const int nb = n0 + t_head;
+        const StageRing<float, kDeRcDepth> sx = stg.ring<float, kDeRcDepth>();
+        StageRing<double, kDeRcDepth> sw[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sw[i] = stg.ring<double, kDeRcDepth>();
+        auto issue = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || t0 + u < m) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+                    sx.fetch(kt, u, xs + o);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, ws[i] + o);
+                }
+            }
+        };
+        auto body = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+            const int valid = FULL ? U : m - t0;
+            // the per-sample body is ~400 instructions: keep the walk rolled (an unrolled tile spills)
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                if (FULL || u < valid) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+                    const float in = sx.get(kt, u, xs + o);
+                    const double voice_db = sw[0].get(kt, u, ws[0] + o);
+                    const double lv[3] = {sw[1].get(kt, u, ws[1] + o), sw[2].get(kt, u, ws[2] + o), sw[3].get(kt, u, ws[3] + o)};
+                    const double ct[3] = {sw[4].get(kt, u, ws[4] + o), sw[5].get(kt, u, ws[5] + o), sw[6].get(kt, u, ws[6] + o)};
+                    xs[o] = sample<false>(in, voice_db, lv, ct, nb + t0 + u, fade_total, k, p, nullptr);
+                    if (clk.at_end(nb + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
+                        rows_de[(size_t)clk.blk * stride] = (float)current;
+                        clk.advance();
+                    }
+                }
+            }
+        };
+        pipelined_tiles_depth<kDeRcDepth>(m, issue, body);
+    }
+};
+constexpr size_t kDeRcStagingBytesPerLane = (size_t)kDeRcDepth * 8 * (4 + 7 * 8);
+
+}  // namespace afsim

@@ -50,11 +50,6 @@ __global__ void __launch_bounds__(128) k_eq(BatchArgs a, ChunkArgs ck, int first
     body_eq<K>(a, ck, s, first);
 }
 
-__global__ void __launch_bounds__(128) k_deesser(BatchArgs a, ChunkArgs ck) {
-    AF_STREAM_INDEX();
-    body_deesser(a, ck, s);
-}
-
 __global__ void __launch_bounds__(128) k_compressor(BatchArgs a, ChunkArgs ck) {
     AF_STREAM_INDEX();
     body_compressor(a, ck, s);
@@ -80,9 +75,9 @@ __global__ void __launch_bounds__(128) k_input_true_peak(BatchArgs a, ChunkArgs 
 // Each thread stages its inputs through shared memory with cp.async (Staging, afsim_split.h).
 extern __shared__ __align__(16) unsigned char stage_smem[];
 #define AF_R_KERNEL(name, body)                                                         \
-    __global__ void __launch_bounds__(kRBlock) name(BatchArgs a, ChunkArgs ck) {        \
+    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) {            \
         AF_STREAM_INDEX();                                                              \
-        const Staging stg{stage_smem, (int)blockDim.x, (int)threadIdx.x, 0};            \
+        const Staging stg{a.stage_inputs ? stage_smem : nullptr, (int)blockDim.x, (int)threadIdx.x, 0}; \
         body(a, ck, s, stg);                                                            \
     }
 AF_R_KERNEL(k_comp_r1, body_comp_r1)
@@ -90,6 +85,8 @@ AF_R_KERNEL(k_comp_r3, body_comp_r3)
 AF_R_KERNEL(k_comp_r5, body_comp_r5)
 AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
+AF_R_KERNEL(k_de_ra, body_de_ra)
+AF_R_KERNEL(k_de_rc, body_de_rc)
 
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
 // A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping
@@ -107,6 +104,7 @@ AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_M_KERNEL(k_comp_m2, kCompMapGroup, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
 AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
+AF_M_KERNEL(k_de_mb, kDeMapGroup, body_de_mb(a, ck, s, g))
 AF_M_KERNEL(k_lim_m, kLimGroup, body_lim_m(a, ck, s, g))
 AF_M_KERNEL(k_tp_fir_in, kGroup, body_tp_fir_in(a, ck, s, g, c_fir))
 AF_M_KERNEL(k_tp_fir_out, kGroup, body_tp_fir_out(a, ck, s, g, c_fir))
@@ -250,11 +248,6 @@ cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first, int k,
         return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
-cudaError_t launch_deesser(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
-    const int b = pick_block(a);
-    k_deesser<<<stream_grid(a, b), b, 0, st>>>(a, ck);
-    return cudaGetLastError();
-}
 cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int b = pick_block(a);
     k_compressor<<<stream_grid(a, b), b, 0, st>>>(a, ck);
@@ -295,12 +288,14 @@ static int sm_count() {
 }
 
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
-    const int rb = kRBlock;
+    // serial kernels: one warp per block with a shared-memory staging area for few-stream batches; plain
+    // 128-thread blocks reading global memory directly when the batch itself fills the GPU
+    const int rb = a.stage_inputs ? kRBlock : 128;
     const dim3 rgrid = stream_grid(a, rb);
-    const size_t rsm = kStagingBytesPerLane * kRBlock;
+    const size_t rsm = a.stage_inputs ? (op == SP_DE_RC ? kDeRcStagingBytesPerLane : kStagingBytesPerLane) * kRBlock : 0;
     const int mb = 32 * kMapWarps;
     const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup
-                      : (op == SP_LIM_M ? kLimGroup : kGroup);
+                      : (op == SP_LIM_M ? kLimGroup : (op == SP_DE_MB ? kDeMapGroup : kGroup));
     const int n_groups = (ck.len + group - 1) / group;
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
@@ -325,6 +320,9 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         case SP_TP_FIR_IN: k_tp_fir_in<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_TP_R: k_tp_r<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_TP_FIR_OUT: k_tp_fir_out<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_DE_RA: k_de_ra<<<rgrid, rb, rsm, st>>>(a, ck); break;
+        case SP_DE_MB: k_de_mb<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_DE_RC: k_de_rc<<<rgrid, rb, rsm, st>>>(a, ck); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

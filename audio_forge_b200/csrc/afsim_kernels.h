@@ -16,7 +16,6 @@ constexpr size_t kFinalizeSmemLimit = 200 * 1024;
 cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);
 cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first_section, int k, cudaStream_t st);
-cudaError_t launch_deesser(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_limiter(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_output(const BatchArgs& a, const ChunkArgs& ck, bool limiter, cudaStream_t st);
@@ -24,7 +23,8 @@ cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cuda
 // split (R/M) path, afsim_split.h
 enum SplitOp {
     SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6,
-    SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT
+    SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT,
+    SP_DE_RA, SP_DE_MB, SP_DE_RC
 };
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);

@@ -9,6 +9,7 @@
 #pragma once
 #include "../../include/afsim.h"
 #include "afsim_cleanup.h"
+#include "afsim_deesser.h"
 #include "afsim_split.h"
 
 namespace afsim {
@@ -141,27 +142,6 @@ AF_HD void body_eq(const BatchArgs& a, const ChunkArgs& ck, int s, int first) {
     st.run(io, t_begin, ck.len);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> sio{table, stride};
-        st.sync(sio);
-    }
-}
-
-// ---- de-esser -------------------------------------------------------------------------------------------------
-AF_HD void body_deesser(const BatchArgs& a, const ChunkArgs& ck, int s) {
-    const size_t stride = (size_t)a.stride;
-    const CandidateParams& p = stream_params(a, s);
-    DeEsserStage st;
-    st.init(p);
-    if (ck.n0 != 0) {
-        StateIO<false> io{a.st_deesser + s, stride};
-        st.sync(io);
-    }
-    BlockClock clk;
-    clk.init(a.block_samples, a.n_samples, ck.n0);
-    const Col io{a.buf_a + (size_t)ck.row0 * stride + s, stride};
-    const DeConst k{a.de_tab + s, stride};
-    st.run(io, ck.n0, ck.len, a.fade_samples, k, &p, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stride);
-    if (ck.n0 + ck.len < a.n_samples) {
-        StateIO<true> sio{a.st_deesser + s, stride};
         st.sync(sio);
     }
 }
@@ -384,6 +364,55 @@ AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     CompSplit st;
     st.init(stream_params(a, s));
     st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);
+}
+
+// ---- de-esser: R_a -> M_b -> R_c (afsim_deesser.h), used by every batch that has the stage ---------------------------
+AF_HD void body_de_ra(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    const CandidateParams& p = stream_params(a, s);
+    DeEsserDetect st;
+    if (ck.n0 == 0) {
+        st.init();
+    } else {
+        StateIO<false> io{a.st_deesser + s, stride};
+        st.sync(io);
+    }
+    const DeConst k{a.de_tab + s, stride};
+    st.run(col_at(a.buf_a, a, ck, s), col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s),
+           col_at(a.w[3], a, ck, s), stride, ck.n0, ck.len, a.fade_samples, k, &p, stg);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{a.st_deesser + s, stride};
+        st.sync(io);
+    }
+}
+AF_HD void body_de_mb(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid, kDeMapGroup)) return;
+    deesser_levels(col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
+                   col_at(a.w[3], a, ck, s, t0), col_at(a.w[4], a, ck, s, t0), col_at(a.w[5], a, ck, s, t0),
+                   col_at(a.w[6], a, ck, s, t0), (size_t)a.stride, valid);
+}
+AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    const CandidateParams& p = stream_params(a, s);
+    DeEsserApply st;
+    st.init(p);
+    double* table = a.st_deesser + (size_t)kStateDeDetect * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const DeConst k{a.de_tab + s, stride};
+    double* const w[7] = {col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s),
+                          col_at(a.w[4], a, ck, s), col_at(a.w[5], a, ck, s), col_at(a.w[6], a, ck, s)};
+    st.run(col_at(a.buf_a, a, ck, s), w, stride, ck.n0, ck.len, a.fade_samples, k, &p, clk,
+           a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync(io);
+    }
 }
 
 AF_HD void body_lim_m(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {

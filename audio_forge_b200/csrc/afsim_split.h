@@ -67,22 +67,28 @@ AF_HD void async_wait_prior() {
 #endif
 }
 
-template <typename T>
+template <typename T, int DEPTH = kPipeDepth>
 struct StageRing {  // one staged input stream of one thread
-    T* p;           // this thread's element of (tile slot 0, sample 0)
+    T* p;           // this thread's element of (tile slot 0, sample 0); nullptr = direct mode (no staging)
     int lanes;      // threads sharing the staging area (element pitch)
-    AF_HD T* at(int tile, int u) const { return p + (size_t)((tile % kPipeDepth) * kGroup + u) * lanes; }
+    AF_HD T* at(int tile, int u) const { return p + (size_t)((tile % DEPTH) * kGroup + u) * lanes; }
+    // direct-mode aware accessors: big batches have enough warps per SM to hide the latency themselves, and
+    // the staging area would only cost them occupancy
+    AF_HD void fetch(int tile, int u, const T* g) const {
+        if (p) async_copy(at(tile, u), g);
+    }
+    AF_HD T get(int tile, int u, const T* g) const { return p ? *at(tile, u) : *g; }
 };
-struct Staging {  // the staging area of a block (shared memory) / of one call (host)
+struct Staging {  // the staging area of a block (shared memory) / of one call (host); base == nullptr: direct mode
     unsigned char* base;
     int lanes, lane;
     size_t used;
-    template <typename T>
-    AF_HD StageRing<T> ring() {
-        StageRing<T> r;
-        r.p = reinterpret_cast<T*>(base + used) + lane;
+    template <typename T, int DEPTH = kPipeDepth>
+    AF_HD StageRing<T, DEPTH> ring() {
+        StageRing<T, DEPTH> r;
+        r.p = base ? reinterpret_cast<T*>(base + used) + lane : nullptr;
         r.lanes = lanes;
-        used += sizeof(T) * (size_t)kPipeDepth * kGroup * (size_t)lanes;
+        used += sizeof(T) * (size_t)DEPTH * kGroup * (size_t)lanes;
         return r;
     }
 };
@@ -93,11 +99,11 @@ constexpr size_t kStagingBytesPerLane = (size_t)kPipeDepth * 8 * 16;  // widest 
 // their code carries no per-sample bounds predicates.
 struct TileFull { static constexpr bool value = true; };
 struct TileRagged { static constexpr bool value = false; };
-template <class Issue, class Body>
-AF_HD void pipelined_tiles(int len, Issue issue, Body body) {
+template <int DEPTH, class Issue, class Body>
+AF_HD void pipelined_tiles_depth(int len, Issue issue, Body body) {
     const int n_tiles = (len + 8 - 1) / 8;
     const int n_full = len / 8;
-    for (int k = 0; k < kPipeDepth - 1; ++k) {
+    for (int k = 0; k < DEPTH - 1; ++k) {
         if (k < n_full)
             issue(k, TileFull());
         else if (k < n_tiles)
@@ -105,18 +111,22 @@ AF_HD void pipelined_tiles(int len, Issue issue, Body body) {
         async_commit();
     }
     for (int k = 0; k < n_tiles; ++k) {
-        const int ahead = k + kPipeDepth - 1;
+        const int ahead = k + DEPTH - 1;
         if (ahead < n_full)
             issue(ahead, TileFull());
         else if (ahead < n_tiles)
             issue(ahead, TileRagged());
         async_commit();
-        async_wait_prior<kPipeDepth - 1>();
+        async_wait_prior<DEPTH - 1>();
         if (k < n_full)
             body(k, TileFull());
         else
             body(k, TileRagged());
     }
+}
+template <class Issue, class Body>
+AF_HD void pipelined_tiles(int len, Issue issue, Body body) {
+    pipelined_tiles_depth<kPipeDepth>(len, issue, body);
 }
 
 template <typename T, int U>

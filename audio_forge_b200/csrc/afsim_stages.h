@@ -374,187 +374,6 @@ struct DeConst {
     AF_HD Bq bq(int field) const { return bq_from_strided(base + (size_t)field * stride, stride); }
 };
 
-struct DeEsserStage {
-    double dz[3][4];      // detector hp z1,z2, lp z1,z2
-    double yz[3][2];      // dynamic EQ state
-    Bq dyn[3];            // live dynamic-EQ coefficients
-    double env[3], conf[3], base[3], red[3], built_gain[3];
-    double broadband, current;
-    double pdz[3][4], pyz[3][2];  // pending-filter state during the configuration crossfade; the crossfade
-                                  // always ends inside chunk 0 (chunk >= F), so it is never parked
-    bool cancel[3];       // set_gain_db_immediate cancelled the configuration fade
-    bool auto_mode;
-
-    AF_HD void init(const CandidateParams& p) {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dz[b][i] = pdz[b][i] = 0.0;
-            yz[b][0] = yz[b][1] = pyz[b][0] = pyz[b][1] = 0.0;
-            dyn[b] = bq_from(p.de_dyn0[b]);
-            env[b] = conf[b] = base[b] = red[b] = built_gain[b] = 0.0;
-            cancel[b] = false;
-        }
-        broadband = 0.0;
-        current = 0.0;
-        auto_mode = (p.flags & LF_DE_AUTO) != 0;
-    }
-    template <class IO>
-    AF_HD void sync(IO& io) {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) io.f64(dz[b][i]);
-            io.f64(yz[b][0]);
-            io.f64(yz[b][1]);
-            io.f64(dyn[b].b0);
-            io.f64(dyn[b].b1);
-            io.f64(dyn[b].b2);
-            io.f64(dyn[b].a1);
-            io.f64(dyn[b].a2);
-            io.f64(env[b]);
-            io.f64(conf[b]);
-            io.f64(base[b]);
-            io.f64(red[b]);
-            io.f64(built_gain[b]);
-            io.flag(cancel[b]);
-        }
-        io.f64(broadband);
-        io.f64(current);
-    }
-
-    // One sample.  HEAD = the render is still inside the F-sample configuration crossfade of the
-    // detector / dynamic biquads (deesser.rs:64-73 schedules it from the setters); p gives the
-    // fade-source coefficients.
-    template <bool HEAD>
-    AF_HD float sample(float input, int n, int fade_total, const DeConst& k, const CandidateParams* p) {
-        const double det_attack = k(DE_DET_ATTACK), det_release = k(DE_DET_RELEASE);
-        const double max_red = k(DE_MAX_RED);
-        broadband = smooth_ar(broadband, (double)fabsf(input), det_attack, det_release);
-        double level_db[3];
-        double total_env = 0.0, max_env = 0.0;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const Bq hp = k.bq(DE_DET + 10 * b);
-            const Bq lp = k.bq(DE_DET + 10 * b + 5);
-            float hp_out, sc;
-            if (HEAD && n < fade_total) {
-                const Bq hp0 = bq_from(p->de_det0[2 * b]);
-                const Bq lp0 = bq_from(p->de_det0[2 * b + 1]);
-                hp_out = (float)bq_step_fading((double)input, hp0, hp, dz[b][0], dz[b][1], pdz[b][0], pdz[b][1], n,
-                                               fade_total);
-                sc = (float)bq_step_fading((double)hp_out, lp0, lp, dz[b][2], dz[b][3], pdz[b][2], pdz[b][3], n,
-                                           fade_total);
-                if (n + 1 == fade_total) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dz[b][i] = pdz[b][i];
-                }
-            } else {
-                hp_out = (float)bq_step((double)input, hp, dz[b][0], dz[b][1]);
-                sc = (float)bq_step((double)hp_out, lp, dz[b][2], dz[b][3]);
-            }
-            env[b] = smooth_ar(env[b], (double)fabsf(sc), det_attack, det_release);
-            total_env += env[b];
-            max_env = fmax(max_env, env[b]);
-            level_db[b] = lin_to_db(env[b], 1e-10);
-        }
-        const double voice_level = fmax(broadband - total_env * 0.6, 1e-8);
-        const double voice_db = lin_to_db(voice_level, 1e-10);
-        const double narrowness = total_env > 1e-10 ? max_env / total_env : 0.0;
-
-        double target[3];
-        double target_sum = 0.0;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            const double ratio_db = fmax(level_db[b] - voice_db, 0.0);
-            const double dominance = max_env > 1e-10 ? sqrt(env[b] / max_env) : 0.0;
-            const double conf_target = de_confidence_target(level_db[b], voice_db, narrowness) * dominance;
-            conf[b] = smooth_ar(conf[b], clampd(conf_target, 0.0, 1.0), det_attack, det_release);
-            double tr = 0.0;
-            if (auto_mode) {
-                const bool voice_active = voice_db > -55.0 || level_db[b] > -55.0;
-                if (voice_active) {
-                    const double base_target = clampd(ratio_db * 0.45, 0.0, 24.0);
-                    const double c = base_target < base[b] ? k(DE_BASE_FALL) : k(DE_BASE_RISE);
-                    base[b] = c * base[b] + (1.0 - c) * base_target;
-                } else {
-                    base[b] *= k(DE_BASE_INACTIVE);
-                }
-                const double conf_gain = norm_range(conf[b], k(DE_CONF_FLOOR), 1.0);
-                const double over_db = fmax(ratio_db - base[b] - k(DE_TRIGGER), 0.0);
-                tr = clampd(over_db * k(DE_SLOPE) * conf_gain, 0.0, k(DE_CAP));
-            } else if (level_db[b] > k(DE_THRESHOLD)) {
-                const double level_over = level_db[b] - k(DE_THRESHOLD);
-                const double ratio_over = ratio_db - k(DE_RATIO_THR);
-                if (ratio_over > 0.0) {
-                    const double over_db = fmin(level_over, ratio_over);
-                    const double conf_gain = norm_range(conf[b], 0.22, 1.0);
-                    tr = clampd(k(DE_RATIO_FACTOR) * over_db * conf_gain, 0.0, k(DE_MANUAL_CAP));
-                }
-            }
-            target[b] = tr;
-            target_sum += tr;
-        }
-        if (target_sum > max_red && target_sum > 0.0) {
-            const double scale = max_red / target_sum;
-#pragma unroll
-            for (int b = 0; b < 3; ++b) target[b] *= scale;
-        }
-        const double attack = k(DE_ATTACK), release = k(DE_RELEASE);
-        float processed = input;
-        double total_red = 0.0;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            red[b] = smooth_ar(red[b], target[b], attack, release);
-            total_red += red[b];
-            const double dyn_gain = -red[b];
-            if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate: cancels any fade, keeps z1/z2
-                built_gain[b] = dyn_gain;
-                dyn[b] = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), dyn_gain);
-                cancel[b] = true;
-            }
-            double y;
-            if (HEAD && n < fade_total && !cancel[b]) {
-                const Bq pend = bq_from(p->de_dyn1[b]);
-                y = bq_step_fading((double)processed, dyn[b], pend, yz[b][0], yz[b][1], pyz[b][0], pyz[b][1], n,
-                                   fade_total);
-                if (n + 1 == fade_total) {
-                    dyn[b] = pend;
-                    yz[b][0] = pyz[b][0];
-                    yz[b][1] = pyz[b][1];
-                }
-            } else {
-                y = bq_step((double)processed, dyn[b], yz[b][0], yz[b][1]);
-            }
-            processed = (float)y;
-        }
-        current = fmin(total_red, max_red);
-        return processed;
-    }
-
-    // rows_de: row.3 table of this stream
-    AF_HD void run(const Col& io, int n0, int len, int fade_total, const DeConst& k, const CandidateParams* p,
-                   BlockClock clk, float* rows_de, size_t stride) {
-        int t = 0;
-        for (; t < len && n0 + t < fade_total; ++t) {
-            const int n = n0 + t;
-            io.set(t, sample<true>(io.get(t), n, fade_total, k, p));
-            if (clk.at_end(n)) {
-                rows_de[(size_t)clk.blk * stride] = (float)current;
-                clk.advance();
-            }
-        }
-        for (; t < len; ++t) {
-            const int n = n0 + t;
-            io.set(t, sample<false>(io.get(t), n, fade_total, k, p));
-            if (clk.at_end(n)) {  // block-end meter sample (block_processor.rs:129-133)
-                rows_de[(size_t)clk.blk * stride] = (float)current;
-                clk.advance();
-            }
-        }
-    }
-};
-
 // The RMS leg of the blended detector (dsp/compressor.rs:681-686) is db_to_linear(linear_to_db(sqrt(e)))
 // = 10^(log10(max(sqrt(e), 1e-10))), i.e. max(sqrt(e), 1e-10) up to the rounding of the log / exp pair
 // (~2e-16 relative).  The device map evaluates the closed form -- the same size of deviation as the device

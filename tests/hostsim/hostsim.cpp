@@ -97,12 +97,17 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     std::vector<float> lim_sfx(static_cast<size_t>(a.lookahead + 1) * sp), rows(static_cast<size_t>(4) * std::max(a.n_rows, 1) * sp, 0.0f);
     std::vector<double> st_input(kStateInput * sp), st_de(kStateDeEsser * sp), st_eq(kStateEqPerSection * kMaxSections * sp),
         st_comp(kStateCompressor * sp), st_lim(kStateLimiter * sp), st_tp(kStateTruePeak * sp), de_tab(DE_FIELDS * sp);
-    std::vector<double> w0(static_cast<size_t>(a.ring_rows) * sp), w1(w0.size()), w2(w0.size()), w3(w0.size());
+    std::vector<double> w0(static_cast<size_t>(a.ring_rows) * sp), w1(w0.size()), w2(w0.size()), w3(w0.size()), w4(w0.size()),
+        w5(w0.size()), w6(w0.size());
     std::vector<float> buf_c(static_cast<size_t>(a.ring_rows) * sp), buf_p(buf_c.size());
     a.w[0] = w0.data();
     a.w[1] = w1.data();
     a.w[2] = w2.data();
     a.w[3] = w3.data();
+    a.w[4] = w4.data();
+    a.w[5] = w5.data();
+    a.w[6] = w6.data();
+    a.stage_inputs = 1;
     a.buf_c = buf_c.data();
     a.buf_p = buf_p.data();
     std::vector<StreamAccum> accum(sp);
@@ -133,7 +138,14 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
 
     if (a.structure & ST_DEESSER)
         for (int s = 0; s < S; ++s) body_expand_deesser(a, s);
-    std::vector<unsigned char> staging_bytes(kStagingBytesPerLane + 64);
+    std::vector<unsigned char> staging_bytes(std::max(kStagingBytesPerLane, kDeRcStagingBytesPerLane) + 64);
+    auto run_deesser = [&](const ChunkArgs& ck) {
+        const Staging st{(split & 8) ? nullptr : staging_bytes.data(), 1, 0, 0};  // split bit 3: direct (unstaged) loads
+        for (int s = 0; s < S; ++s) body_de_ra(a, ck, s, st);
+        for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
+            for (int s = 0; s < S; ++s) body_de_mb(a, ck, s, g);
+        for (int s = 0; s < S; ++s) body_de_rc(a, ck, s, st);
+    };
     const Staging stg{staging_bytes.data(), 1, 0, 0};
     const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
     auto run_eq = [&](const ChunkArgs& ck) {
@@ -158,11 +170,9 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         }
         if (a.structure & ST_EQ_BEFORE_DEESSER) {
             run_eq(ck);
-            if (a.structure & ST_DEESSER)
-                for (int s = 0; s < S; ++s) body_deesser(a, ck, s);
+            if (a.structure & ST_DEESSER) run_deesser(ck);
         } else {
-            if (a.structure & ST_DEESSER)
-                for (int s = 0; s < S; ++s) body_deesser(a, ck, s);
+            if (a.structure & ST_DEESSER) run_deesser(ck);
             run_eq(ck);
         }
         const int n_groups = (ck.len + kGroup - 1) / kGroup + 1;  // one empty group past the end on purpose

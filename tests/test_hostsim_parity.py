@@ -20,7 +20,7 @@ X = golden_chain_input(blocks=60)  # 28 800 samples, the reference golden test's
 
 @pytest.mark.parametrize("name", sorted(CASES))
 @pytest.mark.parametrize("schedule", [(1024, 2, 5, 0), (264, 3, 10, 0), (40000, 2, 5, 0), (1024, 2, 5, 7), (264, 3, 10, 7),
-                                      (2048, 4, 5, 5), (512, 2, 5, 2)])
+                                      (2048, 4, 5, 5), (512, 2, 5, 2), (1024, 2, 5, 15)])
 def test_stage_bodies_bit_exact_with_oracle(name, schedule):
     bands, overrides = CASES[name]
     settings = abi.make_settings(**overrides)
