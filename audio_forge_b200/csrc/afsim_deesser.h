@@ -186,6 +186,38 @@ AF_HD void deesser_levels(double* w0, double* w1, double* w2, double* w3, double
 }
 
 // ---- R_c ------------------------------------------------------------------------------------------------------
+// The constants R_c reads every sample, loaded once per chunk: read through the table on every use they would be
+// ~25 dependent memory accesses per sample (the compiler cannot hoist them past the in-place stores).
+struct DeApplyConst {
+    double det_attack, det_release, max_red, attack, release;
+    double base_fall, base_rise, base_inactive, conf_floor, trigger, slope, cap;      // auto mode
+    double threshold, ratio_thr, ratio_factor, manual_cap;                            // manual mode
+    double dyn_cos[3], dyn_alpha[3];
+    AF_HD void load(const DeConst& k) {
+        det_attack = k(DE_DET_ATTACK);
+        det_release = k(DE_DET_RELEASE);
+        max_red = k(DE_MAX_RED);
+        attack = k(DE_ATTACK);
+        release = k(DE_RELEASE);
+        base_fall = k(DE_BASE_FALL);
+        base_rise = k(DE_BASE_RISE);
+        base_inactive = k(DE_BASE_INACTIVE);
+        conf_floor = k(DE_CONF_FLOOR);
+        trigger = k(DE_TRIGGER);
+        slope = k(DE_SLOPE);
+        cap = k(DE_CAP);
+        threshold = k(DE_THRESHOLD);
+        ratio_thr = k(DE_RATIO_THR);
+        ratio_factor = k(DE_RATIO_FACTOR);
+        manual_cap = k(DE_MANUAL_CAP);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            dyn_cos[b] = k(DE_DYN_COS + b);
+            dyn_alpha[b] = k(DE_DYN_ALPHA + b);
+        }
+    }
+};
+
 struct DeEsserApply {
     double conf[3], base[3], red[3], built_gain[3];
     Bq dyn[3];        // live dynamic-EQ coefficients
@@ -228,9 +260,9 @@ struct DeEsserApply {
     // One sample of the second half of DeEsser::process_sample (deesser.rs:452-547).
     template <bool HEAD>
     AF_HD float sample(float input, double voice_db, const double (&level_db)[3], const double (&conf_target)[3], int n,
-                       int fade_total, const DeConst& k, const CandidateParams* p, double (*pyz)[2]) {
-        const double det_attack = k(DE_DET_ATTACK), det_release = k(DE_DET_RELEASE);
-        const double max_red = k(DE_MAX_RED);
+                       int fade_total, const DeApplyConst& k, const CandidateParams* p, double (*pyz)[2]) {
+        const double det_attack = k.det_attack, det_release = k.det_release;
+        const double max_red = k.max_red;
         double target[3];
         double target_sum = 0.0;
 #pragma unroll
@@ -242,21 +274,21 @@ struct DeEsserApply {
                 const bool voice_active = voice_db > -55.0 || level_db[b] > -55.0;
                 if (voice_active) {
                     const double base_target = clampd(ratio_db * 0.45, 0.0, 24.0);
-                    const double c = base_target < base[b] ? k(DE_BASE_FALL) : k(DE_BASE_RISE);
+                    const double c = base_target < base[b] ? k.base_fall : k.base_rise;
                     base[b] = c * base[b] + (1.0 - c) * base_target;
                 } else {
-                    base[b] *= k(DE_BASE_INACTIVE);
+                    base[b] *= k.base_inactive;
                 }
-                const double conf_gain = norm_range(conf[b], k(DE_CONF_FLOOR), 1.0);
-                const double over_db = fmax(ratio_db - base[b] - k(DE_TRIGGER), 0.0);
-                tr = clampd(over_db * k(DE_SLOPE) * conf_gain, 0.0, k(DE_CAP));
-            } else if (level_db[b] > k(DE_THRESHOLD)) {
-                const double level_over = level_db[b] - k(DE_THRESHOLD);
-                const double ratio_over = ratio_db - k(DE_RATIO_THR);
+                const double conf_gain = norm_range(conf[b], k.conf_floor, 1.0);
+                const double over_db = fmax(ratio_db - base[b] - k.trigger, 0.0);
+                tr = clampd(over_db * k.slope * conf_gain, 0.0, k.cap);
+            } else if (level_db[b] > k.threshold) {
+                const double level_over = level_db[b] - k.threshold;
+                const double ratio_over = ratio_db - k.ratio_thr;
                 if (ratio_over > 0.0) {
                     const double over_db = fmin(level_over, ratio_over);
                     const double conf_gain = norm_range(conf[b], 0.22, 1.0);
-                    tr = clampd(k(DE_RATIO_FACTOR) * over_db * conf_gain, 0.0, k(DE_MANUAL_CAP));
+                    tr = clampd(k.ratio_factor * over_db * conf_gain, 0.0, k.manual_cap);
                 }
             }
             target[b] = tr;
@@ -267,7 +299,7 @@ struct DeEsserApply {
 #pragma unroll
             for (int b = 0; b < 3; ++b) target[b] *= scale;
         }
-        const double attack = k(DE_ATTACK), release = k(DE_RELEASE);
+        const double attack = k.attack, release = k.release;
         float processed = input;
         double total_red = 0.0;
 #pragma unroll
@@ -277,7 +309,7 @@ struct DeEsserApply {
             const double dyn_gain = -red[b];
             if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate: cancels any fade, keeps z1/z2
                 built_gain[b] = dyn_gain;
-                dyn[b] = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), dyn_gain);
+                dyn[b] = design_peaking(k.dyn_cos[b], k.dyn_alpha[b], dyn_gain);
                 cancel[b] = true;
             }
             double y;
@@ -299,9 +331,11 @@ struct DeEsserApply {
     }
 
     // x: chunk column (in place); w[0..6]: ring columns at chunk start (voice dB, 3 level dB, 3 confidence targets)
-    AF_HD void run(float* x, double* const (&w)[7], size_t stride, int n0, int len, int fade_total, const DeConst& k,
+    AF_HD void run(float* x, double* const (&w)[7], size_t stride, int n0, int len, int fade_total, const DeConst& table,
                    const CandidateParams* p, BlockClock clk, float* rows_de, Staging stg) {
         constexpr int U = kGroup;
+        DeApplyConst k;
+        k.load(table);
         int t_head = 0;
         if (n0 < fade_total) {
             double pyz[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
