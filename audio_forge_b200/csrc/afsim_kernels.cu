@@ -86,7 +86,13 @@ AF_R_KERNEL(k_comp_r5, body_comp_r5)
 AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_R_KERNEL(k_de_ra, body_de_ra)
-AF_R_KERNEL(k_de_rc, body_de_rc)
+// R_c keeps ~60 doubles of state and constants live: capping it at 128 registers (4 blocks of 128 threads per
+// SM) trades a few L1-resident spills for twice the warps that hide its long division / exp10 chains.
+__global__ void __launch_bounds__(128, 4) k_de_rc(BatchArgs a, ChunkArgs ck) {
+    AF_STREAM_INDEX();
+    const Staging stg{a.stage_inputs ? stage_smem : nullptr, (int)blockDim.x, (int)threadIdx.x, 0};
+    body_de_rc(a, ck, s, stg);
+}
 
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
 // A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping

@@ -335,7 +335,14 @@ struct EqStage {
 };
 
 // ---- dynamic-EQ de-esser (dsp/deesser.rs:405-547) -----------------------------------------------------------
-AF_HD Bq design_peaking(double cs, double alpha, double gain_db) {  // dsp/biquad.rs:110-126,180-181
+// Not inlined on the device: the de-esser's serial kernel calls it for three bands per sample, and one warp
+// per SM walking a loop body that does not fit the instruction cache stalls on instruction fetch.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+Bq design_peaking(double cs, double alpha, double gain_db) {  // dsp/biquad.rs:110-126,180-181
     const double a = af_exp10(gain_db / 40.0);
     const double b0 = 1.0 + alpha * a;
     const double b1 = -2.0 * cs;
