@@ -65,6 +65,17 @@ STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20
                "de_ra": 36, "de_mb": 88, "de_rc": 64}
 
 
+# DRAM traffic per launch (MB, dram__bytes_read.sum + dram__bytes_write.sum) of each stage kernel from the committed
+# `ncu --set full` capture of the default workload shape (profiles/r01_v9_ncu_kernels.md: 4096 streams, chunk 1024).
+NCU_TRAFFIC_MB = {"input": 0.3, "eq": 16.6, "comp_r1": 93.5, "comp_m2": 161.9, "comp_r3": 81.5, "comp_m4": 109.3,
+                  "comp_r5": 34.8, "comp_m6": 50.9, "lim_m": 19.0, "lim_r": 52.1, "tp_fir_in": 18.1, "tp_r": 34.5,
+                  "tp_fir_out": 17.5}
+# warp-level instructions per launch of the same capture (smsp__inst_executed.sum), for the issue-rate fraction
+NCU_WARP_INSTR = {"input": 2.25e6, "eq": 8.53e6, "comp_r1": 6.54e6, "comp_m2": 5.25e7, "comp_r3": 5.13e6, "comp_m4": 3.62e7,
+                  "comp_r5": 3.91e6, "comp_m6": 1.47e7, "lim_m": 9.4e6, "lim_r": 8.84e6, "tp_fir_in": 2.51e7, "tp_r": 8.53e6,
+                  "tp_fir_out": 2.34e7}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,8 +357,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 stage_table.append({"stage": name, "share": ms / total_ms, "launch_ms": per_launch_ms,
                                     "GBps": bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None})
             dominant = max(stage_table, key=lambda r: r["share"])
+            default_shape = (args.workload == "c2" and n_pairs == 4096 and chunk == 1024)
+            traffic = NCU_TRAFFIC_MB.get(dominant["stage"]) if default_shape else None
+            if default_shape:  # instruction-issue view of every stage (the bound that actually binds)
+                sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
+                issue_peak = 148 * 4 * sm_clock  # warp instructions per second, all SMSPs
+                for row in stage_table:
+                    wi = NCU_WARP_INSTR.get(row["stage"])
+                    if wi and row["launch_ms"]:
+                        row["warp_instr_per_s"] = wi / (row["launch_ms"] * 1e-3)
+                        row["issue_frac"] = row["warp_instr_per_s"] / issue_peak
             roofline = {"bound": "hbm", "achieved": dominant["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                        "frac": dominant["GBps"] / hbm_peak if dominant["GBps"] else None, "traffic": None,
+                        "frac": dominant["GBps"] / hbm_peak if dominant["GBps"] else None,
+                        "traffic": traffic * 1e6 if traffic is not None else None,
                         "kernel": dominant["stage"], "peak_source": peak_src,
                         "timing": "mean launch duration of the stage in a serialised pass (CUDA events around every "
                                   "launch of 64 chunks); in the timed wavefront the stage kernels overlap",
