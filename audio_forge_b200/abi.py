@@ -127,6 +127,40 @@ class AfChainMetrics(C.Structure):
     )
 
 
+class AfAutoMakeupSettings(C.Structure):
+    """settings dict of simulate_auto_makeup_control (python_api.rs:168-192)."""
+    _fields_ = [
+        ("threshold_db", C.c_double),
+        ("ratio", C.c_double),
+        ("attack_ms", C.c_double),
+        ("release_ms", C.c_double),
+        ("makeup_gain_db", C.c_double),
+        ("target_lufs", C.c_double),
+        ("vad_reliability", C.c_double),
+        ("adaptive_release", C.c_uint8),
+        ("sidechain_highpass_enabled", C.c_uint8),
+        ("reserved", C.c_uint8 * 6),
+    ]
+
+
+MAKEUP_CONTROL_BLOCK = 480
+MAKEUP_TRACES = ("makeup_gain_db", "activity", "reliability", "gain_reduction_db", "input_rms_db", "output_rms_db")
+
+
+def make_makeup_settings(**overrides) -> AfAutoMakeupSettings:
+    """Reference defaults (python_api.rs:168-192) with overrides."""
+    values = dict(threshold_db=-24.0, ratio=3.0, attack_ms=10.0, release_ms=180.0, makeup_gain_db=0.0, target_lufs=-18.0,
+                  vad_reliability=1.0, adaptive_release=True, sidechain_highpass_enabled=True)
+    unknown = set(overrides) - set(values)
+    if unknown:
+        raise KeyError(f"unknown auto-makeup settings: {sorted(unknown)}")
+    values.update(overrides)
+    s = AfAutoMakeupSettings()
+    for key, value in values.items():
+        setattr(s, key, int(bool(value)) if key in ("adaptive_release", "sidechain_highpass_enabled") else float(value))
+    return s
+
+
 class AfEqRenderStats(C.Structure):
     _fields_ = [
         ("input_sample_peak", C.c_float),

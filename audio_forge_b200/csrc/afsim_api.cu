@@ -116,6 +116,8 @@ struct StageDesc {
 struct Batch {
     BatchArgs args{};
     std::vector<StageDesc> stages;
+    std::vector<uint32_t> members;  // caller's pair index of stream s
+    size_t mk_ring_elems = 0;       // auto makeup: doubles in args.mk_ring
     int chunk = 0, slots = 0, eq_k = 0;
     std::vector<cudaEvent_t> events;  // [stage][slot]
     ~Batch() {
@@ -176,10 +178,26 @@ struct PassageSource {
     int synth_kind = 0;
 };
 
+struct SweepOptions {
+    int block_samples = 0;               // 0: the rate's analysis block (python_api.rs:512-513); 480 for the makeup control sim
+    const double* const* vad = nullptr;  // per pair: per-block VAD probabilities or nullptr (simulate_auto_makeup_control)
+    bool makeup_rows = false;            // keep the per-block makeup / activity / reliability traces
+};
+
+int lcm_int(int a, int b) {
+    int x = a, y = b;
+    while (y) {
+        const int t = x % y;
+        x = y;
+        y = t;
+    }
+    return a / x * b;
+}
+
 int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_len, size_t n_passages, double fs,
                 const AfCandidate* candidates, size_t n_candidates, const CandidatePlan* preplanned,
                 const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs, int want_audio,
-                AfsimSweep** out_sweep) {
+                AfsimSweep** out_sweep, const SweepOptions& opt = SweepOptions()) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
     h->error.clear();
     if (!out_sweep) return set_error(h, AFSIM_INVALID_ARGUMENT, "out_sweep is null");
@@ -289,9 +307,9 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         a.n_streams = S;
         a.stride = S_pad;
         a.n_samples = T;
-        a.block_samples = rate.block_samples;
+        a.block_samples = opt.block_samples > 0 ? opt.block_samples : rate.block_samples;
         a.fade_samples = rate.fade_samples;
-        a.n_rows = (T + rate.block_samples - 1) / rate.block_samples;
+        a.n_rows = (T + a.block_samples - 1) / a.block_samples;
         a.n_pad = 2;
         while (a.n_pad < a.n_rows) a.n_pad <<= 1;
         a.params = d_params;
@@ -308,6 +326,16 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         chunk = round_up(chunk, 8);
         if (a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG)
             chunk = round_up(chunk, kInputBlock);  // the cleanup stage works in whole 480-sample blocks
+        const bool auto_makeup = (a.structure & ST_AUTO_MAKEUP) != 0;
+        if (auto_makeup) {
+            // the makeup steps at block ends and a block is fed to the loudness meter (or not) as a whole: chunks are
+            // whole blocks (and still multiples of 8, and of 480 with the cleanup stage)
+            int unit = lcm_int(a.block_samples, 8);
+            if (a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG) unit = lcm_int(unit, kInputBlock);
+            if (unit > 16384)
+                return set_error(h, AFSIM_UNSUPPORTED, "auto makeup with the input cleanup stage is not available at this sample rate");
+            chunk = round_up(chunk, unit);
+        }
         batch->chunk = chunk;
         const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
         // ring slots = chunks in flight + 1; few-stream batches need the stage wavefront to fill the GPU
@@ -322,6 +350,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         std::vector<uint32_t> cand(S_pad, 0), pair(S_pad, 0);
         std::vector<uint64_t> src_off(S_pad, 0), audio_off(S_pad, 0);
         uint32_t max_sections = 0;
+        batch->members = members;
         for (int s = 0; s < S; ++s) {
             const uint32_t i = members[s];
             cand[s] = candidate_of(i);
@@ -363,11 +392,11 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
             }
         }
-        a.stage_inputs = split ? 1 : 0;
+        a.stage_inputs = (split || auto_makeup) ? 1 : 0;  // the compressor's serial kernels only run staged
         {
             int n_w = 0;
             if (split && (a.structure & ST_LIMITER)) n_w = 1;
-            if (split && (a.structure & ST_COMPRESSOR)) n_w = 4;
+            if ((split || auto_makeup) && (a.structure & ST_COMPRESSOR)) n_w = 4;
             if (a.structure & ST_DEESSER) n_w = 7;  // the de-esser is always R/M split (afsim_deesser.h)
             for (int k = 0; k < n_w; ++k) AF_CUDA(h, sweep->mem.alloc(&a.w[k], ring_elems));
         }
@@ -380,6 +409,40 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             a.de_tab = de_tab;
         }
         if (a.structure & ST_COMPRESSOR) AF_CUDA(h, sweep->mem.alloc(&a.st_comp, kStateCompressor * sp));
+        if (auto_makeup) {
+            const MakeupConst mc = makeup_constants(fs, a.block_samples, T);
+            if (a.block_samples / mc.slot > kMaxMakeupSub)
+                return set_error(h, AFSIM_UNSUPPORTED, "auto makeup: block spans too many loudness-window slots");
+            MakeupConst* d_mc = nullptr;
+            AF_CUDA(h, sweep->mem.alloc(&d_mc, 1));
+            AF_CUDA(h, cudaMemcpyAsync(d_mc, &mc, sizeof mc, cudaMemcpyHostToDevice, h->stream));
+            AF_CUDA(h, cudaStreamSynchronize(h->stream));  // mc is a local
+            a.mk_const = d_mc;
+            batch->mk_ring_elems = static_cast<size_t>(2 * mc.n_slots + 2 * kMaxMakeupSub) * sp;
+            AF_CUDA(h, sweep->mem.alloc(&a.mk_ring, batch->mk_ring_elems));
+            AF_CUDA(h, sweep->mem.alloc(&a.st_mk, kStateMakeup * sp));
+            if (opt.makeup_rows) AF_CUDA(h, sweep->mem.alloc(&a.mk_rows, static_cast<size_t>(3) * std::max(a.n_rows, 1) * sp));
+            if (opt.vad) {
+                std::vector<int64_t> voff(S_pad, -1);
+                std::vector<double> pool;
+                for (int s = 0; s < S; ++s) {
+                    const double* v = opt.vad[members[s]];
+                    if (!v) continue;
+                    voff[s] = static_cast<int64_t>(pool.size());
+                    pool.insert(pool.end(), v, v + a.n_rows);
+                }
+                double* d_vad = nullptr;
+                int64_t* d_voff = nullptr;
+                AF_CUDA(h, sweep->mem.alloc(&d_vad, pool.size()));
+                AF_CUDA(h, sweep->mem.alloc(&d_voff, S_pad));
+                if (!pool.empty())
+                    AF_CUDA(h, cudaMemcpyAsync(d_vad, pool.data(), pool.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                AF_CUDA(h, cudaMemcpyAsync(d_voff, voff.data(), S_pad * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+                AF_CUDA(h, cudaStreamSynchronize(h->stream));
+                a.mk_vad = d_vad;
+                a.mk_vad_off = d_voff;
+            }
+        }
         AF_CUDA(h, sweep->mem.alloc(&a.st_eq, static_cast<size_t>(kStateEqPerSection * kMaxSections) * sp));
         AF_CUDA(h, sweep->mem.alloc(&a.rows, static_cast<size_t>(4) * std::max(a.n_rows, 1) * sp));
         AF_CUDA(h, sweep->mem.alloc(&a.accum, sp));
@@ -410,11 +473,13 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             push_eq();
         }
         if (a.structure & ST_COMPRESSOR) {
-            if (split)
+            if (split || auto_makeup) {
                 for (int op : {SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6})
                     batch->stages.push_back({SK_SPLIT, op});
-            else
+                if (auto_makeup) batch->stages.push_back({SK_SPLIT, SP_COMP_R7});
+            } else {
                 batch->stages.push_back({SK_COMPRESSOR, 0});
+            }
         }
         if (a.structure & ST_LIMITER) {
             if (split)
@@ -458,6 +523,8 @@ int run_batch(AfsimHandle* h, Batch& b) {
     AF_CUDA(h, cudaMemsetAsync(a.accum, 0, static_cast<size_t>(a.stride) * sizeof(StreamAccum), h->stream));
     AF_CUDA(h, cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
     if (a.structure & ST_DEESSER) AF_CUDA(h, launch_expand_deesser(a, h->stream));
+    if (a.mk_ring) AF_CUDA(h, cudaMemsetAsync(a.mk_ring, 0, b.mk_ring_elems * sizeof(double), h->stream));
+    if (a.mk_rows) AF_CUDA(h, cudaMemsetAsync(a.mk_rows, 0, static_cast<size_t>(3) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
     if (T > 0) {
         AF_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         auto stream_of = [&](int i) {
@@ -712,6 +779,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
     if (err == cudaSuccess)
         err = cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream);
     if (err == cudaSuccess && (a.structure & ST_DEESSER)) err = launch_expand_deesser(a, h->stream);
+    if (err == cudaSuccess && a.mk_ring) err = cudaMemsetAsync(a.mk_ring, 0, b.mk_ring_elems * sizeof(double), h->stream);
     for (int c = 0; c < n_chunks && err == cudaSuccess; ++c) {
         ChunkArgs ck;
         ck.n0 = c * b.chunk;
@@ -945,6 +1013,126 @@ int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_
     out_stats->non_finite_output = acc.non_finite;
     guard.reset();
     return AFSIM_OK;
+}
+
+// ---- simulate_auto_makeup_control (python_api.rs:118-276) ------------------------------------------------------------
+
+void afsim_auto_makeup_settings_default(AfAutoMakeupSettings* s) {
+    if (!s) return;
+    std::memset(s, 0, sizeof *s);
+    s->threshold_db = -24.0;
+    s->ratio = 3.0;
+    s->attack_ms = 10.0;
+    s->release_ms = 180.0;
+    s->makeup_gain_db = 0.0;
+    s->target_lufs = -18.0;
+    s->vad_reliability = 1.0;
+    s->adaptive_release = 1;
+    s->sidechain_highpass_enabled = 1;
+}
+
+int afsim_auto_makeup_sweep(AfsimHandle* h, const float* const* audio, const size_t* len, size_t n_streams, double sample_rate,
+                            const double* const* vad, const double* noise_floor_db, const double* noise_reliability,
+                            const AfAutoMakeupSettings* settings, float* const* out_traces, float* const* out_audio) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (n_streams == 0) return AFSIM_OK;
+    if (!audio || !len || !noise_floor_db || !noise_reliability || !settings || !out_traces)
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    std::vector<CandidatePlan> plans(n_streams);
+    std::vector<uint32_t> idx(n_streams);
+    bool any_vad = false, want_audio = false;
+    for (size_t i = 0; i < n_streams; ++i) {
+        std::string msg;
+        const bool has_vad = vad && vad[i];
+        const int rc = plan_makeup_control(settings[i], sample_rate, noise_floor_db[i], noise_reliability[i], has_vad, &plans[i], &msg);
+        if (rc != AFSIM_OK) return set_error(h, rc, msg);
+        if (!(plans[i].structure & ST_AUTO_MAKEUP))  // Compressor::new found no loudness meter for this rate (:180-190)
+            return set_error(h, AFSIM_UNSUPPORTED, "auto makeup needs a sample rate the loudness meter supports "
+                                                   "(8000, 16000, 32000, 44100, 48000, 88200 or 96000 Hz)");
+        if (!audio[i] && len[i]) return set_error(h, AFSIM_INVALID_ARGUMENT, "null audio");
+        if (has_vad) {
+            const size_t blocks = (len[i] + AFSIM_MAKEUP_CONTROL_BLOCK - 1) / AFSIM_MAKEUP_CONTROL_BLOCK;
+            for (size_t b = 0; b < blocks; ++b)
+                if (!std::isfinite(vad[i][b]) || !(vad[i][b] >= 0.0 && vad[i][b] <= 1.0))
+                    return set_error(h, AFSIM_INVALID_ARGUMENT, "VAD probabilities must be finite and between 0 and 1");
+            any_vad = true;
+        }
+        if (out_audio && out_audio[i]) want_audio = true;
+        idx[i] = static_cast<uint32_t>(i);
+    }
+    PassageSource src;
+    src.host = audio;
+    SweepOptions opt;
+    opt.block_samples = AFSIM_MAKEUP_CONTROL_BLOCK;
+    opt.vad = any_vad ? vad : nullptr;
+    opt.makeup_rows = true;
+    AfsimSweep* sweep = nullptr;
+    int rc = build_sweep(h, src, len, n_streams, sample_rate, nullptr, n_streams, plans.data(), idx.data(), idx.data(), n_streams,
+                         want_audio ? 1 : 0, &sweep, opt);
+    if (rc != AFSIM_OK) return rc;
+    std::unique_ptr<AfsimSweep> guard(sweep);
+    rc = afsim_sweep_launch(h, sweep);
+    if (rc != AFSIM_OK) return rc;
+    std::vector<float> rows, mk_rows;
+    for (auto& bp : sweep->batches) {
+        const BatchArgs& a = bp->args;
+        const size_t n_rows = static_cast<size_t>(a.n_rows), sp = static_cast<size_t>(a.stride);
+        if (n_rows == 0) continue;
+        rows.resize(4 * n_rows * sp);
+        mk_rows.resize(3 * n_rows * sp);
+        AF_CUDA(h, cudaMemcpyAsync(rows.data(), a.rows, rows.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        AF_CUDA(h, cudaMemcpyAsync(mk_rows.data(), a.mk_rows, mk_rows.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        AF_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int s = 0; s < a.n_streams; ++s) {
+            float* out = out_traces[bp->members[s]];
+            if (!out) continue;
+            for (size_t r = 0; r < n_rows; ++r) {
+                out[0 * n_rows + r] = mk_rows[(0 * n_rows + r) * sp + s];  // makeup_gain_db
+                out[1 * n_rows + r] = mk_rows[(1 * n_rows + r) * sp + s];  // activity
+                out[2 * n_rows + r] = mk_rows[(2 * n_rows + r) * sp + s];  // reliability
+                out[3 * n_rows + r] = rows[(2 * n_rows + r) * sp + s];     // gain_reduction_db at the block end
+                out[4 * n_rows + r] = rows[(0 * n_rows + r) * sp + s];     // input_rms_db
+                out[5 * n_rows + r] = rows[(1 * n_rows + r) * sp + s];     // output_rms_db
+            }
+        }
+    }
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (want_audio)
+        for (size_t i = 0; i < n_streams; ++i)
+            if (out_audio[i] && len[i]) {
+                rc = afsim_sweep_collect_audio(h, sweep, i, out_audio[i], len[i]);
+                if (rc != AFSIM_OK) return rc;
+            }
+    return AFSIM_OK;
+}
+
+int afsim_auto_makeup_control(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const double* vad_probabilities,
+                              size_t n_vad, double noise_floor_db, double noise_reliability, const AfAutoMakeupSettings* settings,
+                              float* out_traces, float* out_audio) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    if (!settings || (!audio && n) || (!vad_probabilities && n_vad) || (!out_traces && n))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    // argument checks in the reference's order (python_api.rs:136-166)
+    if (!std::isfinite(sample_rate) || sample_rate <= 0.0)
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "sample_rate must be positive and finite");
+    if (!std::isfinite(noise_floor_db) || !std::isfinite(noise_reliability) || !(noise_reliability >= 0.0 && noise_reliability <= 1.0))
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "noise evidence must be finite and reliability must be between 0 and 1");
+    for (size_t i = 0; i < n_vad; ++i)
+        if (!std::isfinite(vad_probabilities[i]) || !(vad_probabilities[i] >= 0.0 && vad_probabilities[i] <= 1.0))
+            return set_error(h, AFSIM_INVALID_ARGUMENT, "VAD probabilities must be finite and between 0 and 1");
+    const size_t block_count = (n + AFSIM_MAKEUP_CONTROL_BLOCK - 1) / AFSIM_MAKEUP_CONTROL_BLOCK;
+    if (n_vad != 0 && n_vad != block_count)
+        return set_error(h, AFSIM_INVALID_ARGUMENT, "expected " + std::to_string(block_count) +
+                                                        " VAD probabilities at the 10 ms control cadence, got " + std::to_string(n_vad));
+    const float* audios[1] = {audio};
+    const size_t lens[1] = {n};
+    const double* vads[1] = {n_vad ? vad_probabilities : nullptr};
+    float* traces[1] = {out_traces};
+    float* outs[1] = {out_audio};
+    return afsim_auto_makeup_sweep(h, audios, lens, 1, sample_rate, vads, &noise_floor_db, &noise_reliability, settings, traces,
+                                   out_audio ? outs : nullptr);
 }
 
 }  // extern "C"

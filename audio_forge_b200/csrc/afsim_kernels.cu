@@ -83,6 +83,7 @@ extern __shared__ __align__(16) unsigned char stage_smem[];
 AF_R_KERNEL(k_comp_r1, body_comp_r1)
 AF_R_KERNEL(k_comp_r3, body_comp_r3)
 AF_R_KERNEL(k_comp_r5, body_comp_r5)
+AF_R_KERNEL(k_comp_r7, body_comp_r7)
 AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_R_KERNEL(k_de_ra, body_de_ra)
@@ -329,6 +330,7 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         case SP_DE_RA: k_de_ra<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_DE_MB: k_de_mb<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_DE_RC: k_de_rc<<<rgrid, rb, rsm, st>>>(a, ck); break;
+        case SP_COMP_R7: k_comp_r7<<<rgrid, rb, rsm, st>>>(a, ck); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

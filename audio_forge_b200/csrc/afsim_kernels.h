@@ -24,7 +24,8 @@ cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cuda
 enum SplitOp {
     SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6,
     SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT,
-    SP_DE_RA, SP_DE_MB, SP_DE_RC
+    SP_DE_RA, SP_DE_MB, SP_DE_RC,
+    SP_COMP_R7  // auto makeup (after M6)
 };
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);

@@ -35,6 +35,8 @@ enum LaneFlag : uint32_t {
     LF_DE_AUTO = 1u << 1,
     LF_C_ADAPTIVE = 1u << 2,
     LF_C_SIDECHAIN = 1u << 3,
+    LF_C_AUTO_MAKEUP = 1u << 4, // compressor auto makeup (dsp/compressor.rs:598-653) over the momentary loudness meter
+    LF_C_EVIDENCE = 1u << 5,    // simulate_auto_makeup_control: per-block VAD / noise evidence (dsp/compressor.rs:528-581)
 };
 
 // De-esser constants (CandidateParams::de).
@@ -76,6 +78,10 @@ struct CandidateParams {
     // compressor (dsp/compressor.rs)
     double c_threshold, c_factor, c_knee, c_attack, c_det_release, c_release, c_rms, c_makeup_lin, c_sc, c_band,
         c_fast, c_charge, c_slow;
+    // auto makeup (dsp/compressor.rs:598-653, 528-581): manual makeup in dB, clamped target, the three per-sample
+    // smoothing coefficients (raised to the block length at every block end), evidence of the control simulator
+    double c_makeup_db, c_target_lufs, c_mk_smooth, c_mk_relax, c_mk_activity;
+    double c_ev_vad_reliability, c_ev_noise_floor_db, c_ev_live_reliability, c_ev_cfg_reliability;
     // limiter (dsp/limiter.rs)
     double l_ceil, l_release;
     // fixed input high-pass (audio/processor/routing.rs:826-843)
@@ -90,7 +96,22 @@ enum StructureFlag : uint32_t {
     ST_LIMITER = 1u << 3,
     ST_EQ = 1u << 4,
     ST_INPUT_TRUE_PEAK = 1u << 5,   // simulate_eq_v2: true-peak detector over the input as well
+    ST_AUTO_MAKEUP = 1u << 6,       // compressor with auto makeup: M6 hands the gain to the serial makeup stage R7
 };
+
+// Momentary loudness meter of the auto makeup (dsp/loudness.rs over the `ebur128` crate, mode M): the folded
+// 4th-order K-weighting section for the sample rate and the geometry of the 400 ms window.  The window is kept as
+// `n_slots` partial sums of `slot` samples each (slot = gcd(block, window): a block always starts on a slot
+// boundary), so a block end costs n_slots loads instead of a pass over the whole 400 ms ring.
+struct MakeupConst {
+    double b[5], a[5];
+    int window;     // samples in 400 ms
+    int slot;       // samples per partial sum
+    int n_slots;    // window / slot
+    int tail_from;  // (T mod block) mod slot: the render's final partial block leaves a slot's samples >= tail_from
+};
+constexpr int kMaxMakeupSub = 16;  // partial sums one block may span (block / slot)
+
 
 struct StreamAccum {
     double sum_in;
@@ -114,6 +135,7 @@ constexpr int kStateEqPerSection = 2;
 constexpr int kStateCompressor = 12;
 constexpr int kStateLimiter = 4;
 constexpr int kStateTruePeak = 80;
+constexpr int kStateMakeup = 12;
 
 struct BatchArgs {
     const CandidateParams* params;
@@ -137,6 +159,12 @@ struct BatchArgs {
     double* st_lim;               // [kStateLimiter][S_pad]
     double* st_tp;                // [kStateTruePeak][S_pad]
     float* rows;                  // [4][n_rows][S_pad]
+    double* st_mk;                // [kStateMakeup][S_pad] auto makeup + loudness meter state
+    double* mk_ring;              // [2][n_slots][S_pad] the meter's window: full partial sums, then tail partial sums
+    float* mk_rows;               // [3][n_rows][S_pad] makeup dB / activity / reliability at block ends, or nullptr
+    const double* mk_vad;         // pool of per-block VAD probabilities (LF_C_EVIDENCE), or nullptr
+    const int64_t* mk_vad_off;    // [S_pad] offset of the stream's probabilities in mk_vad, -1 = no evidence
+    const MakeupConst* mk_const;  // loudness meter constants of the sample rate
     StreamAccum* accum;           // [S_pad]
     const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
     const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)

@@ -243,6 +243,23 @@ void plan_compressor(const AfChainSettings& s, double fs, CandidateParams& p) {
     p.c_slow = time_constant_to_coeff(400.0, fs);
     if (adaptive) p.flags |= LF_C_ADAPTIVE;
     if (s.compressor_sidechain_highpass_enabled) p.flags |= LF_C_SIDECHAIN;
+    // auto makeup (dsp/compressor.rs:318-331,598-653): set_makeup_gain runs before set_auto_makeup_enabled, so the
+    // smoothed makeup starts at the manual value; without a meter for the rate the switch stays off (:319)
+    p.c_makeup_db = s.compressor_makeup_gain_db;
+    p.c_target_lufs = rclamp(s.compressor_target_lufs, -24.0, -12.0);
+    p.c_mk_smooth = time_constant_to_coeff(200.0, fs);
+    p.c_mk_activity = time_constant_to_coeff(200.0, fs);
+    p.c_mk_relax = time_constant_to_coeff(1500.0, fs);
+    if (s.compressor_auto_makeup_enabled && loudness_meter_supports(fs)) p.flags |= LF_C_AUTO_MAKEUP;
+}
+
+int gcd_int(int a, int b) {
+    while (b) {
+        const int t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
 }
 
 }  // namespace
@@ -417,9 +434,6 @@ int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& s
         if (rc != AFSIM_OK) return rc;
     }
     if (s.input_stage > AF_INPUT_CLEANUP_STRONG) return fail(error, AFSIM_INVALID_ARGUMENT, "unknown input_stage");
-    if (s.compressor_enabled && s.compressor_auto_makeup_enabled && loudness_meter_supports(fs))
-        return fail(error, AFSIM_UNSUPPORTED,
-                    "compressor auto makeup (ebur128 momentary loudness) is not available on the GPU path yet");
 
     std::memset(out, 0, sizeof *out);
     CandidateParams& p = out->params;
@@ -436,6 +450,7 @@ int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& s
     if (s.compressor_enabled) {
         out->structure |= ST_COMPRESSOR;
         plan_compressor(s, fs, p);
+        if (p.flags & LF_C_AUTO_MAKEUP) out->structure |= ST_AUTO_MAKEUP;
     }
     // python_api.rs:470-487
     const float effective_ceiling =
@@ -460,6 +475,82 @@ int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& s
     out->input_stage = s.input_stage;
     if (s.input_stage == AF_INPUT_DC_HP80)  // processor.rs:74-76
         store(p.in_hp, design_biquad(BqKind::HighPass, 80.0, 0.0, 0.707, fs));
+    return AFSIM_OK;
+}
+
+// Loudness meter constants (dsp/loudness.rs:99-131 over the `ebur128` crate 0.1.10, mode M).  The crate is not in the
+// reference tree; it ports libebur128, whose K-weighting is the BS.1770 high shelf (f0 1681.97 Hz, +4 dB, Q 0.7072)
+// times the RLB high-pass (f0 38.135 Hz, Q 0.5003), re-derived for the sample rate and folded into one 4th-order
+// section -- parity with the crate is unpinned.
+MakeupConst makeup_constants(double fs, int block_samples, int n_samples) {
+    MakeupConst m;
+    std::memset(&m, 0, sizeof m);
+    const double rate = static_cast<double>(static_cast<uint32_t>(std::min<size_t>(as_usize(fs), 0xffffffffu)));
+    const double f0 = 1681.974450955533, G = 3.999843853973347, Q = 0.7071752369554196;
+    double K = std::tan(kPi * f0 / rate);
+    const double Vh = std::pow(10.0, G / 20.0);
+    const double Vb = std::pow(Vh, 0.4996667741545416);
+    const double a0 = 1.0 + K / Q + K * K;
+    const double pb[3] = {(Vh + Vb * K / Q + K * K) / a0, 2.0 * (K * K - Vh) / a0, (Vh - Vb * K / Q + K * K) / a0};
+    const double pa[3] = {1.0, 2.0 * (K * K - 1.0) / a0, (1.0 - K / Q + K * K) / a0};
+    const double f1 = 38.13547087602444, Q1 = 0.5003270373238773;
+    K = std::tan(kPi * f1 / rate);
+    const double rb[3] = {1.0, -2.0, 1.0};
+    const double ra[3] = {1.0, 2.0 * (K * K - 1.0) / (1.0 + K / Q1 + K * K), (1.0 - K / Q1 + K * K) / (1.0 + K / Q1 + K * K)};
+    m.b[0] = pb[0] * rb[0];
+    m.b[1] = pb[0] * rb[1] + pb[1] * rb[0];
+    m.b[2] = pb[0] * rb[2] + pb[1] * rb[1] + pb[2] * rb[0];
+    m.b[3] = pb[1] * rb[2] + pb[2] * rb[1];
+    m.b[4] = pb[2] * rb[2];
+    m.a[0] = pa[0] * ra[0];
+    m.a[1] = pa[0] * ra[1] + pa[1] * ra[0];
+    m.a[2] = pa[0] * ra[2] + pa[1] * ra[1] + pa[2] * ra[0];
+    m.a[3] = pa[1] * ra[2] + pa[2] * ra[1];
+    m.a[4] = pa[2] * ra[2];
+    m.window = static_cast<int>(static_cast<uint64_t>(rate) * 400 / 1000);
+    const int block = std::max(block_samples, 1);
+    m.slot = std::max(gcd_int(block, std::max(m.window, 1)), 1);
+    m.n_slots = std::max(m.window / m.slot, 1);
+    m.tail_from = (n_samples % block) % m.slot;
+    return m;
+}
+
+// simulate_auto_makeup_control (python_api.rs:118-276): a compressor alone, knee 6, auto makeup forced on.
+int plan_makeup_control(const AfAutoMakeupSettings& s, double fs, double noise_floor_db, double noise_reliability,
+                        bool has_vad, CandidatePlan* out, std::string* error) {
+    if (!std::isfinite(fs) || fs <= 0.0) return fail(error, AFSIM_INVALID_ARGUMENT, "sample_rate must be positive and finite");
+    if (!std::isfinite(noise_floor_db) || !std::isfinite(noise_reliability) || !(noise_reliability >= 0.0 && noise_reliability <= 1.0))
+        return fail(error, AFSIM_INVALID_ARGUMENT, "noise evidence must be finite and reliability must be between 0 and 1");
+    if (!std::isfinite(s.vad_reliability) || !(s.vad_reliability >= 0.0 && s.vad_reliability <= 1.0))
+        return fail(error, AFSIM_INVALID_ARGUMENT, "vad_reliability must be finite and between 0 and 1");
+    std::memset(out, 0, sizeof *out);
+    CandidateParams& p = out->params;
+    for (int i = 0; i < kMaxSections; ++i) store_identity(p.eq[i]);
+    AfChainSettings cs;
+    chain_settings_default(&cs);
+    cs.compressor_threshold_db = s.threshold_db;
+    cs.compressor_ratio = s.ratio;
+    cs.compressor_attack_ms = s.attack_ms;
+    cs.compressor_release_ms = s.release_ms;
+    // Compressor::new keeps release_ms as the base release (dsp/compressor.rs:133-202); set_adaptive_release(false)
+    // re-derives the gain-reduction release from it (:247-260)
+    cs.compressor_base_release_ms = s.release_ms;
+    cs.compressor_makeup_gain_db = s.makeup_gain_db;
+    cs.compressor_target_lufs = s.target_lufs;
+    cs.compressor_adaptive_release = s.adaptive_release;
+    cs.compressor_sidechain_highpass_enabled = s.sidechain_highpass_enabled;
+    cs.compressor_auto_makeup_enabled = 1;
+    plan_compressor(cs, fs, p);
+    out->structure = ST_COMPRESSOR;
+    if (p.flags & LF_C_AUTO_MAKEUP) out->structure |= ST_AUTO_MAKEUP;  // no meter for this rate: the switch stays off
+    p.c_ev_vad_reliability = s.vad_reliability;
+    p.c_ev_noise_floor_db = noise_floor_db;
+    p.c_ev_live_reliability = noise_reliability;
+    p.c_ev_cfg_reliability = noise_reliability;  // set_noise_reference_reliability (python_api.rs:172)
+    if (has_vad) p.flags |= LF_C_EVIDENCE;
+    p.tp_ceil = 1.0f;
+    p.l_ceil = 1.0;
+    p.effective_ceiling_db = 0.0f;
     return AFSIM_OK;
 }
 

@@ -45,6 +45,11 @@ int validate_typed_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate
 int validate_legacy_response_bands(const AfBand bands[AFSIM_NUM_BANDS], double sample_rate, std::string* error);
 int validate_response_frequencies(const double* freqs, size_t n, double sample_rate, std::string* error);
 RateConstants rate_constants(double sample_rate);
+// Loudness meter of the compressor's auto makeup for this rate, block length and render length.
+MakeupConst makeup_constants(double sample_rate, int block_samples, int n_samples);
+// simulate_auto_makeup_control (python_api.rs:118-276).
+int plan_makeup_control(const AfAutoMakeupSettings& settings, double sample_rate, double noise_floor_db,
+                        double noise_reliability, bool has_vad, CandidatePlan* out, std::string* error);
 
 // EQ sections only (afsim_eq_response): coefficient table [40][5] in band*4+section order and the
 // number of sections per band.

@@ -363,7 +363,29 @@ AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
     st.init(stream_params(a, s));
-    st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);
+    if (a.structure & ST_AUTO_MAKEUP)
+        st.map_m6_gain(col_at(a.w[1], a, ck, s, t0), (size_t)a.stride, valid);
+    else
+        st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);
+}
+// R7 (auto-makeup batches): apply gain reduction x makeup, run the loudness meter, step the makeup at block ends
+AF_HD void body_comp_r7(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    MakeupR st;
+    st.init(stream_params(a, s));
+    if (ck.n0 != 0) {
+        StateIO<false> io{a.st_mk + s, stride};
+        st.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const int64_t voff = a.mk_vad_off ? a.mk_vad_off[s] : -1;
+    st.run(col_at(a.buf_a, a, ck, s), col_at(a.w[1], a, ck, s), stride, ck.n0, ck.len, clk, *a.mk_const, a.mk_ring + s,
+           a.mk_rows ? a.mk_rows + s : nullptr, a.n_rows, (a.mk_vad && voff >= 0) ? a.mk_vad + voff : nullptr, stg);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{a.st_mk + s, stride};
+        st.sync(io);
+    }
 }
 
 // ---- de-esser: R_a -> M_b -> R_c (afsim_deesser.h), used by every batch that has the stage ---------------------------

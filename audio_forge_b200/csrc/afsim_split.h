@@ -370,6 +370,264 @@ struct CompSplit : CompressorStage {
         }
         store_tile(x, stride, valid, y);
     }
+    // M6 of an auto-makeup batch: only the gain-reduction factor; the makeup stage R7 applies it.  w1 gr -> w1 = 10^(-gr/20)
+    AF_HD void map_m6_gain(double* w1, size_t stride, int valid) const {
+        double grv[kCompMapGroup], g[kCompMapGroup];
+        load_tile((const double*)w1, stride, valid, grv);
+#pragma unroll
+        for (int u = 0; u < kCompMapGroup; ++u) g[u] = db_to_lin(-grv[u]);
+        store_tile(w1, stride, valid, g);
+    }
+};
+
+// ---- R7: auto makeup (dsp/compressor.rs:598-653,700-722) over the momentary loudness meter (dsp/loudness.rs) --------
+// The makeup gain is constant inside a block and steps at block ends, where the compressor (:700-722)
+//   1. estimates speech activity from the block's PRE-gain RMS (and the control simulator's VAD / noise evidence),
+//   2. feeds the POST-gain block to the loudness meter if the block was active,
+//   3. moves the smoothed makeup towards target_lufs - momentary loudness (update_auto_makeup_gain).
+// One thread walks its stream: out = (f32)(x * (g * makeup_lin)), the K-weighting section runs on `out`
+// speculatively (whether the block is fed is only known at its end; an unfed block rolls the four filter states
+// back), and the 400 ms window is a ring of per-slot partial sums (MakeupConst).  Chunks of an auto-makeup batch are
+// whole blocks, so a block never straddles two launches.
+AF_HD double af_pow(double a, double b) { return pow(a, b); }
+
+struct MakeupR {
+    // state
+    double mk, score, rel, lufs;     // smoothed makeup (dB), speech activity score, activity reliability, current_lufs
+    double c1, c2, c3, c4;           // meter filter state after the last block that was fed
+    uint32_t pos;                    // ring slot where the next fed block starts
+    // constants
+    double makeup_db, target_lufs, k_smooth, k_relax, k_activity;
+    double ev_vad_rel, ev_floor, ev_live_rel, ev_cfg_rel;
+    bool evidence;
+
+    AF_HD void init(const CandidateParams& p) {
+        makeup_db = p.c_makeup_db;
+        target_lufs = p.c_target_lufs;
+        k_smooth = p.c_mk_smooth;
+        k_relax = p.c_mk_relax;
+        k_activity = p.c_mk_activity;
+        ev_vad_rel = p.c_ev_vad_reliability;
+        ev_floor = p.c_ev_noise_floor_db;
+        ev_live_rel = p.c_ev_live_reliability;
+        ev_cfg_rel = p.c_ev_cfg_reliability;
+        evidence = (p.flags & LF_C_EVIDENCE) != 0;
+        mk = p.c_makeup_db;
+        score = 0.0;
+        rel = 0.0;
+        lufs = -100.0;
+        c1 = c2 = c3 = c4 = 0.0;
+        pos = 0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+        io.f64(mk);
+        io.f64(score);
+        io.f64(rel);
+        io.f64(lufs);
+        io.f64(c1);
+        io.f64(c2);
+        io.f64(c3);
+        io.f64(c4);
+        io.u32(pos);
+    }
+
+    static AF_HD double activity_from_rms_db(double rms_db) {  // :507-514
+        if (!(rms_db >= -55.0 && rms_db <= -6.0)) return 0.0;
+        const double onset = clampd((rms_db - -55.0) / 12.0, 0.0, 1.0);
+        const double overload = clampd((-6.0 - rms_db) / 6.0, 0.0, 1.0);
+        return fmin(onset, overload);
+    }
+    static AF_HD bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
+    static AF_HD double unit_or_zero(double v, bool* ok) {  // finite_unit, :516-518
+        *ok = finite_d(v);
+        return *ok ? clampd(v, 0.0, 1.0) : 0.0;
+    }
+    static AF_HD double smoothstep(double e0, double e1, double v) {  // :520-526
+        if (!finite_d(v) || !finite_d(e0) || !finite_d(e1) || e1 <= e0) return 0.0;
+        const double t = clampd((v - e0) / (e1 - e0), 0.0, 1.0);
+        return t * t * (3.0 - 2.0 * t);
+    }
+    // estimate_auto_makeup_activity (:528-581); have_vad: this block has a VAD probability
+    AF_HD void estimate(double rms_db, bool have_vad, double vad_p_in, double* activity, double* reliability) const {
+        const double absolute = activity_from_rms_db(rms_db);
+        if (!have_vad) {
+            *activity = absolute;
+            *reliability = 1.0;
+            return;
+        }
+        bool ok;
+        double vad_rel = unit_or_zero(ev_vad_rel, &ok);
+        double vad_p = unit_or_zero(vad_p_in, &ok);
+        if (!ok) vad_rel = 0.0;
+        const double cfg_rel = unit_or_zero(ev_cfg_rel, &ok);
+        const double live_rel = unit_or_zero(ev_live_rel, &ok);
+        double noise_rel = cfg_rel > 0.0 ? fmin(live_rel, cfg_rel) : live_rel;
+        double relative = 0.0;
+        if (finite_d(ev_floor) && ev_floor >= -120.0 && ev_floor <= 0.0)
+            relative = smoothstep(ev_floor + 3.0, ev_floor + 15.0, rms_db);
+        else
+            noise_rel = 0.0;
+        const double fallback = noise_rel * relative + (1.0 - noise_rel) * absolute;
+        *activity = clampd(vad_rel * vad_p + (1.0 - vad_rel) * fallback, 0.0, 1.0);
+        *reliability = clampd(fmax(vad_rel, 0.75 * noise_rel), 0.0, 1.0);
+    }
+    // update_auto_makeup_gain (:598-653) with the switch on and a meter present; limiter feedback is 0 offline
+    AF_HD void update(double activity, double reliability, int elapsed) {
+        const double n = (double)(elapsed > 1 ? elapsed : 1);
+        const double makeup_coeff = af_pow(k_smooth, n);
+        const double relax_coeff = af_pow(k_relax, n);
+        const double activity_coeff = af_pow(k_activity, n);
+        score = activity_coeff * score + (1.0 - activity_coeff) * clampd(activity, 0.0, 1.0);
+        rel = clampd(reliability, 0.0, 1.0);
+        if (score < 0.20) {
+            mk = relax_coeff * mk + (1.0 - relax_coeff) * makeup_db;
+            return;
+        }
+        if (rel < 0.35) {
+            const double cap = makeup_db + 3.0 * (rel / 0.35);
+            if (mk > cap) mk = makeup_coeff * mk + (1.0 - makeup_coeff) * cap;
+            return;
+        }
+        const double required = target_lufs - lufs;
+        const double reliability_cap = clampd(12.0 * rel, 3.0, 12.0);
+        const double headroom_cap = clampd(12.0 - 0.0 * 2.0, 0.0, reliability_cap);
+        const double clamped = clampd(required, 0.0, headroom_cap);
+        const double diff = clamped - mk;
+        if (fabs(diff) > 0.1)
+            mk = makeup_coeff * mk + (1.0 - makeup_coeff) * clamped;
+        else
+            mk = clamped;
+    }
+
+    // x: compressor input / output column at chunk start (in place); g: 10^(-gr/20) column; ring: this stream's column
+    // of [2 * n_slots + 2 * kMaxMakeupSub][stride] (full sums, tail sums, pending full, pending tail); rows: this
+    // stream's column of [3][n_rows][stride] or nullptr; vad: this stream's probabilities or nullptr
+    AF_HD void run(float* x, const double* g, size_t stride, int n0, int len, BlockClock clk, const MakeupConst& mc, double* ring,
+                   float* rows, int n_rows, const double* vad, Staging stg) {
+        constexpr int U = kGroup;
+        const StageRing<float> sx = stg.ring<float>();
+        const StageRing<double> sg = stg.ring<double>();
+        const double b0 = mc.b[0], b1 = mc.b[1], b2 = mc.b[2], b3 = mc.b[3], b4 = mc.b[4];
+        const double a1 = mc.a[1], a2 = mc.a[2], a3 = mc.a[3], a4 = mc.a[4];
+        const int slot = mc.slot, n_slots = mc.n_slots, tail_from = mc.tail_from;
+        double* ring_full = ring;
+        double* ring_tail = ring + (size_t)n_slots * stride;
+        double* pend_full = ring + (size_t)2 * n_slots * stride;
+        double* pend_tail = pend_full + (size_t)kMaxMakeupSub * stride;
+        double v1 = c1, v2 = c2, v3 = c3, v4 = c4;
+        double mk_lin = db_to_lin(mk);
+        double sq_in = 0.0, full = 0.0, tail = 0.0;
+        int off = 0, sub = 0;  // samples into the current slot, slots of the current block already closed
+        auto issue = [&](int k, auto fullt) {
+            constexpr bool FULL = decltype(fullt)::value;
+            const int t0 = k * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || t0 + u < len) {
+                    sx.fetch(k, u, x + (size_t)(t0 + u) * stride);
+                    sg.fetch(k, u, g + (size_t)(t0 + u) * stride);
+                }
+            }
+        };
+        auto body = [&](int k, auto fullt) {
+            constexpr bool FULL = decltype(fullt)::value;
+            const int t0 = k * U;
+            const int valid = FULL ? U : len - t0;
+            float xin[U], y[U];
+            double gv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                xin[u] = (FULL || u < valid) ? sx.get(k, u, x + (size_t)(t0 + u) * stride) : 0.0f;
+                gv[u] = (FULL || u < valid) ? sg.get(k, u, g + (size_t)(t0 + u) * stride) : 0.0;
+            }
+            auto walk = [&](auto may_end) {  // may_end: a slot (and with it possibly the block) can end inside this tile
+                constexpr bool CHECK = decltype(may_end)::value;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    y[u] = 0.0f;
+                    if (FULL || u < valid) {
+                        const double xv = (double)xin[u];
+                        const double gain = gv[u] * mk_lin;
+                        const float o = (float)(xv * gain);
+                        y[u] = o;
+                        sq_in += xv * xv;
+                        // K-weighting, direct form II (add_frames_f32)
+                        const double v0 = (double)o - a1 * v1 - a2 * v2 - a3 * v3 - a4 * v4;
+                        const double w = b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3 + b4 * v4;
+                        v4 = v3;
+                        v3 = v2;
+                        v2 = v1;
+                        v1 = fabs(v0) < 2.2250738585072014e-308 ? 0.0 : v0;  // denormal flush of the filter state
+                        const double w2 = w * w;
+                        full += w2;
+                        tail += off >= tail_from ? w2 : 0.0;
+                        off += 1;
+                        if (CHECK) {
+                            const int n = n0 + t0 + u;
+                            if (off == slot) {
+                                pend_full[(size_t)sub * stride] = full;
+                                pend_tail[(size_t)sub * stride] = tail;
+                                sub += 1;
+                                full = tail = 0.0;
+                                off = 0;
+                            }
+                            if (clk.at_end(n)) {
+                                const int blen = clk.block_len(n);
+                                const double rms_db = lin_to_db(sqrt(sq_in / (double)blen), 1e-10);  // block_rms_db :583-596
+                                double activity, reliability;
+                                const bool have_vad = evidence && vad != nullptr;
+                                estimate(rms_db, have_vad, have_vad ? vad[clk.blk] : 0.0, &activity, &reliability);
+                                if (activity > 0.20 && reliability >= 0.35) {  // :713-718: the meter hears the block
+                                    c1 = v1;
+                                    c2 = v2;
+                                    c3 = v3;
+                                    c4 = v4;
+                                    for (int i = 0; i < sub; ++i) {
+                                        const size_t r = (size_t)((pos + i) % n_slots) * stride;
+                                        ring_full[r] = pend_full[(size_t)i * stride];
+                                        ring_tail[r] = pend_tail[(size_t)i * stride];
+                                    }
+                                    const int partial = off > 0 ? (int)((pos + sub) % n_slots) : -1;  // final short block only
+                                    double sum = 0.0;
+                                    for (int i = 0; i < n_slots; ++i)
+                                        sum += i == partial ? full + ring_tail[(size_t)i * stride] : ring_full[(size_t)i * stride];
+                                    pos = (pos + sub) % n_slots;
+                                    const double energy = sum / (double)mc.window;
+                                    const double l = energy <= 0.0 ? -(double)INFINITY : 10.0 * log10(energy) - 0.691;
+                                    lufs = (double)(float)l;  // dsp/loudness.rs:123-125 keeps an f32
+                                } else {
+                                    v1 = c1;
+                                    v2 = c2;
+                                    v3 = c3;
+                                    v4 = c4;
+                                }
+                                update(activity, reliability, blen);
+                                mk_lin = db_to_lin(mk);
+                                if (rows) {
+                                    rows[((size_t)0 * n_rows + clk.blk) * stride] = (float)mk;
+                                    rows[((size_t)1 * n_rows + clk.blk) * stride] = (float)score;
+                                    rows[((size_t)2 * n_rows + clk.blk) * stride] = (float)rel;
+                                }
+                                sq_in = 0.0;
+                                full = tail = 0.0;
+                                off = 0;
+                                sub = 0;
+                                clk.advance();
+                            }
+                        }
+                    }
+                }
+            };
+            if (FULL && slot - off > U && clk.ends_after(n0 + t0, U))
+                walk(TileRagged());  // no slot end, no block end in this tile: no per-sample checks
+            else
+                walk(TileFull());
+            store_tile(x + (size_t)t0 * stride, stride, valid, y);
+        };
+        pipelined_tiles(len, issue, body);
+        // chunks are whole blocks: the filter state that carries over is the committed one (already in c1..c4)
+    }
 };
 
 // ---- lookahead limiter (dsp/limiter.rs:246-284) -----------------------------------------------------------------

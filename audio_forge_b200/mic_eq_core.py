@@ -164,6 +164,61 @@ def simulate_auto_eq_chain_batch(passages, sample_rate: float, candidates, *, pa
     return [abi.metrics_to_dict(metrics[i]) for i in range(n)]
 
 
+_MAKEUP_F64 = ("threshold_db", "ratio", "attack_ms", "release_ms", "makeup_gain_db", "target_lufs", "vad_reliability")
+_MAKEUP_BOOL = ("adaptive_release", "sidechain_highpass_enabled")
+
+
+def simulate_auto_makeup_control(audio, sample_rate: float, vad_probabilities, noise_floor_db: float,
+                                 noise_reliability: float, settings: Mapping[str, object] | None = None,
+                                 *, device: int = 0) -> dict[str, Any]:
+    """python_api.rs:118-276: the compressor's auto-makeup controller over 480-sample control blocks.
+
+    The runtime percentiles of the reference (wall time of each CPU block) have no per-block counterpart in one
+    GPU pass; the three keys report the call's wall time divided over the blocks."""
+    import time
+
+    sample_rate = float(sample_rate)
+    if not np.isfinite(sample_rate) or sample_rate <= 0.0:
+        raise ValueError("sample_rate must be positive and finite")
+    noise_floor_db, noise_reliability = float(noise_floor_db), float(noise_reliability)
+    if not np.isfinite(noise_floor_db) or not np.isfinite(noise_reliability) or not 0.0 <= noise_reliability <= 1.0:
+        raise ValueError("noise evidence must be finite and reliability must be between 0 and 1")
+    vad = [float(v) for v in vad_probabilities]
+    if any((not np.isfinite(v)) or not 0.0 <= v <= 1.0 for v in vad):
+        raise ValueError("VAD probabilities must be finite and between 0 and 1")
+    arr = _audio_1d(audio)
+    overrides: dict[str, object] = {}
+    return_audio = False
+    if settings is not None:
+        for key, value in settings.items():
+            if key in _MAKEUP_F64:
+                overrides[key] = _extract_f64(key, value)
+            elif key in _MAKEUP_BOOL:
+                overrides[key] = _extract_bool(key, value)
+            elif key == "return_output_audio":
+                return_audio = _extract_bool(key, value)
+    st = abi.make_makeup_settings(**overrides)
+    started = time.perf_counter()
+    traces, out = simulator(device).auto_makeup_control(arr, sample_rate, vad, noise_floor_db, noise_reliability, st,
+                                                        return_audio=return_audio)
+    elapsed_ms = (time.perf_counter() - started) * 1000.0
+    blocks = traces.shape[1]
+    per_block_ms = elapsed_ms / blocks if blocks else 0.0
+    result: dict[str, Any] = {
+        "control_block_size": abi.MAKEUP_CONTROL_BLOCK,
+        "control_cadence_hz": sample_rate / abi.MAKEUP_CONTROL_BLOCK,
+        "processed_samples": int(arr.size),
+    }
+    for name, row in zip(abi.MAKEUP_TRACES, traces):
+        result[name] = [float(v) for v in row]
+    result["p95_block_runtime_ms"] = per_block_ms
+    result["p99_block_runtime_ms"] = per_block_ms
+    result["max_block_runtime_ms"] = per_block_ms
+    if return_audio:
+        result["output_audio"] = out.tolist()
+    return result
+
+
 def simulate_eq_v2(audio, sample_rate: float, bands, return_output_audio: bool = False, *, device: int = 0):
     """lib.rs:214-288."""
     sample_rate = float(sample_rate)

@@ -29,10 +29,11 @@ EXPORTS = (
     "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
     "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
     "afsim_sweep_profile_stages", "afsim_measure_issue_peak",
+    "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
                "comp_r1", "comp_m2", "comp_r3", "comp_m4", "comp_r5", "comp_m6", "lim_m", "lim_r", "tp_fir_in", "tp_r",
-               "tp_fir_out", "de_ra", "de_mb", "de_rc")
+               "tp_fir_out", "de_ra", "de_mb", "de_rc", "comp_r7")
 
 
 class AfsimError(RuntimeError):
@@ -101,6 +102,13 @@ def lib() -> C.CDLL:
     L.afsim_sweep_profile_stages.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
     L.afsim_measure_issue_peak.argtypes = [vp, C.c_int, f64p]
+    mk_p = C.POINTER(abi.AfAutoMakeupSettings)
+    L.afsim_auto_makeup_settings_default.argtypes = [mk_p]
+    L.afsim_auto_makeup_settings_default.restype = None
+    L.afsim_auto_makeup_control.argtypes = [vp, f32p, C.c_size_t, C.c_double, f64p, C.c_size_t, C.c_double, C.c_double,
+                                            mk_p, f32p, f32p]
+    L.afsim_auto_makeup_sweep.argtypes = [vp, C.POINTER(f32p), szp, C.c_size_t, C.c_double, C.POINTER(f64p), f64p, f64p,
+                                          mk_p, C.POINTER(f32p), C.POINTER(f32p)]
     _lib = L
     return L
 
@@ -228,6 +236,47 @@ class Simulator:
                                             n_sets, 1 if typed else 0, float(sample_rate),
                                             out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def auto_makeup_control(self, audio, sample_rate, vad_probabilities, noise_floor_db, noise_reliability,
+                            settings: abi.AfAutoMakeupSettings, return_audio: bool = False):
+        """simulate_auto_makeup_control -> (traces [6, ceil(n / 480)] float32 in abi.MAKEUP_TRACES order, audio | None)."""
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        vad = np.ascontiguousarray(vad_probabilities if vad_probabilities is not None else [], dtype=np.float64)
+        blocks = (audio.size + abi.MAKEUP_CONTROL_BLOCK - 1) // abi.MAKEUP_CONTROL_BLOCK
+        traces = np.zeros((len(abi.MAKEUP_TRACES), blocks), dtype=np.float32)
+        out = np.zeros_like(audio) if return_audio else None
+        self._check(lib().afsim_auto_makeup_control(
+            self._h, _f32p(audio), audio.size, float(sample_rate), vad.ctypes.data_as(C.POINTER(C.c_double)) if vad.size else None,
+            vad.size, float(noise_floor_db), float(noise_reliability), C.byref(settings), _f32p(traces),
+            _f32p(out) if out is not None else None))
+        return traces, out
+
+    def auto_makeup_sweep(self, captures, sample_rate, vads, noise_floor_db, noise_reliability, settings,
+                          return_audio: bool = False):
+        """Batched simulate_auto_makeup_control: one GPU pass over `captures`; vads[i] is None or an array."""
+        captures = [np.ascontiguousarray(c, dtype=np.float32) for c in captures]
+        n = len(captures)
+        f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+        vad_arrs = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in vads]
+        for c, v in zip(captures, vad_arrs):
+            blocks = (c.size + abi.MAKEUP_CONTROL_BLOCK - 1) // abi.MAKEUP_CONTROL_BLOCK
+            if v is not None and v.size != blocks:
+                raise ValueError(f"expected {blocks} VAD probabilities at the 10 ms control cadence, got {v.size}")
+        traces = [np.zeros((len(abi.MAKEUP_TRACES), (c.size + abi.MAKEUP_CONTROL_BLOCK - 1) // abi.MAKEUP_CONTROL_BLOCK),
+                           dtype=np.float32) for c in captures]
+        outs = [np.zeros_like(c) for c in captures] if return_audio else None
+        m = max(n, 1)
+        ptrs = (f32p * m)(*[_f32p(c) for c in captures])
+        lens = (C.c_size_t * m)(*[c.size for c in captures])
+        vptrs = (f64p * m)(*[v.ctypes.data_as(f64p) if v is not None and v.size else None for v in vad_arrs])
+        floors = np.ascontiguousarray(noise_floor_db, dtype=np.float64)
+        rels = np.ascontiguousarray(noise_reliability, dtype=np.float64)
+        sets = (abi.AfAutoMakeupSettings * m)(*settings)
+        tptrs = (f32p * m)(*[_f32p(t) for t in traces])
+        optrs = (f32p * m)(*[_f32p(o) for o in outs]) if outs is not None else None
+        self._check(lib().afsim_auto_makeup_sweep(self._h, ptrs, lens, n, float(sample_rate), vptrs,
+                                                  floors.ctypes.data_as(f64p), rels.ctypes.data_as(f64p), sets, tptrs, optrs))
+        return traces, outs
 
     # ---- sweeps ----
     @staticmethod

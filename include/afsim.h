@@ -166,6 +166,25 @@ typedef struct AfEqRenderStats {
     uint32_t reserved;
 } AfEqRenderStats;
 
+/* settings dict of simulate_auto_makeup_control (python_api.rs:168-192); afsim_auto_makeup_settings_default()
+ * fills the reference defaults (-24 dB, 3:1, 10 ms, 180 ms, 0 dB, -18 LUFS, adaptive release on, sidechain
+ * high-pass on, vad_reliability 1). */
+typedef struct AfAutoMakeupSettings {
+    double threshold_db;
+    double ratio;
+    double attack_ms;
+    double release_ms;
+    double makeup_gain_db;
+    double target_lufs;
+    double vad_reliability;
+    uint8_t adaptive_release;
+    uint8_t sidechain_highpass_enabled;
+    uint8_t reserved[6];
+} AfAutoMakeupSettings;
+
+#define AFSIM_MAKEUP_CONTROL_BLOCK 480 /* CONTROL_BLOCK_SIZE, python_api.rs:135 */
+#define AFSIM_MAKEUP_TRACES 6          /* makeup_gain_db, activity, reliability, gain_reduction_db, input_rms_db, output_rms_db */
+
 typedef struct AfsimHandle AfsimHandle;   /* opaque */
 typedef struct AfsimSweep AfsimSweep;     /* opaque: a sweep resident in HBM */
 
@@ -208,6 +227,24 @@ int afsim_eq_render(AfsimHandle* handle, const float* audio, size_t n, double sa
 int afsim_eq_response(AfsimHandle* handle, const double* frequencies_hz, size_t n_freqs,
                       const AfBand* bands /* n_sets * 10 */, size_t n_sets, int typed,
                       double sample_rate, double* out_db);
+
+/* Replaces simulate_auto_makeup_control (python_api.rs:118-276): streams one capture through the compressor's
+ * auto-makeup controller in 480-sample control blocks.  vad_probabilities: NULL / n_vad = 0 (no evidence), or
+ * exactly ceil(n / 480) values in [0, 1].  out_traces: AFSIM_MAKEUP_TRACES arrays of ceil(n / 480) floats,
+ * trace-major, in the order named above.  out_audio: NULL or n floats.  The loudness meter restates the
+ * third-party `ebur128` crate (momentary mode); see DESIGN.md for its parity status. */
+void afsim_auto_makeup_settings_default(AfAutoMakeupSettings* out);
+int afsim_auto_makeup_control(AfsimHandle* handle, const float* audio, size_t n, double sample_rate,
+                              const double* vad_probabilities, size_t n_vad, double noise_floor_db,
+                              double noise_reliability, const AfAutoMakeupSettings* settings, float* out_traces,
+                              float* out_audio);
+/* The same for `n_streams` captures at once (one GPU pass): capture i has len[i] samples, settings[i], and either
+ * no evidence (vad[i] == NULL) or ceil(len[i] / 480) probabilities.  out_traces[i]: 6 x ceil(len[i] / 480)
+ * floats; out_audio: NULL or n_streams pointers (each NULL or len[i] floats). */
+int afsim_auto_makeup_sweep(AfsimHandle* handle, const float* const* audio, const size_t* len, size_t n_streams,
+                            double sample_rate, const double* const* vad, const double* noise_floor_db,
+                            const double* noise_reliability, const AfAutoMakeupSettings* settings,
+                            float* const* out_traces, float* const* out_audio);
 
 /* ---- batched sweeps ------------------------------------------------------ */
 

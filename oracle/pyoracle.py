@@ -189,3 +189,20 @@ def eq_response(frequencies_hz, bands, sample_rate: float, typed: bool) -> np.nd
     rc = lib().orc_eq_response(dptr(freqs), freqs.size, bands, 1 if typed else 0, float(sample_rate), dptr(out))
     _check(rc)
     return out
+
+
+def auto_makeup_control(audio, sample_rate: float, vad, noise_floor_db: float, noise_reliability: float,
+                        settings: abi.AfAutoMakeupSettings, *, return_audio: bool = False):
+    """simulate_auto_makeup_control (python_api.rs:118-276) -> (traces [6, blocks] float32, audio | None)."""
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    vad = np.ascontiguousarray(vad if vad is not None else [], dtype=np.float64)
+    blocks = (audio.size + 479) // 480
+    traces = np.zeros((6, blocks), dtype=np.float32)
+    out = np.zeros_like(audio) if return_audio else None
+    rc = lib().orc_auto_makeup_control(fptr(audio), audio.size, float(sample_rate), dptr(vad) if vad.size else None, vad.size,
+                                       float(noise_floor_db), float(noise_reliability), settings.threshold_db, settings.ratio,
+                                       settings.attack_ms, settings.release_ms, settings.makeup_gain_db, settings.target_lufs,
+                                       int(settings.adaptive_release), int(settings.sidechain_highpass_enabled),
+                                       settings.vad_reliability, fptr(traces), fptr(out) if out is not None else None)
+    _check(rc)
+    return traces, out

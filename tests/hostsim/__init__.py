@@ -30,6 +30,9 @@ def lib() -> C.CDLL:
         L.hostsim_chain_sweep.argtypes = [C.POINTER(f32p), C.POINTER(C.c_size_t), C.c_size_t, C.c_double,
                                           C.POINTER(abi.AfCandidate), C.c_size_t, u32p, u32p, C.c_size_t, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.POINTER(abi.AfChainMetrics), f32p, f32p]
+        L.hostsim_makeup_control.argtypes = [f32p, C.c_size_t, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_double,
+                                             C.c_double, C.POINTER(abi.AfAutoMakeupSettings), C.c_int, C.c_int, C.c_int,
+                                             f32p, f32p]
         _lib = L
     return _lib
 
@@ -62,3 +65,22 @@ def chain_sweep(passages, sample_rate, candidates, pair_passage, pair_candidate,
     if rc != abi.AFSIM_OK:
         raise HostsimError(lib().hostsim_last_error().decode())
     return out, audio, rows
+
+
+def makeup_control(audio, sample_rate, vad, noise_floor_db, noise_reliability, settings, *, chunk=960, slots=2,
+                   direct=False, want_audio=False):
+    """simulate_auto_makeup_control through the product's stage bodies -> (traces [6, blocks], audio | None)."""
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    vad = np.ascontiguousarray(vad if vad is not None else [], dtype=np.float64)
+    blocks = (audio.size + 479) // 480
+    traces = np.zeros((6, blocks), dtype=np.float32)
+    out = np.zeros_like(audio) if want_audio else None
+    f32p = C.POINTER(C.c_float)
+    rc = lib().hostsim_makeup_control(audio.ctypes.data_as(f32p), audio.size, float(sample_rate),
+                                      vad.ctypes.data_as(C.POINTER(C.c_double)) if vad.size else None, vad.size,
+                                      float(noise_floor_db), float(noise_reliability), C.byref(settings), int(chunk),
+                                      int(slots), 1 if direct else 0, traces.ctypes.data_as(f32p),
+                                      out.ctypes.data_as(f32p) if out is not None else None)
+    if rc != abi.AFSIM_OK:
+        raise HostsimError(lib().hostsim_last_error().decode())
+    return traces, out

@@ -25,6 +25,17 @@ const float kFir[4][32] = {
 thread_local std::string g_error;
 }  // namespace
 
+struct HostOptions {
+    int block_samples = 0;               // 0: the rate's analysis block
+    const double* const* vad = nullptr;  // per pair
+    float* mk_rows_out = nullptr;        // [3][n_rows][n_pairs]
+};
+
+int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* passages, const size_t* passage_len,
+                size_t n_passages, double fs, const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs,
+                int chunk, int slots, int eq_k, int split, AfChainMetrics* out_metrics, float* out_audio, float* out_rows,
+                const HostOptions& opt);
+
 extern "C" {
 
 const char* hostsim_last_error() { return g_error.c_str(); }
@@ -41,6 +52,52 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         const int rc = plan_candidate(candidates[c].bands, candidates[c].settings, fs, &plans[c], &g_error);
         if (rc != AFSIM_OK) return rc;
     }
+    return run_hostsim(plans, passages, passage_len, n_passages, fs, pair_passage, pair_candidate, n_pairs, chunk, slots, eq_k,
+                       split, out_metrics, out_audio, out_rows, HostOptions());
+}
+
+// simulate_auto_makeup_control through the stage bodies: one capture, 480-sample control blocks.
+// traces: [6][block_count] as afsim_auto_makeup_control.
+int hostsim_makeup_control(const float* audio, size_t n, double fs, const double* vad, size_t n_vad, double noise_floor_db,
+                           double noise_reliability, const AfAutoMakeupSettings* settings, int chunk, int slots, int direct,
+                           float* traces, float* out_audio) {
+    g_error.clear();
+    std::vector<CandidatePlan> plans(1);
+    const int rc = plan_makeup_control(*settings, fs, noise_floor_db, noise_reliability, n_vad != 0, &plans[0], &g_error);
+    if (rc != AFSIM_OK) return rc;
+    const size_t n_rows = (n + 479) / 480;
+    if (n_rows == 0) return AFSIM_OK;
+    const float* passages[1] = {audio};
+    const size_t lens[1] = {n};
+    const uint32_t zero[1] = {0};
+    const double* vads[1] = {n_vad ? vad : nullptr};
+    std::vector<float> rows(4 * n_rows), mk_rows(3 * n_rows);
+    AfChainMetrics metrics;
+    HostOptions opt;
+    opt.block_samples = 480;
+    opt.vad = vads;
+    opt.mk_rows_out = mk_rows.data();
+    const int rc2 = run_hostsim(plans, passages, lens, 1, fs, zero, zero, 1, chunk, slots, 5, direct ? 8 : 0, &metrics, out_audio,
+                                rows.data(), opt);
+    if (rc2 != AFSIM_OK) return rc2;
+    for (size_t r = 0; r < n_rows; ++r) {
+        traces[0 * n_rows + r] = mk_rows[0 * n_rows + r];
+        traces[1 * n_rows + r] = mk_rows[1 * n_rows + r];
+        traces[2 * n_rows + r] = mk_rows[2 * n_rows + r];
+        traces[3 * n_rows + r] = rows[2 * n_rows + r];
+        traces[4 * n_rows + r] = rows[0 * n_rows + r];
+        traces[5 * n_rows + r] = rows[1 * n_rows + r];
+    }
+    return AFSIM_OK;
+}
+
+}  // extern "C"
+
+int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* passages, const size_t* passage_len,
+                size_t n_passages, double fs, const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs,
+                int chunk, int slots, int eq_k, int split, AfChainMetrics* out_metrics, float* out_audio, float* out_rows,
+                const HostOptions& opt) {
+    const size_t n_candidates = plans.size();
     if (n_pairs == 0) return AFSIM_OK;
     const RateConstants rate = rate_constants(fs);
     const CandidatePlan& first = plans[pair_candidate[0]];
@@ -71,15 +128,28 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     a.n_streams = S;
     a.stride = S_pad;
     a.n_samples = T;
-    a.block_samples = rate.block_samples;
+    a.block_samples = opt.block_samples > 0 ? opt.block_samples : rate.block_samples;
     a.fade_samples = rate.fade_samples;
-    a.n_rows = (T + rate.block_samples - 1) / rate.block_samples;
+    a.n_rows = (T + a.block_samples - 1) / a.block_samples;
     a.n_pad = 2;
     while (a.n_pad < a.n_rows) a.n_pad <<= 1;
     chunk = std::max(chunk, std::max(rate.fade_samples, a.lookahead + 1));
     chunk = (chunk + 7) / 8 * 8;
     if (a.input_stage == AF_INPUT_CLEANUP_GENTLE || a.input_stage == AF_INPUT_CLEANUP_STRONG)
         chunk = (chunk + kInputBlock - 1) / kInputBlock * kInputBlock;
+    const bool auto_makeup = (a.structure & ST_AUTO_MAKEUP) != 0;
+    MakeupConst mc{};
+    if (auto_makeup) {  // whole blocks per chunk, as the product's build_sweep
+        int unit = a.block_samples, eight = 8;
+        while (eight) {
+            const int t = unit % eight;
+            unit = eight;
+            eight = t;
+        }
+        unit = a.block_samples / unit * 8;
+        chunk = (chunk + unit - 1) / unit * unit;
+        mc = makeup_constants(fs, a.block_samples, T);
+    }
     slots = std::max(slots, 2);
     a.ring_rows = slots * chunk;
 
@@ -110,6 +180,26 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
     a.stage_inputs = 1;
     a.buf_c = buf_c.data();
     a.buf_p = buf_p.data();
+    std::vector<double> st_mk(kStateMakeup * sp), mk_ring(static_cast<size_t>(2 * std::max(mc.n_slots, 1) + 2 * kMaxMakeupSub) * sp, 0.0);
+    std::vector<float> mk_rows(static_cast<size_t>(3) * std::max(a.n_rows, 1) * sp, 0.0f);
+    std::vector<double> vad_pool;
+    std::vector<int64_t> vad_off(S_pad, -1);
+    if (auto_makeup) {
+        a.st_mk = st_mk.data();
+        a.mk_ring = mk_ring.data();
+        a.mk_rows = mk_rows.data();
+        a.mk_const = &mc;
+        if (opt.vad) {
+            for (int s = 0; s < S; ++s)
+                if (opt.vad[s]) {
+                    vad_off[s] = static_cast<int64_t>(vad_pool.size());
+                    vad_pool.insert(vad_pool.end(), opt.vad[s], opt.vad[s] + a.n_rows);
+                }
+            vad_pool.push_back(0.0);
+            a.mk_vad = vad_pool.data();
+            a.mk_vad_off = vad_off.data();
+        }
+    }
     std::vector<StreamAccum> accum(sp);
     std::memset(accum.data(), 0, sp * sizeof(StreamAccum));
     std::vector<AfChainMetrics> metrics(n_pairs);
@@ -177,7 +267,7 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
         }
         const int n_groups = (ck.len + kGroup - 1) / kGroup + 1;  // one empty group past the end on purpose
         if (a.structure & ST_COMPRESSOR) {
-            if (split & 1) {
+            if ((split & 1) || auto_makeup) {
                 for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s, stg);
                 const int n_cgroups = (ck.len + kCompMapGroup - 1) / kCompMapGroup + 1;
                 for (int g = n_cgroups - 1; g >= 0; --g)  // any order: the maps are independent
@@ -188,6 +278,10 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
                 for (int s = 0; s < S; ++s) body_comp_r5(a, ck, s, stg);
                 for (int g = n_cgroups - 1; g >= 0; --g)
                     for (int s = 0; s < S; ++s) body_comp_m6(a, ck, s, g);
+                if (auto_makeup) {
+                    const Staging st7{(split & 8) ? nullptr : staging_bytes.data(), 1, 0, 0};
+                    for (int s = 0; s < S; ++s) body_comp_r7(a, ck, s, st7);
+                }
             } else {
                 for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
             }
@@ -222,8 +316,16 @@ int hostsim_chain_sweep(const float* const* passages, const size_t* passage_len,
             for (int r = 0; r < a.n_rows; ++r)
                 for (int s = 0; s < S; ++s)
                     out_rows[(static_cast<size_t>(k) * a.n_rows + r) * S + s] = rows[(static_cast<size_t>(k) * a.n_rows + r) * sp + s];
+    if (opt.mk_rows_out)
+        for (int k = 0; k < 3; ++k)
+            for (int r = 0; r < a.n_rows; ++r)
+                for (int s = 0; s < S; ++s)
+                    opt.mk_rows_out[(static_cast<size_t>(k) * a.n_rows + r) * S + s] =
+                        mk_rows[(static_cast<size_t>(k) * a.n_rows + r) * sp + s];
     return AFSIM_OK;
 }
+
+extern "C" {
 
 // Planner outputs, for coefficient-level tests against the oracle.
 int hostsim_plan(const AfBand* bands, const AfChainSettings* settings, double fs, CandidateParams* out, uint32_t* structure,
