@@ -516,7 +516,12 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
 // One batch: the chunk x stage wavefront.  Stage i runs on its own CUDA stream (so its chunks stay
 // ordered, which carries the parked state); stage i of chunk c waits for stage i-1 of chunk c; the
 // first stage of chunk c waits for the last stage of chunk c - slots + 1 before it reuses a ring slot.
-int run_batch(AfsimHandle* h, Batch& b) {
+struct WavefrontTrace {  // timing events around the launches of chunks [c0, c0 + n) in the live wavefront
+    int c0 = 0, n = 0;
+    std::vector<cudaEvent_t> ev;  // [chunk][stage][2]
+};
+
+int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
     const BatchArgs& a = b.args;
     const int n_stages = static_cast<int>(b.stages.size());
     const int T = a.n_samples;
@@ -549,7 +554,11 @@ int run_batch(AfsimHandle* h, Batch& b) {
                     const int old_slot = (c - b.slots + 1) % b.slots;
                     AF_CUDA(h, cudaStreamWaitEvent(st, b.events[static_cast<size_t>(n_stages - 1) * b.slots + old_slot], 0));
                 }
+                const bool traced = trace && c >= trace->c0 && c < trace->c0 + trace->n;
+                const size_t te = traced ? (static_cast<size_t>(c - trace->c0) * n_stages + i) * 2 : 0;
+                if (traced) AF_CUDA(h, cudaEventRecord(trace->ev[te], st));  // after the waits: the launch is eligible
                 AF_CUDA(h, launch_stage(b, b.stages[i], ck, st));
+                if (traced) AF_CUDA(h, cudaEventRecord(trace->ev[te + 1], st));
                 AF_CUDA(h, cudaEventRecord(b.events[static_cast<size_t>(i) * b.slots + slot], st));
             }
         }
@@ -823,6 +832,66 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
     out_launches[n_stages] = 1;
     *out_n = n_stages + 1;
     destroy();
+    return AFSIM_OK;
+}
+
+int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_chunk, int n_chunks, int capacity, int* out_kind,
+                                  float* out_busy_ms, float* out_period_ms, int* out_n) {
+    if (!h || !sweep || !out_kind || !out_busy_ms || !out_period_ms || !out_n) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    *out_n = 0;
+    if (sweep->batches.empty()) return AFSIM_OK;
+    AF_CUDA(h, cudaSetDevice(h->device));
+    Batch& b = *sweep->batches[0];
+    const int n_stages = static_cast<int>(b.stages.size());
+    if (capacity < n_stages) return set_error(h, AFSIM_INVALID_ARGUMENT, "capacity too small");
+    const int total_chunks = b.args.n_samples > 0 ? (b.args.n_samples + b.chunk - 1) / b.chunk : 0;
+    WavefrontTrace tr;
+    tr.c0 = std::max(0, std::min(first_chunk, total_chunks - 1));
+    tr.n = std::max(0, std::min(n_chunks, total_chunks - tr.c0));
+    if (tr.n < 2) return set_error(h, AFSIM_INVALID_ARGUMENT, "need at least two chunks to trace");
+    tr.ev.resize(static_cast<size_t>(tr.n) * n_stages * 2);
+    for (cudaEvent_t& e : tr.ev) AF_CUDA(h, cudaEventCreate(&e));
+    int rc = run_batch(h, b, &tr);
+    cudaError_t err = cudaStreamSynchronize(h->stream);
+    if (rc == AFSIM_OK && err != cudaSuccess) rc = cuda_fail(h, err, "afsim_sweep_profile_wavefront");
+    if (rc == AFSIM_OK) {
+        static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
+                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT};
+        for (int i = 0; i < n_stages; ++i) {
+            double busy = 0.0;
+            for (int c = 0; c < tr.n; ++c) {
+                float ms = 0.0f;
+                const size_t e0 = (static_cast<size_t>(c) * n_stages + i) * 2;
+                cudaEventElapsedTime(&ms, tr.ev[e0], tr.ev[e0 + 1]);
+                busy += ms;
+            }
+            float span = 0.0f;  // completion of the first traced chunk -> completion of the last one, on this stage
+            cudaEventElapsedTime(&span, tr.ev[static_cast<size_t>(i) * 2 + 1],
+                                 tr.ev[(static_cast<size_t>(tr.n - 1) * n_stages + i) * 2 + 1]);
+            out_kind[i] = b.stages[i].kind == SK_SPLIT ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
+            out_busy_ms[i] = static_cast<float>(busy / tr.n);
+            out_period_ms[i] = span / static_cast<float>(tr.n - 1);
+        }
+        *out_n = n_stages;
+    }
+    for (cudaEvent_t e : tr.ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int afsim_selftest_math(AfsimHandle* h, uint64_t n, uint64_t out_mismatches[6]) {
+    if (!h || !out_mismatches) return AFSIM_INVALID_ARGUMENT;
+    h->error.clear();
+    AF_CUDA(h, cudaSetDevice(h->device));
+    DeviceBuffers mem;
+    unsigned long long* d = nullptr;
+    AF_CUDA(h, mem.alloc(&d, 6));
+    AF_CUDA(h, cudaMemsetAsync(d, 0, 6 * sizeof(unsigned long long), h->stream));
+    AF_CUDA(h, launch_selftest_math(n, d, h->stream));
+    unsigned long long host[6] = {0, 0, 0, 0, 0, 0};
+    AF_CUDA(h, cudaMemcpyAsync(host, d, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 6; ++k) out_mismatches[k] = host[k];
     return AFSIM_OK;
 }
 

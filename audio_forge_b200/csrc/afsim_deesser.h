@@ -258,9 +258,11 @@ struct DeEsserApply {
     }
 
     // One sample of the second half of DeEsser::process_sample (deesser.rs:452-547).
+    // conf_div: prepared divisor 1 - conf_lo of norm_range(conf, conf_lo, 1.0) (conf_lo = the mode's confidence floor)
     template <bool HEAD>
     AF_HD float sample(float input, double voice_db, const double (&level_db)[3], const double (&conf_target)[3], int n,
-                       int fade_total, const DeApplyConst& k, const CandidateParams* p, double (*pyz)[2]) {
+                       int fade_total, const DeApplyConst& k, const CandidateParams* p, double (*pyz)[2], double conf_lo,
+                       const AfDivisor& conf_div) {
         const double det_attack = k.det_attack, det_release = k.det_release;
         const double max_red = k.max_red;
         double target[3];
@@ -279,7 +281,7 @@ struct DeEsserApply {
                 } else {
                     base[b] *= k.base_inactive;
                 }
-                const double conf_gain = norm_range(conf[b], k.conf_floor, 1.0);
+                const double conf_gain = clampd(af_div(conf[b] - conf_lo, conf_div), 0.0, 1.0);
                 const double over_db = fmax(ratio_db - base[b] - k.trigger, 0.0);
                 tr = clampd(over_db * k.slope * conf_gain, 0.0, k.cap);
             } else if (level_db[b] > k.threshold) {
@@ -287,7 +289,7 @@ struct DeEsserApply {
                 const double ratio_over = ratio_db - k.ratio_thr;
                 if (ratio_over > 0.0) {
                     const double over_db = fmin(level_over, ratio_over);
-                    const double conf_gain = norm_range(conf[b], 0.22, 1.0);
+                    const double conf_gain = clampd(af_div(conf[b] - conf_lo, conf_div), 0.0, 1.0);
                     tr = clampd(k.ratio_factor * over_db * conf_gain, 0.0, k.manual_cap);
                 }
             }
@@ -336,6 +338,8 @@ struct DeEsserApply {
         constexpr int U = kGroup;
         DeApplyConst k;
         k.load(table);
+        const double conf_lo = auto_mode ? k.conf_floor : 0.22;
+        const AfDivisor conf_div = af_divisor(1.0 - conf_lo);
         int t_head = 0;
         if (n0 < fade_total) {
             double pyz[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -343,7 +347,7 @@ struct DeEsserApply {
                 const size_t o = (size_t)t_head * stride;
                 const double lv[3] = {w[1][o], w[2][o], w[3][o]};
                 const double ct[3] = {w[4][o], w[5][o], w[6][o]};
-                x[o] = sample<true>(x[o], w[0][o], lv, ct, n0 + t_head, fade_total, k, p, pyz);
+                x[o] = sample<true>(x[o], w[0][o], lv, ct, n0 + t_head, fade_total, k, p, pyz, conf_lo, conf_div);
                 if (clk.at_end(n0 + t_head)) {
                     rows_de[(size_t)clk.blk * stride] = (float)current;
                     clk.advance();
@@ -377,7 +381,8 @@ struct DeEsserApply {
             constexpr bool FULL = decltype(full)::value;
             const int t0 = kt * U;
             const int valid = FULL ? U : m - t0;
-            // the per-sample body is ~400 instructions: keep the walk rolled (an unrolled tile spills)
+            // the per-sample body (three bands side by side, each with its coefficient rebuild inline so that their
+            // exp10 / division chains overlap) is ~600 instructions: keep the walk rolled
 #pragma unroll 1
             for (int u = 0; u < U; ++u) {
                 if (FULL || u < valid) {
@@ -386,7 +391,7 @@ struct DeEsserApply {
                     const double voice_db = sw[0].get(kt, u, ws[0] + o);
                     const double lv[3] = {sw[1].get(kt, u, ws[1] + o), sw[2].get(kt, u, ws[2] + o), sw[3].get(kt, u, ws[3] + o)};
                     const double ct[3] = {sw[4].get(kt, u, ws[4] + o), sw[5].get(kt, u, ws[5] + o), sw[6].get(kt, u, ws[6] + o)};
-                    xs[o] = sample<false>(in, voice_db, lv, ct, nb + t0 + u, fade_total, k, p, nullptr);
+                    xs[o] = sample<false>(in, voice_db, lv, ct, nb + t0 + u, fade_total, k, p, nullptr, conf_lo, conf_div);
                     if (clk.at_end(nb + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
                         rows_de[(size_t)clk.blk * stride] = (float)current;
                         clk.advance();

@@ -87,11 +87,17 @@ AF_R_KERNEL(k_comp_r7, body_comp_r7)
 AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_R_KERNEL(k_de_ra, body_de_ra)
-// R_c keeps ~60 doubles of state and constants live: capping it at 128 registers (4 blocks of 128 threads per
-// SM) trades a few L1-resident spills for twice the warps that hide its long division / exp10 chains.
-__global__ void __launch_bounds__(128, 4) k_de_rc(BatchArgs a, ChunkArgs ck) {
+// R_c works on tiles of 8 samples x 3 bands (afsim_deesser.h) and wants every register it can get: the staged
+// variant runs one warp per block (few-stream batches), the direct variant 128-thread blocks capped at 128
+// registers (big batches: twice the warps hide the spills that the cap costs).
+__global__ void __launch_bounds__(kRBlock) k_de_rc(BatchArgs a, ChunkArgs ck) {
     AF_STREAM_INDEX();
-    const Staging stg{a.stage_inputs ? stage_smem : nullptr, (int)blockDim.x, (int)threadIdx.x, 0};
+    const Staging stg{stage_smem, (int)blockDim.x, (int)threadIdx.x, 0};
+    body_de_rc(a, ck, s, stg);
+}
+__global__ void __launch_bounds__(128, 4) k_de_rc_direct(BatchArgs a, ChunkArgs ck) {
+    AF_STREAM_INDEX();
+    const Staging stg{nullptr, (int)blockDim.x, (int)threadIdx.x, 0};
     body_de_rc(a, ck, s, stg);
 }
 
@@ -219,9 +225,46 @@ __global__ void __launch_bounds__(256) k_issue_peak(int kind, int iters, double*
     }
 }
 
+// Self-test of afsim_math.h: the custom routines against the CUDA math library / division on hashed arguments;
+// counts[k] = results that differ in any bit (k: 0 log10, 1 exp10, 2 x/20, 3 x/40, 4 x/3.75, 5 a/b through AfDivisor).
+__global__ void __launch_bounds__(256) k_selftest_math(unsigned long long n, unsigned long long* counts) {
+    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0};
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint64_t z = 0x9e3779b97f4a7c15ull * (i + 1);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z = z ^ (z >> 31);
+        const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+        const double v = (double)((z * 0xd1342543de82ef95ull) >> 11) * (1.0 / 9007199254740992.0);
+        // log10: magnitudes the chain sees (1e-10 floors .. a few), plus the whole normal range now and then
+        const int wide = (int)(z & 15) == 0;
+        const double lx = wide ? __longlong_as_double((long long)((z >> 1) & 0x7fefffffffffffffull) | 0x0010000000000000ll)
+                               : exp2(-40.0 + 44.0 * u) * (1.0 + v);
+        // exp10 / divisions: dB-sized arguments, both signs, plus tiny and huge ones now and then
+        const double ex = wide ? (u - 0.5) * 700.0 : (u - 0.5) * 24.0;
+        const double dx = wide ? __longlong_as_double((long long)(z & 0xffefffffffffffffull)) : (u - 0.5) * 240.0 * v;
+        bad[0] += __double_as_longlong(af_log10(lx)) != __double_as_longlong(log10(lx));
+        bad[1] += __double_as_longlong(af_exp10_fast(ex)) != __double_as_longlong(exp10(ex));
+        bad[2] += __double_as_longlong(af_div_const(dx, 20.0, 0.05)) != __double_as_longlong(dx / 20.0);
+        bad[3] += __double_as_longlong(af_div_const(dx, 40.0, 0.025)) != __double_as_longlong(dx / 40.0);
+        bad[4] += __double_as_longlong(af_div_const(dx, 3.75, 1.0 / 3.75)) != __double_as_longlong(dx / 3.75);
+        // prepared divisor: biquad-sized operands, and arbitrary finite ones now and then
+        const double num = wide ? dx : (v - 0.5) * 4.0;
+        const double den = wide ? __longlong_as_double((long long)((z * 0x2545f4914f6cdd1dull) & 0xffefffffffffffffull)) : 0.25 + 3.0 * u;
+        bad[5] += __double_as_longlong(af_div(num, af_divisor(den))) != __double_as_longlong(num / den);
+    }
+    for (int k = 0; k < 6; ++k)
+        if (bad[k]) atomicAdd(counts + k, bad[k]);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------
+cudaError_t launch_selftest_math(unsigned long long n, unsigned long long* counts, cudaStream_t st) {
+    k_selftest_math<<<148 * 4, 256, 0, st>>>(n, counts);
+    return cudaGetLastError();
+}
 cudaError_t launch_issue_peak(int kind, int iters, int blocks, double* sink, cudaStream_t st) {
     k_issue_peak<<<blocks, 256, 0, st>>>(kind, iters, sink);
     return cudaGetLastError();
@@ -329,7 +372,12 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         case SP_TP_FIR_OUT: k_tp_fir_out<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_DE_RA: k_de_ra<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_DE_MB: k_de_mb<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_DE_RC: k_de_rc<<<rgrid, rb, rsm, st>>>(a, ck); break;
+        case SP_DE_RC:
+            if (a.stage_inputs)
+                k_de_rc<<<rgrid, rb, rsm, st>>>(a, ck);
+            else
+                k_de_rc_direct<<<rgrid, rb, 0, st>>>(a, ck);
+            break;
         case SP_COMP_R7: k_comp_r7<<<rgrid, rb, rsm, st>>>(a, ck); break;
         default: return cudaErrorInvalidValue;
     }

@@ -32,6 +32,7 @@ cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);
 size_t finalize_workspace_bytes(int n_rows, int n_pad);
 cudaError_t launch_eq_response(const double* coeffs, const int* n_sections, const double* freqs, int n_freqs,
                                int n_sets, double fs, double* out, cudaStream_t st);
+cudaError_t launch_selftest_math(unsigned long long n, unsigned long long* counts, cudaStream_t st);
 cudaError_t launch_issue_peak(int kind, int iters, int blocks, double* sink, cudaStream_t st);
 cudaError_t launch_synth(float* out, size_t n_per, int n_passages, int kind, double fs, cudaStream_t st);
 

@@ -233,7 +233,7 @@ struct CompSplit : CompressorStage {
                 const double voiced_rms = fmax(sqrt(vsq[u]), 1e-8);
                 const double presence_rms = sqrt(psq[u]);
                 const double plosive = clampd(low_rms / voiced_rms, 0.0, 32.0);
-                const double amount = clampd((plosive - 1.25) / (5.0 - 1.25), 0.0, 1.0);
+                const double amount = clampd(af_div_const(plosive - 1.25, 5.0 - 1.25, 1.0 / (5.0 - 1.25)), 0.0, 1.0);
                 const double penalty = 1.0 - amount * (1.0 - 0.35);
                 const double presence_ratio = clampd(presence_rms / voiced_rms, 0.0, 4.0);
                 const double pw = 1.0 + 0.18 * clampd(presence_ratio - 0.75, 0.0, 1.0);
@@ -541,88 +541,89 @@ struct MakeupR {
                 xin[u] = (FULL || u < valid) ? sx.get(k, u, x + (size_t)(t0 + u) * stride) : 0.0f;
                 gv[u] = (FULL || u < valid) ? sg.get(k, u, g + (size_t)(t0 + u) * stride) : 0.0;
             }
-            auto walk = [&](auto may_end) {  // may_end: a slot (and with it possibly the block) can end inside this tile
-                constexpr bool CHECK = decltype(may_end)::value;
+            // one sample: gain, output, pre-gain energy, K-weighting (direct form II, add_frames_f32), slot sums
+            auto step = [&](int u) {
+                const double xv = (double)xin[u];
+                const double gain = gv[u] * mk_lin;
+                const float o = (float)(xv * gain);
+                y[u] = o;
+                sq_in += xv * xv;
+                const double v0 = (double)o - a1 * v1 - a2 * v2 - a3 * v3 - a4 * v4;
+                const double w = b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3 + b4 * v4;
+                v4 = v3;
+                v3 = v2;
+                v2 = v1;
+                v1 = fabs(v0) < 2.2250738585072014e-308 ? 0.0 : v0;  // denormal flush of the filter state
+                const double w2 = w * w;
+                full += w2;
+                tail += off >= tail_from ? w2 : 0.0;
+                off += 1;
+            };
+            if (FULL && slot - off > U && clk.ends_after(n0 + t0, U)) {
+                // no slot end, no block end in this tile: no per-sample checks
 #pragma unroll
+                for (int u = 0; u < U; ++u) step(u);
+            } else {
+                // a slot (and with it possibly the block) can end inside this tile: rolled, so that the block-end code
+                // exists once
+#pragma unroll 1
                 for (int u = 0; u < U; ++u) {
                     y[u] = 0.0f;
-                    if (FULL || u < valid) {
-                        const double xv = (double)xin[u];
-                        const double gain = gv[u] * mk_lin;
-                        const float o = (float)(xv * gain);
-                        y[u] = o;
-                        sq_in += xv * xv;
-                        // K-weighting, direct form II (add_frames_f32)
-                        const double v0 = (double)o - a1 * v1 - a2 * v2 - a3 * v3 - a4 * v4;
-                        const double w = b0 * v0 + b1 * v1 + b2 * v2 + b3 * v3 + b4 * v4;
-                        v4 = v3;
-                        v3 = v2;
-                        v2 = v1;
-                        v1 = fabs(v0) < 2.2250738585072014e-308 ? 0.0 : v0;  // denormal flush of the filter state
-                        const double w2 = w * w;
-                        full += w2;
-                        tail += off >= tail_from ? w2 : 0.0;
-                        off += 1;
-                        if (CHECK) {
-                            const int n = n0 + t0 + u;
-                            if (off == slot) {
-                                pend_full[(size_t)sub * stride] = full;
-                                pend_tail[(size_t)sub * stride] = tail;
-                                sub += 1;
-                                full = tail = 0.0;
-                                off = 0;
+                    if (!(FULL || u < valid)) continue;
+                    step(u);
+                    const int n = n0 + t0 + u;
+                    if (off == slot) {
+                        pend_full[(size_t)sub * stride] = full;
+                        pend_tail[(size_t)sub * stride] = tail;
+                        sub += 1;
+                        full = tail = 0.0;
+                        off = 0;
+                    }
+                    if (clk.at_end(n)) {
+                        const int blen = clk.block_len(n);
+                        const double rms_db = lin_to_db(sqrt(sq_in / (double)blen), 1e-10);  // block_rms_db :583-596
+                        double activity, reliability;
+                        const bool have_vad = evidence && vad != nullptr;
+                        estimate(rms_db, have_vad, have_vad ? vad[clk.blk] : 0.0, &activity, &reliability);
+                        if (activity > 0.20 && reliability >= 0.35) {  // :713-718: the meter hears the block
+                            c1 = v1;
+                            c2 = v2;
+                            c3 = v3;
+                            c4 = v4;
+                            for (int i = 0; i < sub; ++i) {
+                                const size_t r = (size_t)((pos + i) % n_slots) * stride;
+                                ring_full[r] = pend_full[(size_t)i * stride];
+                                ring_tail[r] = pend_tail[(size_t)i * stride];
                             }
-                            if (clk.at_end(n)) {
-                                const int blen = clk.block_len(n);
-                                const double rms_db = lin_to_db(sqrt(sq_in / (double)blen), 1e-10);  // block_rms_db :583-596
-                                double activity, reliability;
-                                const bool have_vad = evidence && vad != nullptr;
-                                estimate(rms_db, have_vad, have_vad ? vad[clk.blk] : 0.0, &activity, &reliability);
-                                if (activity > 0.20 && reliability >= 0.35) {  // :713-718: the meter hears the block
-                                    c1 = v1;
-                                    c2 = v2;
-                                    c3 = v3;
-                                    c4 = v4;
-                                    for (int i = 0; i < sub; ++i) {
-                                        const size_t r = (size_t)((pos + i) % n_slots) * stride;
-                                        ring_full[r] = pend_full[(size_t)i * stride];
-                                        ring_tail[r] = pend_tail[(size_t)i * stride];
-                                    }
-                                    const int partial = off > 0 ? (int)((pos + sub) % n_slots) : -1;  // final short block only
-                                    double sum = 0.0;
-                                    for (int i = 0; i < n_slots; ++i)
-                                        sum += i == partial ? full + ring_tail[(size_t)i * stride] : ring_full[(size_t)i * stride];
-                                    pos = (pos + sub) % n_slots;
-                                    const double energy = sum / (double)mc.window;
-                                    const double l = energy <= 0.0 ? -(double)INFINITY : 10.0 * log10(energy) - 0.691;
-                                    lufs = (double)(float)l;  // dsp/loudness.rs:123-125 keeps an f32
-                                } else {
-                                    v1 = c1;
-                                    v2 = c2;
-                                    v3 = c3;
-                                    v4 = c4;
-                                }
-                                update(activity, reliability, blen);
-                                mk_lin = db_to_lin(mk);
-                                if (rows) {
-                                    rows[((size_t)0 * n_rows + clk.blk) * stride] = (float)mk;
-                                    rows[((size_t)1 * n_rows + clk.blk) * stride] = (float)score;
-                                    rows[((size_t)2 * n_rows + clk.blk) * stride] = (float)rel;
-                                }
-                                sq_in = 0.0;
-                                full = tail = 0.0;
-                                off = 0;
-                                sub = 0;
-                                clk.advance();
-                            }
+                            const int partial = off > 0 ? (int)((pos + sub) % n_slots) : -1;  // final short block only
+                            double sum = 0.0;
+                            for (int i = 0; i < n_slots; ++i)
+                                sum += i == partial ? full + ring_tail[(size_t)i * stride] : ring_full[(size_t)i * stride];
+                            pos = (pos + sub) % n_slots;
+                            const double energy = sum / (double)mc.window;
+                            const double l = energy <= 0.0 ? -(double)INFINITY : 10.0 * log10(energy) - 0.691;
+                            lufs = (double)(float)l;  // dsp/loudness.rs:123-125 keeps an f32
+                        } else {
+                            v1 = c1;
+                            v2 = c2;
+                            v3 = c3;
+                            v4 = c4;
                         }
+                        update(activity, reliability, blen);
+                        mk_lin = db_to_lin(mk);
+                        if (rows) {
+                            rows[((size_t)0 * n_rows + clk.blk) * stride] = (float)mk;
+                            rows[((size_t)1 * n_rows + clk.blk) * stride] = (float)score;
+                            rows[((size_t)2 * n_rows + clk.blk) * stride] = (float)rel;
+                        }
+                        sq_in = 0.0;
+                        full = tail = 0.0;
+                        off = 0;
+                        sub = 0;
+                        clk.advance();
                     }
                 }
-            };
-            if (FULL && slot - off > U && clk.ends_after(n0 + t0, U))
-                walk(TileRagged());  // no slot end, no block end in this tile: no per-sample checks
-            else
-                walk(TileFull());
+            }
             store_tile(x + (size_t)t0 * stride, stride, valid, y);
         };
         pipelined_tiles(len, issue, body);

@@ -26,6 +26,8 @@
 #define AF_HD inline
 #endif
 
+#include "afsim_math.h"
+
 namespace afsim {
 
 // ---- numeric helpers -----------------------------------------------------------------------------------
@@ -36,13 +38,7 @@ AF_HD float af_fmaf(float a, float b, float c) {
     return fmaf(a, b, c);
 #endif
 }
-AF_HD double af_exp10(double x) {
-#if defined(__CUDA_ARCH__)
-    return exp10(x);
-#else
-    return pow(10.0, x);
-#endif
-}
+AF_HD double af_exp10(double x) { return af_exp10_fast(x); }  // afsim_math.h: the library's algorithm, constant-bank operands
 AF_HD float af_log10_f32(float v) {  // f32::log10
 #if defined(__CUDA_ARCH__)
     return (float)log10((double)v);
@@ -51,8 +47,8 @@ AF_HD float af_log10_f32(float v) {  // f32::log10
 #endif
 }
 AF_HD bool af_finite(float v) { return fabsf(v) <= 3.402823466e+38f; }  // false for inf and NaN
-AF_HD double lin_to_db(double v, double floor_) { return 20.0 * log10(fmax(fabs(v), floor_)); }  // dsp/util.rs:17-20
-AF_HD double db_to_lin(double db) { return af_exp10(db / 20.0); }                                  // dsp/util.rs:11-14
+AF_HD double lin_to_db(double v, double floor_) { return 20.0 * af_log10(fmax(fabs(v), floor_)); }  // dsp/util.rs:17-20
+AF_HD double db_to_lin(double db) { return af_exp10(af_div_const(db, 20.0, 0.05)); }                 // dsp/util.rs:11-14
 AF_HD float lin_to_db_f32(float v) { return 20.0f * af_log10_f32(fmaxf(v, 1.0e-12f)); }            // python_api.rs:54-56
 AF_HD double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 AF_HD float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -335,27 +331,22 @@ struct EqStage {
 };
 
 // ---- dynamic-EQ de-esser (dsp/deesser.rs:405-547) -----------------------------------------------------------
-// Not inlined on the device: the de-esser's serial kernel calls it for three bands per sample, and one warp
-// per SM walking a loop body that does not fit the instruction cache stalls on instruction fetch.
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__
-#else
-inline
-#endif
-Bq design_peaking(double cs, double alpha, double gain_db) {  // dsp/biquad.rs:110-126,180-181
-    const double a = af_exp10(gain_db / 40.0);
+// The five coefficients share the divisor a0 (one refined reciprocal, afsim_math.h); a1 / a0 is the same quotient as
+// b1 / a0 (both numerators are -2 cos w).
+AF_HD Bq design_peaking(double cs, double alpha, double gain_db) {  // dsp/biquad.rs:110-126,180-181
+    const double a = af_exp10(af_div_const(gain_db, 40.0, 0.025));
     const double b0 = 1.0 + alpha * a;
     const double b1 = -2.0 * cs;
     const double b2 = 1.0 - alpha * a;
     const double a0 = 1.0 + alpha / a;
-    const double a1 = -2.0 * cs;
     const double a2 = 1.0 - alpha / a;
+    const AfDivisor d = af_divisor(a0);
     Bq c;
-    c.b0 = b0 / a0;
-    c.b1 = b1 / a0;
-    c.b2 = b2 / a0;
-    c.a1 = a1 / a0;
-    c.a2 = a2 / a0;
+    c.b0 = af_div(b0, d);
+    c.b1 = af_div(b1, d);
+    c.b2 = af_div(b2, d);
+    c.a1 = c.b1;
+    c.a2 = af_div(a2, d);
     return c;
 }
 
@@ -491,7 +482,7 @@ struct CompressorStage {
                     const double voiced_rms = fmax(sqrt(vsq[i]), 1e-8);
                     const double presence_rms = sqrt(psq[i]);
                     const double plosive = clampd(low_rms / voiced_rms, 0.0, 32.0);
-                    const double amount = clampd((plosive - 1.25) / (5.0 - 1.25), 0.0, 1.0);
+                    const double amount = clampd(af_div_const(plosive - 1.25, 5.0 - 1.25, 1.0 / (5.0 - 1.25)), 0.0, 1.0);
                     const double penalty = 1.0 - amount * (1.0 - 0.35);
                     const double presence_ratio = clampd(presence_rms / voiced_rms, 0.0, 4.0);
                     const double pw = 1.0 + 0.18 * clampd(presence_ratio - 0.75, 0.0, 1.0);

@@ -28,8 +28,8 @@ EXPORTS = (
     "afsim_eq_response", "afsim_chain_sweep", "afsim_sweep_prepare", "afsim_sweep_prepare_synthetic",
     "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
     "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
-    "afsim_sweep_profile_stages", "afsim_measure_issue_peak",
-    "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
+    "afsim_sweep_profile_stages", "afsim_sweep_profile_wavefront", "afsim_measure_issue_peak",
+    "afsim_selftest_math", "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
                "comp_r1", "comp_m2", "comp_r3", "comp_m4", "comp_r5", "comp_m6", "lim_m", "lim_r", "tp_fir_in", "tp_r",
@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
     L.afsim_sweep_profile_stages.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
     L.afsim_measure_issue_peak.argtypes = [vp, C.c_int, f64p]
+    L.afsim_sweep_profile_wavefront.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, f32p,
+                                                C.POINTER(C.c_int)]
+    L.afsim_selftest_math.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
     mk_p = C.POINTER(abi.AfAutoMakeupSettings)
     L.afsim_auto_makeup_settings_default.argtypes = [mk_p]
     L.afsim_auto_makeup_settings_default.restype = None
@@ -153,6 +156,14 @@ class Sweep:
         self._sim._check(lib().afsim_sweep_profile_stages(self._sim._h, self._ptr, int(max_chunks), cap, kinds, ms,
                                                           launches, C.byref(n)))
         return [(STAGE_NAMES[kinds[i]], float(ms[i]), int(launches[i])) for i in range(n.value)]
+
+    def profile_wavefront(self, first_chunk: int = 64, n_chunks: int = 64):
+        """Live wavefront with timing events -> [(stage name, busy ms per launch under contention, period ms)]."""
+        cap = 32
+        kinds, busy, period, n = (C.c_int * cap)(), (C.c_float * cap)(), (C.c_float * cap)(), C.c_int(0)
+        self._sim._check(lib().afsim_sweep_profile_wavefront(self._sim._h, self._ptr, int(first_chunk), int(n_chunks), cap,
+                                                             kinds, busy, period, C.byref(n)))
+        return [(STAGE_NAMES[kinds[i]], float(busy[i]), float(period[i])) for i in range(n.value)]
 
     @property
     def kernel_count(self) -> int:
@@ -209,6 +220,12 @@ class Simulator:
         out = C.c_double(0.0)
         self._check(lib().afsim_measure_issue_peak(self._h, int(kind), C.byref(out)))
         return float(out.value)
+
+    def selftest_math(self, n: int = 1 << 24) -> dict[str, int]:
+        """Bit mismatches of the map kernels' device math against the CUDA library on n hashed arguments."""
+        out = (C.c_uint64 * 6)()
+        self._check(lib().afsim_selftest_math(self._h, int(n), out))
+        return dict(zip(("log10", "exp10", "div20", "div40", "div3.75", "div_prepared"), (int(v) for v in out)))
 
     # ---- single-stream entry points ----
     def chain_render(self, audio, sample_rate, bands, settings: abi.AfChainSettings, return_audio: bool = False):

@@ -314,6 +314,18 @@ typedef enum AfStageKind {
  * of its launch durations, out_launches[i] = launches timed.  *out_n = entries written (<= capacity). */
 int afsim_sweep_profile_stages(AfsimHandle* handle, AfsimSweep* sweep, int max_chunks, int capacity,
                                int* out_kind, float* out_ms, int* out_launches, int* out_n);
+/* The same batch in the LIVE wavefront (every stage on its own stream, as afsim_sweep_launch runs it) with timing
+ * events around the launches of chunks [first_chunk, first_chunk + n_chunks): per stage, out_busy_ms[i] = mean time
+ * from "launch eligible" (its waits satisfied) to "kernel done" -- the stage's duration under contention -- and
+ * out_period_ms[i] = mean time between the completions of consecutive chunks on that stage (the pipeline period). */
+int afsim_sweep_profile_wavefront(AfsimHandle* handle, AfsimSweep* sweep, int first_chunk, int n_chunks, int capacity,
+                                  int* out_kind, float* out_busy_ms, float* out_period_ms, int* out_n);
+/* Self-test of the device math of the map kernels (csrc/afsim_math.h: the CUDA library's log10 / exp10 algorithms
+ * with constant-bank coefficients, division by a constant as multiply + exact remainder + correction) against the
+ * library routines / the division instruction sequence on n hashed arguments: out_mismatches[k] = results that
+ * differ in any bit, k = 0 log10, 1 exp10, 2 x/20, 3 x/40, 4 x/3.75, 5 a/b with a shared prepared divisor.  All
+ * six must be 0. */
+int afsim_selftest_math(AfsimHandle* handle, uint64_t n, uint64_t out_mismatches[6]);
 /* Sustained issue rate of this GPU in 1e9 warp-lane instructions per second: kind 0 = dependent
  * FP64 DMUL+DADD chains (the instruction mix of the unfused biquads), kind 1 = FP32 FFMA chains. */
 int afsim_measure_issue_peak(AfsimHandle* handle, int kind, double* out_giga_instr_per_s);
