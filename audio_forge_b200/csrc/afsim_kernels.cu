@@ -74,10 +74,19 @@ __global__ void __launch_bounds__(128) k_input_true_peak(BatchArgs a, ChunkArgs 
 // ---- split (R/M) path: serial recurrences, one thread per stream --------------------------------------------
 // Each thread stages its inputs through shared memory with cp.async (Staging, afsim_split.h).
 extern __shared__ __align__(16) unsigned char stage_smem[];
+// Staged kernels run one warp per block (kRBlock lanes share the staging area): base and lane count are
+// compile-time constants, so every staging address folds to `lane + constant`.  The de-esser's serial kernels also
+// exist as direct variants (128-thread blocks reading global memory) for batches that fill the GPU by themselves.
 #define AF_R_KERNEL(name, body)                                                         \
-    __global__ void __launch_bounds__(128) name(BatchArgs a, ChunkArgs ck) {            \
+    __global__ void __launch_bounds__(kRBlock) name(BatchArgs a, ChunkArgs ck) {        \
         AF_STREAM_INDEX();                                                              \
-        const Staging stg{a.stage_inputs ? stage_smem : nullptr, (int)blockDim.x, (int)threadIdx.x, 0}; \
+        const Staging stg{stage_smem, kRBlock, (int)threadIdx.x, 0};                    \
+        body(a, ck, s, stg);                                                            \
+    }
+#define AF_R_KERNEL_DIRECT(name, body, minblocks)                                       \
+    __global__ void __launch_bounds__(128, minblocks) name(BatchArgs a, ChunkArgs ck) { \
+        AF_STREAM_INDEX();                                                              \
+        const Staging stg{nullptr, 128, (int)threadIdx.x, 0};                           \
         body(a, ck, s, stg);                                                            \
     }
 AF_R_KERNEL(k_comp_r1, body_comp_r1)
@@ -87,19 +96,11 @@ AF_R_KERNEL(k_comp_r7, body_comp_r7)
 AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_R_KERNEL(k_de_ra, body_de_ra)
-// R_c works on tiles of 8 samples x 3 bands (afsim_deesser.h) and wants every register it can get: the staged
-// variant runs one warp per block (few-stream batches), the direct variant 128-thread blocks capped at 128
-// registers (big batches: twice the warps hide the spills that the cap costs).
-__global__ void __launch_bounds__(kRBlock) k_de_rc(BatchArgs a, ChunkArgs ck) {
-    AF_STREAM_INDEX();
-    const Staging stg{stage_smem, (int)blockDim.x, (int)threadIdx.x, 0};
-    body_de_rc(a, ck, s, stg);
-}
-__global__ void __launch_bounds__(128, 4) k_de_rc_direct(BatchArgs a, ChunkArgs ck) {
-    AF_STREAM_INDEX();
-    const Staging stg{nullptr, (int)blockDim.x, (int)threadIdx.x, 0};
-    body_de_rc(a, ck, s, stg);
-}
+AF_R_KERNEL_DIRECT(k_de_ra_direct, body_de_ra, 1)
+// R_c keeps ~60 doubles of state and constants live and walks three bands side by side: the staged variant takes
+// every register it can get; the direct variant is capped at 128 (twice the warps hide the spills the cap costs).
+AF_R_KERNEL(k_de_rc, body_de_rc)
+AF_R_KERNEL_DIRECT(k_de_rc_direct, body_de_rc, 4)
 
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
 // A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping
@@ -370,7 +371,12 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         case SP_TP_FIR_IN: k_tp_fir_in<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_TP_R: k_tp_r<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_TP_FIR_OUT: k_tp_fir_out<<<mgrid, mb, 0, st>>>(a, ck); break;
-        case SP_DE_RA: k_de_ra<<<rgrid, rb, rsm, st>>>(a, ck); break;
+        case SP_DE_RA:
+            if (a.stage_inputs)
+                k_de_ra<<<rgrid, rb, rsm, st>>>(a, ck);
+            else
+                k_de_ra_direct<<<rgrid, rb, 0, st>>>(a, ck);
+            break;
         case SP_DE_MB: k_de_mb<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_DE_RC:
             if (a.stage_inputs)
