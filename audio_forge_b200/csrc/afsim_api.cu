@@ -107,7 +107,7 @@ struct DeviceBuffers {  // returns what it allocated to the handle's pool
     }
 };
 
-enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT };
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT };
 struct StageDesc {
     StageKind kind;
     int arg;  // SK_EQ: first section; SK_SPLIT: SplitOp
@@ -115,6 +115,8 @@ struct StageDesc {
 
 struct Batch {
     BatchArgs args{};
+    BatchArgs shared_input{};       // the distinct passages' input stage (n_streams == 0: every stream renders its own)
+    size_t shared_rows_elems = 0;
     std::vector<StageDesc> stages;
     std::vector<uint32_t> members;  // caller's pair index of stream s
     size_t mk_ring_elems = 0;       // auto makeup: doubles in args.mk_ring
@@ -463,7 +465,68 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             if (!(a.structure & ST_DEESSER)) return;
             for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC}) batch->stages.push_back({SK_SPLIT, op});
         };
-        batch->stages.push_back({SK_INPUT, 0});
+        // Shared input stage: when several streams of the batch read the same passage (a candidate sweep), the input
+        // stage -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.
+        {
+            std::map<uint64_t, uint32_t> distinct;
+            std::vector<uint32_t> uidx(S_pad, 0);
+            std::vector<uint64_t> usrc;
+            std::vector<uint32_t> ucand;
+            for (int s = 0; s < S; ++s) {
+                auto it = distinct.find(src_off[s]);
+                if (it == distinct.end()) {
+                    it = distinct.emplace(src_off[s], static_cast<uint32_t>(usrc.size())).first;
+                    usrc.push_back(src_off[s]);
+                    ucand.push_back(cand[s]);
+                }
+                uidx[s] = it->second;
+            }
+            const int U = static_cast<int>(usrc.size());
+            if (S >= 64 && U * 4 <= S && env_int("AFSIM_SHARED_INPUT", 1) != 2) {
+                const int U_pad = round_up(U, 32);
+                usrc.resize(U_pad, 0);
+                ucand.resize(U_pad, 0);
+                BatchArgs& ua = batch->shared_input;
+                ua = a;
+                ua.n_streams = U;
+                ua.stride = U_pad;
+                uint32_t *d_uidx = nullptr, *d_ucand = nullptr;
+                uint64_t* d_usrc = nullptr;
+                float *d_ubuf = nullptr, *d_urows = nullptr;
+                StreamAccum* d_uaccum = nullptr;
+                double* d_ustate = nullptr;
+                batch->shared_rows_elems = static_cast<size_t>(std::max(a.n_rows, 1)) * U_pad;
+                AF_CUDA(h, sweep->mem.alloc(&d_uidx, S_pad));
+                AF_CUDA(h, sweep->mem.alloc(&d_ucand, U_pad));
+                AF_CUDA(h, sweep->mem.alloc(&d_usrc, U_pad));
+                AF_CUDA(h, sweep->mem.alloc(&d_ubuf, static_cast<size_t>(a.ring_rows) * U_pad));
+                AF_CUDA(h, sweep->mem.alloc(&d_urows, batch->shared_rows_elems));
+                AF_CUDA(h, sweep->mem.alloc(&d_uaccum, U_pad));
+                AF_CUDA(h, sweep->mem.alloc(&d_ustate, static_cast<size_t>(kStateInput) * U_pad));
+                AF_CUDA(h, cudaMemcpyAsync(d_uidx, uidx.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+                AF_CUDA(h, cudaMemcpyAsync(d_ucand, ucand.data(), U_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+                AF_CUDA(h, cudaMemcpyAsync(d_usrc, usrc.data(), U_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+                AF_CUDA(h, cudaStreamSynchronize(h->stream));
+                ua.cand = d_ucand;
+                ua.src_off = d_usrc;
+                ua.buf_a = d_ubuf;
+                ua.rows = d_urows;
+                ua.accum = d_uaccum;
+                ua.st_input = d_ustate;
+                ua.stage_inputs = 0;
+                a.in_unique = d_uidx;
+                a.in_src = d_ubuf;
+                a.in_rows = d_urows;
+                a.in_accum = d_uaccum;
+                a.in_stride = U_pad;
+            }
+        }
+        if (batch->shared_input.n_streams > 0) {
+            batch->stages.push_back({SK_INPUT_SHARED, 0});
+            batch->stages.push_back({SK_INPUT_FANOUT, 0});
+        } else {
+            batch->stages.push_back({SK_INPUT, 0});
+        }
         if (a.structure & ST_INPUT_TRUE_PEAK) batch->stages.push_back({SK_INPUT_TP, 0});
         if (a.structure & ST_EQ_BEFORE_DEESSER) {
             push_eq();
@@ -504,6 +567,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
 cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& ck, cudaStream_t stream) {
     switch (st.kind) {
         case SK_INPUT: return launch_input(b.args, ck, stream);
+        case SK_INPUT_SHARED: return launch_input(b.shared_input, ck, stream);
+        case SK_INPUT_FANOUT: return launch_input_fanout(b.args, ck, stream);
         case SK_INPUT_TP: return launch_input_true_peak(b.args, ck, stream);
         case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
@@ -527,6 +592,10 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
     const int T = a.n_samples;
     AF_CUDA(h, cudaMemsetAsync(a.accum, 0, static_cast<size_t>(a.stride) * sizeof(StreamAccum), h->stream));
     AF_CUDA(h, cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
+    if (b.shared_input.n_streams > 0) {
+        AF_CUDA(h, cudaMemsetAsync(b.shared_input.accum, 0, static_cast<size_t>(b.shared_input.stride) * sizeof(StreamAccum), h->stream));
+        AF_CUDA(h, cudaMemsetAsync(b.shared_input.rows, 0, b.shared_rows_elems * sizeof(float), h->stream));
+    }
     if (a.structure & ST_DEESSER) AF_CUDA(h, launch_expand_deesser(a, h->stream));
     if (a.mk_ring) AF_CUDA(h, cudaMemsetAsync(a.mk_ring, 0, b.mk_ring_elems * sizeof(double), h->stream));
     if (a.mk_rows) AF_CUDA(h, cudaMemsetAsync(a.mk_rows, 0, static_cast<size_t>(3) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
@@ -534,6 +603,7 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
         AF_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         auto stream_of = [&](int i) {
             const StageDesc& sd = b.stages[i];
+            if (sd.kind == SK_INPUT_FANOUT) return h->stage_stream_map[i];
             const bool is_map = sd.kind == SK_SPLIT && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
                                                         sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT ||
                                                         sd.arg == SP_DE_MB);
@@ -812,7 +882,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
         return cuda_fail(h, err, "afsim_sweep_profile_stages");
     }
     static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT};
+                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT};
     for (int i = 0; i < n_stages; ++i) {
         double total = 0.0;
         for (int c = 0; c < timed_chunks; ++c) {
@@ -857,7 +927,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
     if (rc == AFSIM_OK && err != cudaSuccess) rc = cuda_fail(h, err, "afsim_sweep_profile_wavefront");
     if (rc == AFSIM_OK) {
         static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT};
+                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT};
         for (int i = 0; i < n_stages; ++i) {
             double busy = 0.0;
             for (int c = 0; c < tr.n; ++c) {
@@ -1014,6 +1084,94 @@ int afsim_eq_response(AfsimHandle* h, const double* frequencies_hz, size_t n_fre
     return AFSIM_OK;
 }
 
+// max of the configured response over 512 log-spaced points 20 Hz .. 20 kHz (lib.rs:252-262)
+static int eq_render_max_response(AfsimHandle* h, const AfBand bands[AFSIM_NUM_BANDS], double sample_rate, double* out_max) {
+    std::vector<double> freqs(512), resp(512);
+    for (int i = 0; i < 512; ++i) freqs[i] = 20.0 * std::pow(20000.0 / 20.0, static_cast<double>(i) / 511.0);
+    std::vector<double> coeffs(kMaxSections * 5);
+    std::vector<int> sections(AFSIM_NUM_BANDS);
+    plan_eq_sections(bands, true, sample_rate, reinterpret_cast<double(*)[5]>(coeffs.data()), sections.data());
+    DeviceBuffers mem;
+    mem.pool = &h->pool;
+    double *d_coeffs = nullptr, *d_freqs = nullptr, *d_out = nullptr;
+    int* d_sections = nullptr;
+    AF_CUDA(h, mem.alloc(&d_coeffs, coeffs.size()));
+    AF_CUDA(h, mem.alloc(&d_sections, sections.size()));
+    AF_CUDA(h, mem.alloc(&d_freqs, freqs.size()));
+    AF_CUDA(h, mem.alloc(&d_out, resp.size()));
+    AF_CUDA(h, cudaMemcpyAsync(d_coeffs, coeffs.data(), coeffs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(d_sections, sections.data(), sections.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(d_freqs, freqs.data(), freqs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, launch_eq_response(d_coeffs, d_sections, d_freqs, 512, 1, sample_rate, d_out, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(resp.data(), d_out, resp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    double max_resp = -std::numeric_limits<double>::infinity();
+    for (double v : resp) max_resp = std::fmax(max_resp, v);
+    *out_max = max_resp;
+    return AFSIM_OK;
+}
+
+// One long passage: the time-parallel cascade (afsim_eqscan.h) instead of a batch of one stream.
+static int eq_render_scan(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
+                          const CandidatePlan& plan, AfEqRenderStats* out_stats, float* out_audio) {
+    AF_CUDA(h, cudaSetDevice(h->device));
+    int log2_len = 6;  // 64-sample segments; longer ones once the passage has more than 32768 of them
+    while ((n >> log2_len) > 32768 && log2_len < 20) ++log2_len;
+    const size_t len = size_t(1) << log2_len, n_seg = (n + len - 1) / len;
+    DeviceBuffers mem;
+    mem.pool = &h->pool;
+    float *d_in = nullptr, *d_out = nullptr, *d_xt = nullptr;
+    double* d_state = nullptr;
+    EqScanStats *d_partial = nullptr, *d_stats = nullptr;
+    AF_CUDA(h, mem.alloc(&d_in, n));
+    AF_CUDA(h, mem.alloc(&d_out, n));
+    AF_CUDA(h, mem.alloc(&d_xt, n_seg * len));
+    AF_CUDA(h, mem.alloc(&d_state, 4 * n_seg));
+    AF_CUDA(h, mem.alloc(&d_partial, eqscan_stats_partials(n)));
+    AF_CUDA(h, mem.alloc(&d_stats, 2));
+    cudaEvent_t e0, e1;
+    AF_CUDA(h, cudaEventCreate(&e0));
+    AF_CUDA(h, cudaEventCreate(&e1));
+    struct EventGuard {
+        cudaEvent_t a, b;
+        ~EventGuard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } guard{e0, e1};
+    AF_CUDA(h, cudaMemcpyAsync(d_in, audio, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaEventRecord(e0, h->stream));
+    int launches = 0;
+    AF_CUDA(h, launch_plain_stats(d_in, n, d_partial, d_stats, h->stream));
+    AF_CUDA(h, launch_eqscan(d_in, d_out, n, plan.params.eq, static_cast<int>(plan.params.n_sections), log2_len, d_xt, d_state,
+                             &launches, h->stream));
+    AF_CUDA(h, launch_plain_stats(d_out, n, d_partial, d_stats + 1, h->stream));
+    AF_CUDA(h, cudaEventRecord(e1, h->stream));
+    EqScanStats st[2];
+    AF_CUDA(h, cudaMemcpyAsync(st, d_stats, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    if (out_audio) AF_CUDA(h, cudaMemcpyAsync(out_audio, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.0f;
+    AF_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+    double max_resp = 0.0;
+    const int rc = eq_render_max_response(h, bands, sample_rate, &max_resp);
+    if (rc != AFSIM_OK) return rc;
+    std::memset(out_stats, 0, sizeof *out_stats);
+    const double divisor = static_cast<double>(std::max<size_t>(n, 1));
+    out_stats->input_sample_peak = st[0].peak;
+    out_stats->output_sample_peak = st[1].peak;
+    out_stats->input_true_peak = st[0].tp_peak;
+    out_stats->output_true_peak = st[1].tp_peak;
+    out_stats->input_rms = std::sqrt(st[0].sum / divisor);
+    out_stats->output_rms = std::sqrt(st[1].sum / divisor);
+    out_stats->max_response_db = max_resp;
+    out_stats->runtime_ms = static_cast<double>(ms);
+    out_stats->sample_count = n;
+    out_stats->algorithmic_latency_samples = 0;
+    out_stats->non_finite_output = st[1].non_finite;
+    return AFSIM_OK;
+}
+
 int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
                     AfEqRenderStats* out_stats, float* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
@@ -1025,6 +1183,10 @@ int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_
     if (rc != AFSIM_OK) return set_error(h, rc, msg);
     for (size_t i = 0; i < n; ++i)  // lib.rs:225-229
         if (!std::isfinite(audio[i])) return set_error(h, AFSIM_INVALID_ARGUMENT, "audio must contain only finite samples");
+    // Long single passages take the time-parallel cascade (within the render tolerance of the serial walk); short
+    // ones stay on the bit-exact stage kernels.  AFSIM_EQ_SCAN_MIN overrides the threshold (samples).
+    if (n >= static_cast<size_t>(env_int("AFSIM_EQ_SCAN_MIN", 65536)))
+        return eq_render_scan(h, audio, n, sample_rate, bands, plan, out_stats, out_audio);
     const float* passages[1] = {audio};
     const size_t lens[1] = {n};
     PassageSource src;
@@ -1044,29 +1206,9 @@ int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_
         rc = afsim_sweep_collect_audio(h, sweep, 0, out_audio, n);
         if (rc != AFSIM_OK) return rc;
     }
-    // max of the configured response over 512 log-spaced points 20 Hz .. 20 kHz (lib.rs:252-262)
-    std::vector<double> freqs(512), resp(512);
-    for (int i = 0; i < 512; ++i) freqs[i] = 20.0 * std::pow(20000.0 / 20.0, static_cast<double>(i) / 511.0);
-    double max_resp = -std::numeric_limits<double>::infinity();
-    {
-        std::vector<double> coeffs(kMaxSections * 5);
-        std::vector<int> sections(AFSIM_NUM_BANDS);
-        plan_eq_sections(bands, true, sample_rate, reinterpret_cast<double(*)[5]>(coeffs.data()), sections.data());
-        DeviceBuffers mem;
-        double *d_coeffs = nullptr, *d_freqs = nullptr, *d_out = nullptr;
-        int* d_sections = nullptr;
-        AF_CUDA(h, mem.alloc(&d_coeffs, coeffs.size()));
-        AF_CUDA(h, mem.alloc(&d_sections, sections.size()));
-        AF_CUDA(h, mem.alloc(&d_freqs, freqs.size()));
-        AF_CUDA(h, mem.alloc(&d_out, resp.size()));
-        AF_CUDA(h, cudaMemcpyAsync(d_coeffs, coeffs.data(), coeffs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        AF_CUDA(h, cudaMemcpyAsync(d_sections, sections.data(), sections.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        AF_CUDA(h, cudaMemcpyAsync(d_freqs, freqs.data(), freqs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        AF_CUDA(h, launch_eq_response(d_coeffs, d_sections, d_freqs, 512, 1, sample_rate, d_out, h->stream));
-        AF_CUDA(h, cudaMemcpyAsync(resp.data(), d_out, resp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        AF_CUDA(h, cudaStreamSynchronize(h->stream));
-        for (double v : resp) max_resp = std::fmax(max_resp, v);
-    }
+    double max_resp = 0.0;
+    rc = eq_render_max_response(h, bands, sample_rate, &max_resp);
+    if (rc != AFSIM_OK) return rc;
     std::memset(out_stats, 0, sizeof *out_stats);
     const double divisor = static_cast<double>(std::max<size_t>(n, 1));
     out_stats->input_sample_peak = acc.peak_in;

@@ -115,6 +115,7 @@ AF_R_KERNEL_DIRECT(k_de_rc_direct, body_de_rc, 4)
             call;                                                                        \
         }                                                                                \
     }
+AF_M_KERNEL(k_input_fanout, kFanoutGroup, body_input_fanout(a, ck, s, g))
 AF_M_KERNEL(k_comp_m2, kCompMapGroup, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
 AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
@@ -287,6 +288,12 @@ cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t s
         k_input_cleanup<<<stream_grid(a, b), b, 0, st>>>(a, ck);
     else
         k_input<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    return cudaGetLastError();
+}
+cudaError_t launch_input_fanout(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
+    const int n_groups = (ck.len + kFanoutGroup - 1) / kFanoutGroup;
+    const dim3 grid((unsigned)((a.n_streams + 31) / 32), (unsigned)((n_groups + kMapWarps - 1) / kMapWarps));
+    k_input_fanout<<<grid, 32 * kMapWarps, 0, st>>>(a, ck);
     return cudaGetLastError();
 }
 cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first, int k, cudaStream_t st) {

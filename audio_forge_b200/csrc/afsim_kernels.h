@@ -15,6 +15,7 @@ constexpr size_t kFinalizeSmemLimit = 200 * 1024;
 
 cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);
 cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t launch_input_fanout(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first_section, int k, cudaStream_t st);
 cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_limiter(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
@@ -32,6 +33,16 @@ cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);
 size_t finalize_workspace_bytes(int n_rows, int n_pad);
 cudaError_t launch_eq_response(const double* coeffs, const int* n_sections, const double* freqs, int n_freqs,
                                int n_sets, double fs, double* out, cudaStream_t st);
+// time-parallel EQ render of one long passage + plain-array statistics (afsim_eqscan.cu)
+struct EqScanStats {  // layout of PlainStats
+    double sum;
+    float peak, tp_peak;
+    unsigned non_finite, pad;
+};
+size_t eqscan_stats_partials(size_t n);
+cudaError_t launch_plain_stats(const float* x, size_t n, void* partial, void* out, cudaStream_t st);
+cudaError_t launch_eqscan(const float* d_in, float* d_out, size_t n, const double (*coeffs)[5], int n_sections, int log2_len,
+                          float* xt, double* seg_state, int* launches, cudaStream_t st);
 cudaError_t launch_selftest_math(unsigned long long n, unsigned long long* counts, cudaStream_t st);
 cudaError_t launch_issue_peak(int kind, int iters, int blocks, double* sink, cudaStream_t st);
 cudaError_t launch_synth(float* out, size_t n_per, int n_passages, int kind, double fs, cudaStream_t st);

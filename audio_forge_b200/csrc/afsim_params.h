@@ -166,6 +166,13 @@ struct BatchArgs {
     const int64_t* mk_vad_off;    // [S_pad] offset of the stream's probabilities in mk_vad, -1 = no evidence
     const MakeupConst* mk_const;  // loudness meter constants of the sample rate
     StreamAccum* accum;           // [S_pad]
+    // shared input stage: streams of a batch have one input stage setting, so its output depends on the passage
+    // alone; it is rendered once per distinct passage (a small batch of its own) and fanned out to the streams
+    const uint32_t* in_unique;    // [S_pad] index of the stream's passage among the batch's distinct ones, or nullptr
+    const float* in_src;          // [ring_rows][in_stride] input stage output of the distinct passages
+    const float* in_rows;         // [n_rows][in_stride] their input-level rows (row.0)
+    const StreamAccum* in_accum;  // [in_stride] their input statistics
+    int in_stride;
     const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
     const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)
     const struct CleanupConst* cleanup;  // sample-rate constants of the adaptive input cleanup (afsim_cleanup.h)

@@ -123,6 +123,29 @@ AF_HD void body_input(const BatchArgs& a, const ChunkArgs& ck, int s) {
     }
 }
 
+// ---- shared input stage: copy the distinct passage's input stage output, rows and statistics to stream s -----------
+constexpr int kFanoutGroup = 32;  // samples per thread
+AF_HD void body_input_fanout(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    const size_t stride = (size_t)a.stride, ustride = (size_t)a.in_stride;
+    const uint32_t u = a.in_unique[s];
+    const int t0 = g * kFanoutGroup;
+    const int valid = ck.len - t0 < kFanoutGroup ? ck.len - t0 : kFanoutGroup;
+    const float* src = a.in_src + (size_t)(ck.row0 + t0) * ustride + u;
+    float* dst = a.buf_a + (size_t)(ck.row0 + t0) * stride + s;
+    for (int t = 0; t < valid; ++t) dst[(size_t)t * stride] = src[(size_t)t * ustride];
+    if (g != 0) return;
+    const int end = ck.n0 + ck.len;  // analysis blocks that end inside this chunk
+    for (int b = ck.n0 / a.block_samples; b < a.n_rows; ++b) {
+        const int block_end = (b + 1) * a.block_samples < a.n_samples ? (b + 1) * a.block_samples : a.n_samples;
+        if (block_end > end) break;
+        if (block_end > ck.n0) a.rows[(size_t)b * stride + s] = a.in_rows[(size_t)b * ustride + u];
+    }
+    if (end >= a.n_samples) {
+        a.accum[s].sum_in = a.in_accum[u].sum_in;
+        a.accum[s].peak_in = a.in_accum[u].peak_in;
+    }
+}
+
 // ---- EQ slice: sections [first, first + K) -------------------------------------------------------------------
 template <int K>
 AF_HD void body_eq(const BatchArgs& a, const ChunkArgs& ck, int s, int first) {

@@ -62,7 +62,7 @@ WORKLOADS = {
 STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20, "output": 4,
                "comp_r1": 36, "comp_m2": 48, "comp_r3": 32, "comp_m4": 32, "comp_r5": 16, "comp_m6": 16,
                "lim_m": 12, "lim_r": 16, "tp_fir_in": 8, "tp_r": 12, "tp_fir_out": 4,
-               "de_ra": 36, "de_mb": 88, "de_rc": 64}
+               "de_ra": 36, "de_mb": 88, "de_rc": 64, "comp_r7": 16}
 
 
 # DRAM traffic per launch (MB, dram__bytes_read.sum + dram__bytes_write.sum) of each stage kernel from the committed
@@ -292,9 +292,13 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     metrics = sweep.collect()
 
     # ---- per-stage timing (serialised pass) + issue peaks --------------------------------------------------
-    stages, fp64_peak, fp32_peak = [], None, None
+    stages, wave, fp64_peak, fp32_peak = [], [], None, None
     if rank == 0 and not args.no_profile:
         stages = sweep.profile_stages(max_chunks=64)
+        try:  # the same batch in the live wavefront: per-stage duration under contention and the pipeline period
+            wave = sweep.profile_wavefront(first_chunk=64, n_chunks=64)
+        except ValueError:
+            wave = []
         fp64_peak = sim.issue_peak(0)
         fp32_peak = sim.issue_peak(1)
     sweep.release()
@@ -376,6 +380,19 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                         "note": "the chain is FP64 / FP32 issue bound, not HBM bound (SURVEY 8(d)); see `issue` and profiles/",
                         "issue": {"fp64_peak_ginstr_s": fp64_peak, "fp32_fma_peak_ginstr_s": fp32_peak,
                                   "unit": "1e9 warp-lane instructions/s, measured in this run"}}
+        wavefront = None
+        if wave:
+            periods = sorted(p for _, _, p in wave)
+            period_ms = periods[len(periods) // 2]
+            wavefront = {"period_ms": period_ms, "chunks_timed": 64,
+                         "stages": [{"stage": n, "busy_ms": b} for n, b, _ in wave],
+                         "note": "live wavefront (every stage on its own stream): busy_ms = launch eligible -> kernel done, "
+                                 "under contention with the other stages; period_ms = time between consecutive chunks"}
+            if stages and (args.workload == "c2" and n_pairs == 4096 and int(os.environ.get("AFSIM_CHUNK", "1024")) == 1024):
+                sm_clock = (clocks.summary()["sm_mhz"] or 1965.0) * 1e6
+                instr = sum(NCU_WARP_INSTR.get(n, 0.0) for n, _, _ in wave)
+                wavefront["warp_instr_per_chunk"] = instr
+                wavefront["issue_frac"] = instr / (period_ms * 1e-3) / (148 * 4 * sm_clock)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -387,6 +404,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "clocks": clocks.summary(),
             "roofline": roofline,
             "stages": stage_table,
+            "wavefront": wavefront,
         }
         if WORKLOADS[args.workload]["kind"] == "headroom":
             line["decisions"] = {"safe_candidates": int(sum(workloads.is_headroom_safe(abi.metrics_to_dict(metrics[i]))

@@ -33,6 +33,7 @@ def lib() -> C.CDLL:
         L.hostsim_makeup_control.argtypes = [f32p, C.c_size_t, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_double,
                                              C.c_double, C.POINTER(abi.AfAutoMakeupSettings), C.c_int, C.c_int, C.c_int,
                                              f32p, f32p]
+        L.hostsim_eq_scan.argtypes = [f32p, C.c_size_t, C.c_double, C.POINTER(abi.AfBand), C.c_int, f32p]
         _lib = L
     return _lib
 
@@ -84,3 +85,15 @@ def makeup_control(audio, sample_rate, vad, noise_floor_db, noise_reliability, s
     if rc != abi.AFSIM_OK:
         raise HostsimError(lib().hostsim_last_error().decode())
     return traces, out
+
+
+def eq_scan(audio, sample_rate, bands, log2_len=6):
+    """The time-parallel EQ render (afsim_eqscan.h) walked on the host -> audio."""
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    out = np.zeros_like(audio)
+    f32p = C.POINTER(C.c_float)
+    rc = lib().hostsim_eq_scan(audio.ctypes.data_as(f32p), audio.size, float(sample_rate), bands, int(log2_len),
+                               out.ctypes.data_as(f32p))
+    if rc != abi.AFSIM_OK:
+        raise HostsimError(lib().hostsim_last_error().decode())
+    return out

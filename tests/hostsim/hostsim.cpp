@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../audio_forge_b200/csrc/afsim_plan.h"
+#include "../../audio_forge_b200/csrc/afsim_eqscan.h"
 #include "../../audio_forge_b200/csrc/afsim_render.h"
 
 using namespace afsim;
@@ -226,6 +227,46 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     a.de_tab = de_tab.data();
     a.metrics = metrics.data();
 
+    // shared input stage (split bit 4): one render per distinct passage + fan-out, as build_sweep does for sweeps
+    BatchArgs ua{};
+    std::vector<uint32_t> uidx(S_pad, 0), ucand;
+    std::vector<uint64_t> usrc;
+    std::vector<float> ubuf, urows;
+    std::vector<double> ustate;
+    std::vector<StreamAccum> uaccum;
+    if (split & 16) {
+        for (int s = 0; s < S; ++s) {
+            size_t u = 0;
+            while (u < usrc.size() && usrc[u] != src_off[s]) ++u;
+            if (u == usrc.size()) {
+                usrc.push_back(src_off[s]);
+                ucand.push_back(cand[s]);
+            }
+            uidx[s] = static_cast<uint32_t>(u);
+        }
+        const int U = static_cast<int>(usrc.size()), U_pad = (U + 31) / 32 * 32;
+        usrc.resize(U_pad, 0);
+        ucand.resize(U_pad, 0);
+        ubuf.assign(static_cast<size_t>(a.ring_rows) * U_pad, 0.0f);
+        urows.assign(static_cast<size_t>(std::max(a.n_rows, 1)) * U_pad, 0.0f);
+        ustate.assign(static_cast<size_t>(kStateInput) * U_pad, 0.0);
+        uaccum.resize(U_pad);
+        std::memset(uaccum.data(), 0, U_pad * sizeof(StreamAccum));
+        ua = a;
+        ua.n_streams = U;
+        ua.stride = U_pad;
+        ua.cand = ucand.data();
+        ua.src_off = usrc.data();
+        ua.buf_a = ubuf.data();
+        ua.rows = urows.data();
+        ua.accum = uaccum.data();
+        ua.st_input = ustate.data();
+        a.in_unique = uidx.data();
+        a.in_src = ubuf.data();
+        a.in_rows = urows.data();
+        a.in_accum = uaccum.data();
+        a.in_stride = U_pad;
+    }
     if (a.structure & ST_DEESSER)
         for (int s = 0; s < S; ++s) body_expand_deesser(a, s);
     std::vector<unsigned char> staging_bytes(std::max(kStagingBytesPerLane, kDeRcStagingBytesPerLane) + 64);
@@ -252,11 +293,22 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         ck.n0 = c * chunk;
         ck.len = std::min(chunk, T - ck.n0);
         ck.row0 = (c % slots) * chunk;
-        for (int s = 0; s < S; ++s) {
-            if (input_uses_cleanup(a))
-                body_input_cleanup(a, ck, s);
-            else
-                body_input(a, ck, s);
+        if (split & 16) {
+            for (int u = 0; u < ua.n_streams; ++u) {
+                if (input_uses_cleanup(ua))
+                    body_input_cleanup(ua, ck, u);
+                else
+                    body_input(ua, ck, u);
+            }
+            for (int g = (ck.len + kFanoutGroup - 1) / kFanoutGroup; g >= 0; --g)
+                for (int s = 0; s < S; ++s) body_input_fanout(a, ck, s, g);
+        } else {
+            for (int s = 0; s < S; ++s) {
+                if (input_uses_cleanup(a))
+                    body_input_cleanup(a, ck, s);
+                else
+                    body_input(a, ck, s);
+            }
         }
         if (a.structure & ST_EQ_BEFORE_DEESSER) {
             run_eq(ck);
@@ -339,5 +391,78 @@ int hostsim_plan(const AfBand* bands, const AfChainSettings* settings, double fs
     return AFSIM_OK;
 }
 size_t hostsim_candidate_params_size() { return sizeof(CandidateParams); }
+
+// The time-parallel EQ render of one passage (afsim_eqscan.h) walked on the host with the kernel's structure:
+// transposed segments, zero-state local pass, the 1024-thread block scan (per-thread composites, Kogge-Stone inside
+// each 32-lane group, group totals scanned the same way), apply pass fused with the next section's local pass.
+int hostsim_eq_scan(const float* audio, size_t n, double fs, const AfBand* bands, int log2_len, float* out) {
+    g_error.clear();
+    CandidatePlan plan;
+    const int rc = plan_eq_only(bands, fs, &plan, &g_error);
+    if (rc != AFSIM_OK) return rc;
+    if (n == 0) return AFSIM_OK;
+    const int n_sections = static_cast<int>(plan.params.n_sections);
+    if (n_sections == 0) {
+        std::memcpy(out, audio, n * sizeof(float));
+        return AFSIM_OK;
+    }
+    const size_t len = size_t(1) << log2_len, n_seg = (n + len - 1) / len;
+    std::vector<float> xt(n_seg * len, 0.0f);
+    for (size_t i = 0; i < n; ++i) xt[(i % len) * n_seg + i / len] = audio[i];
+    std::vector<double> end(2 * n_seg), init(2 * n_seg);
+    const Bq first = bq_from(plan.params.eq[0]);
+    for (size_t k = 0; k < n_seg; ++k)
+        eqscan_segment<false, true>(xt.data(), n_seg, k, static_cast<int>(len), first, 0.0, 0.0, first, &end[k], &end[n_seg + k]);
+    constexpr int T = 1024;
+    for (int j = 0; j < n_sections; ++j) {
+        const Bq cur = bq_from(plan.params.eq[j]);
+        double m[4];
+        biquad_transition_power(cur, log2_len, m);
+        const size_t per = (n_seg + T - 1) / T;
+        std::vector<Affine2> incl(T), tot(T / 32);
+        for (int t = 0; t < T; ++t) {
+            Affine2 comp = affine_identity();
+            for (size_t k = t * per; k < std::min(n_seg, (t + 1) * per); ++k)
+                comp = affine_then(comp, Affine2{m[0], m[1], m[2], m[3], end[k], end[n_seg + k]});
+            incl[t] = comp;
+        }
+        auto group_scan = [](Affine2* v) {  // Kogge-Stone over 32 lanes
+            for (int d = 1; d < 32; d <<= 1) {
+                Affine2 prev[32];
+                for (int l = 0; l < 32; ++l) prev[l] = l >= d ? v[l - d] : v[l];
+                for (int l = d; l < 32; ++l) v[l] = affine_then(prev[l], v[l]);
+            }
+        };
+        for (int w = 0; w < T / 32; ++w) {
+            group_scan(&incl[w * 32]);
+            tot[w] = incl[w * 32 + 31];
+        }
+        group_scan(tot.data());
+        for (int t = 0; t < T; ++t) {
+            const int lane = t & 31, warp = t >> 5;
+            Affine2 excl = lane == 0 ? affine_identity() : incl[t - 1];
+            if (warp > 0) excl = affine_then(tot[warp - 1], excl);
+            double s1 = excl.v0, s2 = excl.v1;
+            for (size_t k = t * per; k < std::min(n_seg, (t + 1) * per); ++k) {
+                init[k] = s1;
+                init[n_seg + k] = s2;
+                const double t1 = m[0] * s1 + m[1] * s2 + end[k];
+                const double t2 = m[2] * s1 + m[3] * s2 + end[n_seg + k];
+                s1 = t1;
+                s2 = t2;
+            }
+        }
+        const bool last = j + 1 == n_sections;
+        const Bq nxt = last ? cur : bq_from(plan.params.eq[j + 1]);
+        for (size_t k = 0; k < n_seg; ++k) {
+            if (last)
+                eqscan_segment<true, false>(xt.data(), n_seg, k, static_cast<int>(len), cur, init[k], init[n_seg + k], nxt, nullptr, nullptr);
+            else
+                eqscan_segment<true, true>(xt.data(), n_seg, k, static_cast<int>(len), cur, init[k], init[n_seg + k], nxt, &end[k], &end[n_seg + k]);
+        }
+    }
+    for (size_t i = 0; i < n; ++i) out[i] = xt[(i % len) * n_seg + i / len];
+    return AFSIM_OK;
+}
 
 }  // extern "C"

@@ -206,3 +206,26 @@ def test_adaptive_input_cleanup_matches_oracle(sim, mode, path, monkeypatch):
     m1, a1 = sim.chain_render(x, FS, bands, settings, return_audio=True)
     assert audio_within_tolerance(a0, a1) <= 0.0
     assert metric_mismatches(m0, m1, tol_db=TOL_DB) == {}
+
+
+@pytest.mark.parametrize("input_stage", ["none", "strong"])
+def test_shared_input_stage_is_bit_identical(sim, input_stage, monkeypatch):
+    """Candidate sweeps (>= 64 streams, >= 4 per passage) render the input stage once per distinct passage and fan
+    it out: metrics and audio identical, bit for bit, to every stream rendering its own input stage."""
+    passages = [_hum_signal(24000 + 333, seed=s) for s in range(2)]
+    bands, overrides = CASES["legacy_eq"]
+    cand_list = [candidate(bands, **dict(overrides, input_stage=input_stage, compressor_threshold_db=-40.0 + 0.7 * i,
+                                         deesser_enabled=True)) for i in range(36)]
+    cands = candidate_array(cand_list)
+    monkeypatch.setenv("AFSIM_SHARED_INPUT", "2")  # off
+    m_own, a_own = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    monkeypatch.setenv("AFSIM_SHARED_INPUT", "1")
+    m_shared, a_shared = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    for i in range(len(cand_list) * 2):
+        d0, d1 = abi.metrics_to_dict(m_own[i]), abi.metrics_to_dict(m_shared[i])
+        d0.pop("candidate_runtime_ms"), d1.pop("candidate_runtime_ms")
+        assert d0 == d1, i
+        assert np.array_equal(a_own[i], a_shared[i]), i
+    m0, a0, _ = pyoracle.chain_render(passages[1], FS, cand_list[5].bands, cand_list[5].settings, return_audio=True)
+    assert audio_within_tolerance(a0, a_shared[5 * 2 + 1]) <= 0.0
+    assert metric_mismatches(m0, m_shared[5 * 2 + 1], tol_db=TOL_DB) == {}

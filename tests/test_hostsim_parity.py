@@ -49,6 +49,27 @@ def test_multi_stream_batch_and_ragged_tail():
         _check_pairs(passages, cand_list, pp, pc, got, audio)
 
 
+@pytest.mark.parametrize("input_stage", ["none", "dc_hp80", "strong"])
+def test_shared_input_stage_fan_out(input_stage):
+    """A candidate sweep renders its input stage once per distinct passage and copies it to the streams (split bit 4):
+    bit-identical to every stream rendering its own; chunk / block / passage length mutually ragged."""
+    n = 4 * 960 + 437
+    passages = [_hum_signal(n, seed=s) if input_stage == "strong" else speech_like(n, seed=s, level=0.7) for s in range(3)]
+    bands, overrides = CASES["legacy_eq"]
+    cand_list = [candidate(bands, **dict(overrides, input_stage=input_stage, compressor_threshold_db=thr, deesser_enabled=de))
+                 for thr in (-30.0, -18.0) for de in (False, False)]
+    cands = candidate_array(cand_list)
+    pp = np.array([p for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
+    pc = np.array([c for c in range(len(cand_list)) for p in range(3)], dtype=np.uint32)
+    for split, chunk in ((16, 1000), (16 | 7, 512)):
+        got, audio, rows = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=chunk, slots=2, split=split, want_audio=True,
+                                               want_rows=True)
+        _check_pairs(passages, cand_list, pp, pc, got, audio)
+        for i in range(pp.size):  # the input-level rows (row.0) came through the fan-out as well
+            _, _, r0 = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings, return_rows=True)
+            assert np.array_equal(r0, rows[:, :, i].T), i
+
+
 def _check_pairs(passages, cand_list, pp, pc, got, audio):
     for i in range(pp.size):
         m0, a0, _ = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings,
@@ -99,6 +120,7 @@ def test_other_sample_rates():
 
 def _hum_signal(n, hum_hz=50.37, level=0.1, seed=9):
     """Speech-like passage + mains hum and its second harmonic at -26 dBFS + a rumble burst."""
+    # (defined below the tests that use it; looked up at call time)
     x = speech_like(n, seed=seed, level=0.5).astype(np.float64)
     t = np.arange(n) / FS
     x += level * np.sin(2 * np.pi * hum_hz * t) + 0.5 * level * np.sin(2 * np.pi * 2 * hum_hz * t + 0.3)
