@@ -399,7 +399,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             int n_w = 0;
             if (split && (a.structure & ST_LIMITER)) n_w = 1;
             if ((split || auto_makeup) && (a.structure & ST_COMPRESSOR)) n_w = 4;
-            if (a.structure & ST_DEESSER) n_w = 7;  // the de-esser is always R/M split (afsim_deesser.h)
+            if (a.structure & ST_DEESSER) n_w = 13;  // the de-esser is always R/M split (afsim_deesser.h)
             for (int k = 0; k < n_w; ++k) AF_CUDA(h, sweep->mem.alloc(&a.w[k], ring_elems));
         }
         AF_CUDA(h, sweep->mem.alloc(&a.st_input, kStateInput * sp));
@@ -463,7 +463,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         };
         auto push_deesser = [&]() {
             if (!(a.structure & ST_DEESSER)) return;
-            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC}) batch->stages.push_back({SK_SPLIT, op});
+            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3}) batch->stages.push_back({SK_SPLIT, op});
         };
         // Shared input stage: when several streams of the batch read the same passage (a candidate sweep), the input
         // stage -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.
@@ -606,7 +606,7 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
             if (sd.kind == SK_INPUT_FANOUT) return h->stage_stream_map[i];
             const bool is_map = sd.kind == SK_SPLIT && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
                                                         sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT ||
-                                                        sd.arg == SP_DE_MB);
+                                                        sd.arg == SP_DE_MB || sd.arg == SP_DE_MC2);
             return is_map ? h->stage_stream_map[i] : h->stage_stream[i];
         };
         for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(stream_of(i), h->ev_fork, 0));

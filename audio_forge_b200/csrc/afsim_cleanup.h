@@ -126,9 +126,17 @@ AF_HD float smooth_toward_f32(float cur, float target, float attack, float relea
     return cur + c * (target - cur);
 }
 
-struct CleanupStage {
-    // hum analyser: 26 rotating phasors + accumulators
-    float cosp[2 * kHumBins], sinp[2 * kHumBins], iacc[2 * kHumBins], qacc[2 * kHumBins];
+// NB = 26: one thread owns all bins of its stream (the per-stream kernels and the host harness).
+// NB = 1: one WARP per stream, lane i owns bin i (the shared input stage of a candidate sweep renders a handful of
+// distinct passages, so its serial chain is the wavefront's critical path: spreading the 26 independent phasor
+// chains over the lanes cuts the instructions per sample from ~490 to ~130).  Everything that is not a bin is
+// computed redundantly -- and identically -- by every lane; the window decision gathers the bins with shuffles.
+template <int NB>
+struct CleanupStageT {
+    // hum analyser: rotating phasors + accumulators of this thread's bins [bin0, bin0 + NB)
+    float cosp[NB], sinp[NB], iacc[NB], qacc[NB];
+    int bin0;
+    float my_bin_cos, my_bin_sin;  // NB == 1: this lane's rotation (CleanupConst::bin_cos / bin_sin of bin0)
     float lowpass, low_env, slow_low_env, broadband_env, total_energy;
     float hum_line_hz, prev_phase, hum_strength, harmonic_strength, highpass_hz;
     uint32_t rumble_hold, hum_hold, windows_observed, window_pos, candidate_windows;
@@ -139,9 +147,12 @@ struct CleanupStage {
     uint32_t hp_fade_remaining;
     SmoothNotchF32 hum_notch, harmonic_notch;
 
-    AF_HD void init(const CleanupConst& k) {
+    AF_HD void init(const CleanupConst& k, int first_bin = 0) {
+        bin0 = first_bin;
+        my_bin_cos = k.bin_cos[first_bin];
+        my_bin_sin = k.bin_sin[first_bin];
 #pragma unroll
-        for (int i = 0; i < 2 * kHumBins; ++i) {
+        for (int i = 0; i < NB; ++i) {
             cosp[i] = 1.0f;
             sinp[i] = 0.0f;
             iacc[i] = qacc[i] = 0.0f;
@@ -161,12 +172,22 @@ struct CleanupStage {
 
     template <class IO>
     AF_HD void sync(IO& io) {
+        if (NB == 2 * kHumBins) {
 #pragma unroll
-        for (int i = 0; i < 2 * kHumBins; ++i) {
-            io.f32(cosp[i]);
-            io.f32(sinp[i]);
-            io.f32(iacc[i]);
-            io.f32(qacc[i]);
+            for (int i = 0; i < NB; ++i) {
+                io.f32(cosp[i]);
+                io.f32(sinp[i]);
+                io.f32(iacc[i]);
+                io.f32(qacc[i]);
+            }
+        } else {  // same table layout: bin b lives in slots 4b .. 4b+3
+            IO mine = io;
+            mine.p += (size_t)(4 * bin0) * io.stride;
+            mine.f32(cosp[0]);
+            mine.f32(sinp[0]);
+            mine.f32(iacc[0]);
+            mine.f32(qacc[0]);
+            io.p += (size_t)(4 * 2 * kHumBins) * io.stride;
         }
         io.f32(lowpass);
         io.f32(low_env);
@@ -209,10 +230,11 @@ struct CleanupStage {
         const float n = (float)(k.window_samples > 1 ? k.window_samples : 1);
         float primary[kHumBins], harmonic[kHumBins], phase[kHumBins];
         float best_f = 0.0f, best_primary = 0.0f, best_harm = 0.0f, best_score = 0.0f, best_phase = 0.0f;
+        float my_power[NB], my_phase[NB];
 #pragma unroll
-        for (int i = 0; i < 2 * kHumBins; ++i) {  // HumBin::power_phase_and_reset, routing.rs:90-109
-            const float power = (iacc[i] * iacc[i] + qacc[i] * qacc[i]) * (2.0f / (n * n));
-            const float ph = atan2f(qacc[i], iacc[i]);
+        for (int i = 0; i < NB; ++i) {  // HumBin::power_phase_and_reset, routing.rs:90-109
+            my_power[i] = (iacc[i] * iacc[i] + qacc[i] * qacc[i]) * (2.0f / (n * n));
+            my_phase[i] = atan2f(qacc[i], iacc[i]);
             iacc[i] = 0.0f;
             qacc[i] = 0.0f;
             const float norm = sqrtf(cosp[i] * cosp[i] + sinp[i] * sinp[i]);
@@ -220,12 +242,26 @@ struct CleanupStage {
                 cosp[i] /= norm;
                 sinp[i] /= norm;
             }
-            if (i < kHumBins) {
-                primary[i] = power;
-                phase[i] = ph;
-            } else {
-                harmonic[i - kHumBins] = power;
+        }
+        if (NB == 2 * kHumBins) {
+#pragma unroll
+            for (int i = 0; i < kHumBins; ++i) {
+                primary[i] = my_power[i % NB];
+                phase[i] = my_phase[i % NB];
+                harmonic[i] = my_power[(kHumBins + i) % NB];
             }
+        } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+            for (int i = 0; i < kHumBins; ++i) {  // every lane ends up with all 26 bins
+                primary[i] = __shfl_sync(0xffffffffu, my_power[0], i);
+                phase[i] = __shfl_sync(0xffffffffu, my_phase[0], i);
+                harmonic[i] = __shfl_sync(0xffffffffu, my_power[0], kHumBins + i);
+            }
+#else
+#pragma unroll
+            for (int i = 0; i < kHumBins; ++i) primary[i] = phase[i] = harmonic[i] = 0.0f;  // the lane form is device only
+#endif
         }
 #pragma unroll
         for (int i = 0; i < kHumBins; ++i) {
@@ -308,11 +344,12 @@ struct CleanupStage {
     AF_HD void analyze(float s, const CleanupConst& k, bool gentle) {
         total_energy += s * s;
 #pragma unroll
-        for (int i = 0; i < 2 * kHumBins; ++i) {  // HumBin::analyze, routing.rs:78-88
+        for (int i = 0; i < NB; ++i) {  // HumBin::analyze, routing.rs:78-88
+            const float bc = NB == 2 * kHumBins ? k.bin_cos[i] : my_bin_cos, bs = NB == 2 * kHumBins ? k.bin_sin[i] : my_bin_sin;
             iacc[i] += s * cosp[i];
             qacc[i] += s * sinp[i];
-            const float nc = cosp[i] * k.bin_cos[i] - sinp[i] * k.bin_sin[i];
-            const float ns = sinp[i] * k.bin_cos[i] + cosp[i] * k.bin_sin[i];
+            const float nc = cosp[i] * bc - sinp[i] * bs;
+            const float ns = sinp[i] * bc + cosp[i] * bs;
             cosp[i] = nc;
             sinp[i] = ns;
         }
@@ -385,5 +422,7 @@ struct CleanupStage {
         return (float)out;
     }
 };
+
+using CleanupStage = CleanupStageT<2 * kHumBins>;
 
 }  // namespace afsim

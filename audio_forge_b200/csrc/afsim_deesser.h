@@ -1,11 +1,12 @@
-// afsim_deesser.h -- the dynamic-EQ de-esser (rust-core/src/dsp/deesser.rs:405-547) cut into two serial
-// recurrence kernels and one map kernel:
+// afsim_deesser.h -- the dynamic-EQ de-esser (rust-core/src/dsp/deesser.rs:405-547) cut into three serial
+// recurrence kernels and two map kernels:
 //     R_a  detector biquads (3 bands x high-pass + low-pass), band / broadband envelopes
 //     M_b  levels in dB, voice level, narrowness, dominance, confidence targets   (4 log10, 3 sqrt, ~20 divisions)
-//     R_c  confidence / baseline / reduction smoothing, the target logic, the dynamic-EQ gain hysteresis with
-//          its coefficient rebuilds, and the three time-varying peaking biquads
-// The map holds most of the arithmetic and runs one thread per (stream, 2 samples); the serial kernels keep
-// ~16 / ~37 state values per stream in registers.  Per sample the operations and their order are those of
+//     R_c1 confidence / baseline / reduction smoothing, the target logic, the dynamic-EQ gain hysteresis
+//     M_c2 the peaking-filter coefficients of the samples whose gain moved (exp10 + six divisions per band)
+//     R_c3 the three time-varying peaking biquads
+// The maps hold most of the arithmetic and run one thread per (stream, 2 samples); the serial kernels keep
+// ~16 / ~13 / ~24 state values per stream in registers.  Per sample the operations and their order are those of
 // DeEsser::process_sample, so the result is the same as a fused walk (tests/hostsim: bit-exact vs the oracle).
 //
 // Hand-off rings (f64, [row][stream]): R_a writes w0 = broadband envelope, w1..w3 = band envelopes; M_b
@@ -17,7 +18,7 @@ namespace afsim {
 
 constexpr int kDeMapGroup = 2;    // samples per thread of the de-esser map
 constexpr int kDeRcDepth = 3;     // staging depth of R_c (8 staged streams: keep the shared-memory footprint small)
-constexpr int kStateDeDetect = 16;  // state slots of R_a; R_c's follow
+constexpr int kStateDeDetect = 16;  // state slots of R_a; R_c1's and R_c3's follow
 
 // ---- R_a ------------------------------------------------------------------------------------------------------
 struct DeEsserDetect {
@@ -163,9 +164,10 @@ AF_HD void deesser_levels(double* w0, double* w1, double* w2, double* w3, double
         const double voice_db = lin_to_db(voice_level, 1e-10);
         const double narrowness = total_env > 1e-10 ? max_env / total_env : 0.0;
         double conf[3];
+        const AfDivisor by_max = af_divisor(max_env);  // one refined reciprocal for the three dominance quotients
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const double dominance = max_env > 1e-10 ? sqrt(env[b] / max_env) : 0.0;
+            const double dominance = max_env > 1e-10 ? sqrt(af_div(env[b], by_max)) : 0.0;
             conf[b] = clampd(de_confidence_target(level_db[b], voice_db, narrowness) * dominance, 0.0, 1.0);
         }
         voice[u] = voice_db;
@@ -185,14 +187,23 @@ AF_HD void deesser_levels(double* w0, double* w1, double* w2, double* w3, double
     store_tile(w6, stride, valid, c2);
 }
 
-// ---- R_c ------------------------------------------------------------------------------------------------------
-// The constants R_c reads every sample, loaded once per chunk: read through the table on every use they would be
-// ~25 dependent memory accesses per sample (the compiler cannot hoist them past the in-place stores).
+// ---- R_c1 / M_c2 / R_c3 -------------------------------------------------------------------------------------------
+// The second half of DeEsser::process_sample (deesser.rs:452-547) in three kernels:
+//   R_c1  serial, light: confidence / baseline smoothing, the reduction targets and their cap, reduction smoothing
+//         and the 0.001 dB gain hysteresis of set_gain_db_immediate.  Per sample it hands on a 3-bit mask of the
+//         bands whose peaking filter is rebuilt (w0) and the gain they are rebuilt with (w4..w6).
+//   M_c2  map: the rebuilt coefficients (exp10, six divisions per band) -- the expensive part, a pure function of
+//         the gain -- for the flagged (sample, band) pairs: b0 b1 b2 a2 (a1 == b1) into w1..w3 / w4..w6 / w7..w12.
+//   R_c3  serial, light: the three time-varying biquads (with the configuration crossfade of the first F samples
+//         and its cancellation by the first rebuild), in place on the signal.
+// Cutting the serial chain in two and moving the rebuilds to a map takes the de-esser off the wavefront's critical
+// path: R_c was ~515 instructions per sample on one warp per 32 streams.
+
+// The constants R_c1 reads every sample, loaded once per chunk.
 struct DeApplyConst {
     double det_attack, det_release, max_red, attack, release;
     double base_fall, base_rise, base_inactive, conf_floor, trigger, slope, cap;      // auto mode
     double threshold, ratio_thr, ratio_factor, manual_cap;                            // manual mode
-    double dyn_cos[3], dyn_alpha[3];
     AF_HD void load(const DeConst& k) {
         det_attack = k(DE_DET_ATTACK);
         det_release = k(DE_DET_RELEASE);
@@ -210,30 +221,19 @@ struct DeApplyConst {
         ratio_thr = k(DE_RATIO_THR);
         ratio_factor = k(DE_RATIO_FACTOR);
         manual_cap = k(DE_MANUAL_CAP);
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            dyn_cos[b] = k(DE_DYN_COS + b);
-            dyn_alpha[b] = k(DE_DYN_ALPHA + b);
-        }
     }
 };
 
-struct DeEsserApply {
+constexpr int kStateDeTargets = 16;  // state slots of R_c1 (after R_a's); R_c3's follow
+
+struct DeEsserTargets {  // R_c1
     double conf[3], base[3], red[3], built_gain[3];
-    Bq dyn[3];        // live dynamic-EQ coefficients
-    double yz[3][2];  // dynamic-EQ state
     double current;
-    bool cancel[3];   // set_gain_db_immediate cancelled the configuration crossfade
     bool auto_mode;
 
     AF_HD void init(const CandidateParams& p) {
 #pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            conf[b] = base[b] = red[b] = built_gain[b] = 0.0;
-            dyn[b] = bq_from(p.de_dyn0[b]);
-            yz[b][0] = yz[b][1] = 0.0;
-            cancel[b] = false;
-        }
+        for (int b = 0; b < 3; ++b) conf[b] = base[b] = red[b] = built_gain[b] = 0.0;
         current = 0.0;
         auto_mode = (p.flags & LF_DE_AUTO) != 0;
     }
@@ -245,32 +245,19 @@ struct DeEsserApply {
             io.f64(base[b]);
             io.f64(red[b]);
             io.f64(built_gain[b]);
-            io.f64(dyn[b].b0);
-            io.f64(dyn[b].b1);
-            io.f64(dyn[b].b2);
-            io.f64(dyn[b].a1);
-            io.f64(dyn[b].a2);
-            io.f64(yz[b][0]);
-            io.f64(yz[b][1]);
-            io.flag(cancel[b]);
         }
         io.f64(current);
     }
 
-    // One sample of the second half of DeEsser::process_sample (deesser.rs:452-547).
-    // conf_div: prepared divisor 1 - conf_lo of norm_range(conf, conf_lo, 1.0) (conf_lo = the mode's confidence floor)
-    template <bool HEAD>
-    AF_HD float sample(float input, double voice_db, const double (&level_db)[3], const double (&conf_target)[3], int n,
-                       int fade_total, const DeApplyConst& k, const CandidateParams* p, double (*pyz)[2], double conf_lo,
-                       const AfDivisor& conf_div) {
-        const double det_attack = k.det_attack, det_release = k.det_release;
-        const double max_red = k.max_red;
+    // One sample: returns the rebuild mask, gains[b] = the new gain of a flagged band.
+    AF_HD unsigned sample(double voice_db, const double (&level_db)[3], const double (&conf_target)[3], const DeApplyConst& k,
+                          double conf_lo, const AfDivisor& conf_div, double (&gains)[3]) {
         double target[3];
         double target_sum = 0.0;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             const double ratio_db = fmax(level_db[b] - voice_db, 0.0);
-            conf[b] = smooth_ar(conf[b], conf_target[b], det_attack, det_release);
+            conf[b] = smooth_ar(conf[b], conf_target[b], k.det_attack, k.det_release);
             double tr = 0.0;
             if (auto_mode) {
                 const bool voice_active = voice_db > -55.0 || level_db[b] > -55.0;
@@ -281,7 +268,7 @@ struct DeEsserApply {
                 } else {
                     base[b] *= k.base_inactive;
                 }
-                const double conf_gain = clampd(af_div(conf[b] - conf_lo, conf_div), 0.0, 1.0);
+                const double conf_gain = clampd(af_div(conf[b] - conf_lo, conf_div), 0.0, 1.0);  // norm_range(conf, floor, 1)
                 const double over_db = fmax(ratio_db - base[b] - k.trigger, 0.0);
                 tr = clampd(over_db * k.slope * conf_gain, 0.0, k.cap);
             } else if (level_db[b] > k.threshold) {
@@ -296,74 +283,188 @@ struct DeEsserApply {
             target[b] = tr;
             target_sum += tr;
         }
-        if (target_sum > max_red && target_sum > 0.0) {
-            const double scale = max_red / target_sum;
+        if (target_sum > k.max_red && target_sum > 0.0) {
+            const double scale = k.max_red / target_sum;
 #pragma unroll
             for (int b = 0; b < 3; ++b) target[b] *= scale;
         }
-        const double attack = k.attack, release = k.release;
-        float processed = input;
+        unsigned mask = 0;
         double total_red = 0.0;
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            red[b] = smooth_ar(red[b], target[b], attack, release);
+            red[b] = smooth_ar(red[b], target[b], k.attack, k.release);
             total_red += red[b];
             const double dyn_gain = -red[b];
-            if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate: cancels any fade, keeps z1/z2
+            gains[b] = dyn_gain;
+            if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate rebuilds the filter
                 built_gain[b] = dyn_gain;
-                dyn[b] = design_peaking(k.dyn_cos[b], k.dyn_alpha[b], dyn_gain);
-                cancel[b] = true;
+                mask |= 1u << b;
             }
-            double y;
-            if (HEAD && n < fade_total && !cancel[b]) {
-                const Bq pend = bq_from(p->de_dyn1[b]);
-                y = bq_step_fading((double)processed, dyn[b], pend, yz[b][0], yz[b][1], pyz[b][0], pyz[b][1], n, fade_total);
-                if (n + 1 == fade_total) {
-                    dyn[b] = pend;
-                    yz[b][0] = pyz[b][0];
-                    yz[b][1] = pyz[b][1];
-                }
-            } else {
-                y = bq_step((double)processed, dyn[b], yz[b][0], yz[b][1]);
-            }
-            processed = (float)y;
         }
-        current = fmin(total_red, max_red);
-        return processed;
+        current = fmin(total_red, k.max_red);
+        return mask;
     }
 
-    // x: chunk column (in place); w[0..6]: ring columns at chunk start (voice dB, 3 level dB, 3 confidence targets)
-    AF_HD void run(float* x, double* const (&w)[7], size_t stride, int n0, int len, int fade_total, const DeConst& table,
-                   const CandidateParams* p, BlockClock clk, float* rows_de, Staging stg) {
+    // w[0..6]: ring columns at chunk start (voice dB, 3 level dB, 3 confidence targets); on return w[0] holds the
+    // rebuild masks and w[4..6] the gains
+    AF_HD void run(double* const (&w)[7], size_t stride, int n0, int len, const DeConst& table, BlockClock clk, float* rows_de,
+                   Staging stg) {
         constexpr int U = kGroup;
         DeApplyConst k;
         k.load(table);
         const double conf_lo = auto_mode ? k.conf_floor : 0.22;
         const AfDivisor conf_div = af_divisor(1.0 - conf_lo);
-        int t_head = 0;
-        if (n0 < fade_total) {
-            double pyz[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-            for (; t_head < len && n0 + t_head < fade_total; ++t_head) {
-                const size_t o = (size_t)t_head * stride;
-                const double lv[3] = {w[1][o], w[2][o], w[3][o]};
-                const double ct[3] = {w[4][o], w[5][o], w[6][o]};
-                x[o] = sample<true>(x[o], w[0][o], lv, ct, n0 + t_head, fade_total, k, p, pyz, conf_lo, conf_div);
-                if (clk.at_end(n0 + t_head)) {
-                    rows_de[(size_t)clk.blk * stride] = (float)current;
-                    clk.advance();
-                }
-            }
-        }
-        float* xs = x + (size_t)t_head * stride;
-        const double* ws[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) ws[i] = w[i] + (size_t)t_head * stride;
-        const int m = len - t_head;
-        const int nb = n0 + t_head;
-        const StageRing<float, kDeRcDepth> sx = stg.ring<float, kDeRcDepth>();
         StageRing<double, kDeRcDepth> sw[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) sw[i] = stg.ring<double, kDeRcDepth>();
+        auto issue = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || t0 + u < len) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, w[i] + o);
+                }
+            }
+        };
+        // (a phased tile -- recurrences / feed-forward targets / recurrences -- was measured slower: it spills)
+        auto body = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+            const int valid = FULL ? U : len - t0;
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) {
+                if (FULL || u < valid) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+                    const double voice_db = sw[0].get(kt, u, w[0] + o);
+                    const double lv[3] = {sw[1].get(kt, u, w[1] + o), sw[2].get(kt, u, w[2] + o), sw[3].get(kt, u, w[3] + o)};
+                    const double ct[3] = {sw[4].get(kt, u, w[4] + o), sw[5].get(kt, u, w[5] + o), sw[6].get(kt, u, w[6] + o)};
+                    double gains[3];
+                    const unsigned mask = sample(voice_db, lv, ct, k, conf_lo, conf_div, gains);
+                    w[0][o] = (double)mask;
+                    w[4][o] = gains[0];
+                    w[5][o] = gains[1];
+                    w[6][o] = gains[2];
+                    if (clk.at_end(n0 + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
+                        rows_de[(size_t)clk.blk * stride] = (float)current;
+                        clk.advance();
+                    }
+                }
+            }
+        };
+        pipelined_tiles_depth<kDeRcDepth>(len, issue, body);
+    }
+};
+constexpr size_t kDeRc1StagingBytesPerLane = (size_t)kDeRcDepth * 8 * (7 * 8);
+
+// ---- M_c2: coefficients of the rebuilt filters ------------------------------------------------------------------------
+// coefficient rings of band b: w[kDeCoefRing[b][i]], i = b0 b1 b2 a2
+AF_HD int de_coef_ring(int band, int i) { return band == 0 ? (i < 3 ? 1 + i : 7) : (band == 1 ? 8 + i : (i < 1 ? 12 : 3 + i)); }
+// band 0: w1 w2 w3 w7 ; band 1: w8 w9 w10 w11 ; band 2: w12 w4 w5 w6 (the gains in w4..w6 are read before they are overwritten)
+constexpr int kDeRebuildGroup = 2;
+AF_HD void deesser_rebuild(double* const (&w)[13], size_t stride, int valid, const DeConst& k) {
+    constexpr int G = kDeRebuildGroup;
+    double mask[G], g0[G], g1[G], g2[G];
+    load_tile((const double*)w[0], stride, valid, mask);
+    load_tile((const double*)w[4], stride, valid, g0);
+    load_tile((const double*)w[5], stride, valid, g1);
+    load_tile((const double*)w[6], stride, valid, g2);
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        if (u >= valid) continue;
+        const unsigned m = (unsigned)mask[u];
+        const double gains[3] = {g0[u], g1[u], g2[u]};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (m & (1u << b)) {
+                const Bq c = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), gains[b]);
+                w[de_coef_ring(b, 0)][(size_t)u * stride] = c.b0;
+                w[de_coef_ring(b, 1)][(size_t)u * stride] = c.b1;
+                w[de_coef_ring(b, 2)][(size_t)u * stride] = c.b2;
+                w[de_coef_ring(b, 3)][(size_t)u * stride] = c.a2;
+            }
+        }
+    }
+}
+
+// ---- R_c3: the time-varying dynamic EQ ------------------------------------------------------------------------------------
+constexpr int kDeRc3Depth = 3;
+struct DeEsserFilter {
+    Bq dyn[3];        // live dynamic-EQ coefficients
+    double yz[3][2];  // dynamic-EQ state
+    bool cancel[3];   // set_gain_db_immediate cancelled the configuration crossfade
+
+    AF_HD void init(const CandidateParams& p) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            dyn[b] = bq_from(p.de_dyn0[b]);
+            yz[b][0] = yz[b][1] = 0.0;
+            cancel[b] = false;
+        }
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            io.f64(dyn[b].b0);
+            io.f64(dyn[b].b1);
+            io.f64(dyn[b].b2);
+            io.f64(dyn[b].a1);
+            io.f64(dyn[b].a2);
+            io.f64(yz[b][0]);
+            io.f64(yz[b][1]);
+            io.flag(cancel[b]);
+        }
+    }
+
+    AF_HD void run(float* x, double* const (&w)[13], size_t stride, int n0, int len, int fade_total, const CandidateParams* p,
+                   Staging stg) {
+        constexpr int U = kGroup;
+        int t_head = 0;
+        if (n0 < fade_total) {  // head of the render: the configuration crossfade (deesser.rs:312-327), sample by sample
+            double pyz[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            for (; t_head < len && n0 + t_head < fade_total; ++t_head) {
+                const int n = n0 + t_head;
+                const size_t o = (size_t)t_head * stride;
+                const unsigned mask = (unsigned)w[0][o];
+                float processed = x[o];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (mask & (1u << b)) {
+                        dyn[b].b0 = w[de_coef_ring(b, 0)][o];
+                        dyn[b].b1 = dyn[b].a1 = w[de_coef_ring(b, 1)][o];
+                        dyn[b].b2 = w[de_coef_ring(b, 2)][o];
+                        dyn[b].a2 = w[de_coef_ring(b, 3)][o];
+                        cancel[b] = true;
+                    }
+                    double y;
+                    if (!cancel[b]) {
+                        const Bq pend = bq_from(p->de_dyn1[b]);
+                        y = bq_step_fading((double)processed, dyn[b], pend, yz[b][0], yz[b][1], pyz[b][0], pyz[b][1], n, fade_total);
+                        if (n + 1 == fade_total) {
+                            dyn[b] = pend;
+                            yz[b][0] = pyz[b][0];
+                            yz[b][1] = pyz[b][1];
+                        }
+                    } else {
+                        y = bq_step((double)processed, dyn[b], yz[b][0], yz[b][1]);
+                    }
+                    processed = (float)y;
+                }
+                x[o] = processed;
+            }
+        }
+        float* xs = x + (size_t)t_head * stride;
+        const double* ws[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) ws[i] = w[i] + (size_t)t_head * stride;
+        const int m = len - t_head;
+        const StageRing<float, kDeRc3Depth> sx = stg.ring<float, kDeRc3Depth>();
+        StageRing<double, kDeRc3Depth> sw[13];
+#pragma unroll
+        for (int i = 0; i < 13; ++i) sw[i] = stg.ring<double, kDeRc3Depth>();
         auto issue = [&](int kt, auto full) {
             constexpr bool FULL = decltype(full)::value;
             const int t0 = kt * U;
@@ -373,7 +474,7 @@ struct DeEsserApply {
                     const size_t o = (size_t)(t0 + u) * stride;
                     sx.fetch(kt, u, xs + o);
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, ws[i] + o);
+                    for (int i = 0; i < 13; ++i) sw[i].fetch(kt, u, ws[i] + o);
                 }
             }
         };
@@ -381,27 +482,33 @@ struct DeEsserApply {
             constexpr bool FULL = decltype(full)::value;
             const int t0 = kt * U;
             const int valid = FULL ? U : m - t0;
-            // the per-sample body (three bands side by side, each with its coefficient rebuild inline so that their
-            // exp10 / division chains overlap) is ~600 instructions: keep the walk rolled
-#pragma unroll 1
+            float y[U];
+#pragma unroll
             for (int u = 0; u < U; ++u) {
+                y[u] = 0.0f;
                 if (FULL || u < valid) {
                     const size_t o = (size_t)(t0 + u) * stride;
-                    const float in = sx.get(kt, u, xs + o);
-                    const double voice_db = sw[0].get(kt, u, ws[0] + o);
-                    const double lv[3] = {sw[1].get(kt, u, ws[1] + o), sw[2].get(kt, u, ws[2] + o), sw[3].get(kt, u, ws[3] + o)};
-                    const double ct[3] = {sw[4].get(kt, u, ws[4] + o), sw[5].get(kt, u, ws[5] + o), sw[6].get(kt, u, ws[6] + o)};
-                    xs[o] = sample<false>(in, voice_db, lv, ct, nb + t0 + u, fade_total, k, p, nullptr, conf_lo, conf_div);
-                    if (clk.at_end(nb + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
-                        rows_de[(size_t)clk.blk * stride] = (float)current;
-                        clk.advance();
+                    const unsigned mask = (unsigned)sw[0].get(kt, u, ws[0] + o);
+                    float processed = sx.get(kt, u, xs + o);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        if (mask & (1u << b)) {
+                            dyn[b].b0 = sw[de_coef_ring(b, 0)].get(kt, u, ws[de_coef_ring(b, 0)] + o);
+                            dyn[b].b1 = dyn[b].a1 = sw[de_coef_ring(b, 1)].get(kt, u, ws[de_coef_ring(b, 1)] + o);
+                            dyn[b].b2 = sw[de_coef_ring(b, 2)].get(kt, u, ws[de_coef_ring(b, 2)] + o);
+                            dyn[b].a2 = sw[de_coef_ring(b, 3)].get(kt, u, ws[de_coef_ring(b, 3)] + o);
+                            cancel[b] = true;
+                        }
+                        processed = (float)bq_step((double)processed, dyn[b], yz[b][0], yz[b][1]);
                     }
+                    y[u] = processed;
                 }
             }
+            store_tile(xs + (size_t)t0 * stride, stride, valid, y);
         };
-        pipelined_tiles_depth<kDeRcDepth>(m, issue, body);
+        pipelined_tiles_depth<kDeRc3Depth>(m, issue, body);
     }
 };
-constexpr size_t kDeRcStagingBytesPerLane = (size_t)kDeRcDepth * 8 * (4 + 7 * 8);
+constexpr size_t kDeRc3StagingBytesPerLane = (size_t)kDeRc3Depth * 8 * (4 + 13 * 8);
 
 }  // namespace afsim

@@ -44,6 +44,74 @@ __global__ void __launch_bounds__(128) k_input_cleanup(BatchArgs a, ChunkArgs ck
     body_input_cleanup(a, ck, s);
 }
 
+// The same stage with one WARP per stream (CleanupStageT<1>, afsim_cleanup.h): lane i owns hum bin i, everything
+// else is computed redundantly by every lane and lane 0 stores it.  Used for the shared input stage of candidate
+// sweeps (a handful of distinct passages), where this serial chain sets the wavefront's period.
+__global__ void __launch_bounds__(32) k_input_cleanup_warp(BatchArgs a, ChunkArgs ck) {
+    const int s = (int)blockIdx.x;
+    if (s >= a.n_streams) return;
+    const int lane = (int)threadIdx.x;
+    const size_t stride = (size_t)a.stride;
+    const CleanupConst& k = *a.cleanup;
+    const bool gentle = a.input_stage == AF_INPUT_CLEANUP_GENTLE;
+    InputStage st;
+    CleanupStageT<1> cl;
+    cl.init(k, lane < 2 * kHumBins ? lane : 2 * kHumBins - 1);
+    if (ck.n0 == 0) {
+        st.init();
+    } else {
+        StateIO<false> io{a.st_input + s, stride};
+        st.sync(io);
+        cl.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const Col out{a.buf_a + (size_t)ck.row0 * stride + s, stride};
+    const float* src = a.signals + a.src_off[s];
+    float* rows_in = a.rows + s;
+    for (int b0 = 0; b0 < ck.len; b0 += kInputBlock) {
+        const int blen = ck.len - b0 < kInputBlock ? ck.len - b0 : kInputBlock;
+        for (int t = 0; t < blen; ++t) {  // analyze_input on the raw (sanitised) block
+            float v = src[ck.n0 + b0 + t];
+            if (!af_finite(v)) v = 0.0f;
+            cl.analyze(v, k, gentle);
+        }
+        bool hum_detected;
+        cl.begin_block(k, gentle, &hum_detected);
+        for (int t = 0; t < blen; ++t) {
+            const int n = ck.n0 + b0 + t;
+            float in = src[n];
+            if (!af_finite(in)) in = 0.0f;
+            const float dc = in - st.x1 + 0.995f * st.y1;  // routing.rs:832-836
+            st.x1 = in;
+            st.y1 = dc;
+            float v = cl.process(dc, k);
+            if (!af_finite(v)) v = 0.0f;
+            const double sq = (double)v * (double)v;
+            st.sum_in += sq;
+            st.blk_in += sq;
+            st.peak_in = fmaxf(st.peak_in, fabsf(v));
+            if (lane == 0) out.set(b0 + t, v);
+            if (clk.at_end(n)) {
+                const float rms = (float)sqrt(st.blk_in / (double)clk.block_len(n));
+                if (lane == 0) rows_in[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                st.blk_in = 0.0;
+                clk.advance();
+            }
+        }
+    }
+    if (ck.n0 + ck.len >= a.n_samples) {
+        if (lane == 0) {
+            a.accum[s].sum_in = st.sum_in;
+            a.accum[s].peak_in = st.peak_in;
+        }
+    } else {
+        StateIO<true> io{a.st_input + s, stride};
+        st.sync(io);
+        cl.sync(io);
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) k_eq(BatchArgs a, ChunkArgs ck, int first) {
     AF_STREAM_INDEX();
@@ -97,10 +165,11 @@ AF_R_KERNEL(k_lim_r, body_lim_r)
 AF_R_KERNEL(k_tp_r, body_tp_r)
 AF_R_KERNEL(k_de_ra, body_de_ra)
 AF_R_KERNEL_DIRECT(k_de_ra_direct, body_de_ra, 1)
-// R_c keeps ~60 doubles of state and constants live and walks three bands side by side: the staged variant takes
-// every register it can get; the direct variant is capped at 128 (twice the warps hide the spills the cap costs).
+// de-esser R_c1 (targets, hysteresis) and R_c3 (time-varying biquads): staged and direct variants
 AF_R_KERNEL(k_de_rc, body_de_rc)
 AF_R_KERNEL_DIRECT(k_de_rc_direct, body_de_rc, 4)
+AF_R_KERNEL(k_de_rc3, body_de_rc3)
+AF_R_KERNEL_DIRECT(k_de_rc3_direct, body_de_rc3, 4)
 
 // ---- split path: maps, one thread per (stream, group of kGroup samples); blockIdx.y = group -------------------
 // A block is kMapWarps warps over the SAME 32 streams and consecutive sample groups, so the overlapping
@@ -120,6 +189,7 @@ AF_M_KERNEL(k_comp_m2, kCompMapGroup, body_comp_m2(a, ck, s, g))
 AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
 AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
 AF_M_KERNEL(k_de_mb, kDeMapGroup, body_de_mb(a, ck, s, g))
+AF_M_KERNEL(k_de_mc2, kDeRebuildGroup, body_de_mc2(a, ck, s, g))
 AF_M_KERNEL(k_lim_m, kLimGroup, body_lim_m(a, ck, s, g))
 AF_M_KERNEL(k_tp_fir_in, kGroup, body_tp_fir_in(a, ck, s, g, c_fir))
 AF_M_KERNEL(k_tp_fir_out, kGroup, body_tp_fir_out(a, ck, s, g, c_fir))
@@ -230,7 +300,7 @@ __global__ void __launch_bounds__(256) k_issue_peak(int kind, int iters, double*
 // Self-test of afsim_math.h: the custom routines against the CUDA math library / division on hashed arguments;
 // counts[k] = results that differ in any bit (k: 0 log10, 1 exp10, 2 x/20, 3 x/40, 4 x/3.75, 5 a/b through AfDivisor).
 __global__ void __launch_bounds__(256) k_selftest_math(unsigned long long n, unsigned long long* counts) {
-    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0};  // [4] also covers the de-esser's norm_range divisors
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         uint64_t z = 0x9e3779b97f4a7c15ull * (i + 1);
@@ -251,6 +321,10 @@ __global__ void __launch_bounds__(256) k_selftest_math(unsigned long long n, uns
         bad[2] += __double_as_longlong(af_div_const(dx, 20.0, 0.05)) != __double_as_longlong(dx / 20.0);
         bad[3] += __double_as_longlong(af_div_const(dx, 40.0, 0.025)) != __double_as_longlong(dx / 40.0);
         bad[4] += __double_as_longlong(af_div_const(dx, 3.75, 1.0 / 3.75)) != __double_as_longlong(dx / 3.75);
+        bad[4] += __double_as_longlong(af_div_const(dx, 10.0 - 1.5, 1.0 / (10.0 - 1.5))) != __double_as_longlong(dx / (10.0 - 1.5));
+        bad[4] += __double_as_longlong(af_div_const(dx, -24.0 - -62.0, 1.0 / (-24.0 - -62.0))) != __double_as_longlong(dx / (-24.0 - -62.0));
+        bad[4] += __double_as_longlong(af_div_const(dx, -34.0 - -58.0, 1.0 / (-34.0 - -58.0))) != __double_as_longlong(dx / (-34.0 - -58.0));
+        bad[4] += __double_as_longlong(af_div_const(dx, 0.68 - 0.34, 1.0 / (0.68 - 0.34))) != __double_as_longlong(dx / (0.68 - 0.34));
         // prepared divisor: biquad-sized operands, and arbitrary finite ones now and then
         const double num = wide ? dx : (v - 0.5) * 4.0;
         const double den = wide ? __longlong_as_double((long long)((z * 0x2545f4914f6cdd1dull) & 0xffefffffffffffffull)) : 0.25 + 3.0 * u;
@@ -284,7 +358,9 @@ cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int b = pick_block(a);
-    if (input_uses_cleanup(a))
+    if (input_uses_cleanup(a) && a.n_streams <= kWarpPerStreamMax && a.n_streams > 0)
+        k_input_cleanup_warp<<<(unsigned)a.n_streams, 32, 0, st>>>(a, ck);  // few streams: one warp each, a lane per hum bin
+    else if (input_uses_cleanup(a))
         k_input_cleanup<<<stream_grid(a, b), b, 0, st>>>(a, ck);
     else
         k_input<<<stream_grid(a, b), b, 0, st>>>(a, ck);
@@ -350,10 +426,11 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     // 128-thread blocks reading global memory directly when the batch itself fills the GPU
     const int rb = a.stage_inputs ? kRBlock : 128;
     const dim3 rgrid = stream_grid(a, rb);
-    const size_t rsm = a.stage_inputs ? (op == SP_DE_RC ? kDeRcStagingBytesPerLane : kStagingBytesPerLane) * kRBlock : 0;
+    const size_t lane_bytes = op == SP_DE_RC ? kDeRc1StagingBytesPerLane : (op == SP_DE_RC3 ? kDeRc3StagingBytesPerLane : kStagingBytesPerLane);
+    const size_t rsm = a.stage_inputs ? lane_bytes * kRBlock : 0;
     const int mb = 32 * kMapWarps;
     const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup
-                      : (op == SP_LIM_M ? kLimGroup : (op == SP_DE_MB ? kDeMapGroup : kGroup));
+                      : (op == SP_LIM_M ? kLimGroup : (op == SP_DE_MB ? kDeMapGroup : (op == SP_DE_MC2 ? kDeRebuildGroup : kGroup)));
     const int n_groups = (ck.len + group - 1) / group;
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
@@ -392,6 +469,20 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
                 k_de_rc_direct<<<rgrid, rb, 0, st>>>(a, ck);
             break;
         case SP_COMP_R7: k_comp_r7<<<rgrid, rb, rsm, st>>>(a, ck); break;
+        case SP_DE_MC2: k_de_mc2<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_DE_RC3:
+            if (a.stage_inputs) {
+                static bool attr_set = false;
+                if (!attr_set && rsm > 48 * 1024) {
+                    const cudaError_t err = cudaFuncSetAttribute(k_de_rc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+                    if (err != cudaSuccess) return err;
+                    attr_set = true;
+                }
+                k_de_rc3<<<rgrid, rb, rsm, st>>>(a, ck);
+            } else {
+                k_de_rc3_direct<<<rgrid, rb, 0, st>>>(a, ck);
+            }
+            break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -12,6 +12,7 @@ constexpr int kFinalizeThreads = 128;
 constexpr int kMapWarps = 4;  // warps per block of the map (M) kernels
 constexpr int kRBlock = 32;  // threads per block of the serial (R) kernels: one warp, so few-stream batches reach every SM
 constexpr size_t kFinalizeSmemLimit = 200 * 1024;
+constexpr int kWarpPerStreamMax = 2048;  // input cleanup: batches up to this many streams run one warp per stream
 
 cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);
 cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
@@ -26,7 +27,8 @@ enum SplitOp {
     SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6,
     SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT,
     SP_DE_RA, SP_DE_MB, SP_DE_RC,
-    SP_COMP_R7  // auto makeup (after M6)
+    SP_COMP_R7,  // auto makeup (after M6)
+    SP_DE_MC2, SP_DE_RC3  // de-esser: coefficient rebuild map, dynamic-EQ biquads (SP_DE_RC is R_c1)
 };
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);

@@ -149,7 +149,7 @@ struct BatchArgs {
     float* buf_b;                 // [ring_rows][S_pad] signal after the sample limiter
     float* lim_sfx;               // [lookahead + 1][S_pad] suffix maxima of the previous limiter block (fused limiter)
     // split (R/M) path, afsim_split.h: hand-off rings shared by the serial and the map kernels
-    double* w[7];                 // [ring_rows][S_pad] f64 each (compressor: 4, limiter: 1, de-esser: 7)
+    double* w[13];                // [ring_rows][S_pad] f64 each (compressor: 4, limiter: 1, de-esser: 13)
     float* buf_c;                 // [ring_rows][S_pad] true-peak limiter output
     float* buf_p;                 // [ring_rows][S_pad] input true peaks
     double* st_input;             // [kStateInput][S_pad]

@@ -411,7 +411,7 @@ AF_HD void body_comp_r7(const BatchArgs& a, const ChunkArgs& ck, int s, Staging 
     }
 }
 
-// ---- de-esser: R_a -> M_b -> R_c (afsim_deesser.h), used by every batch that has the stage ---------------------------
+// ---- de-esser: R_a -> M_b -> R_c1 -> M_c2 -> R_c3 (afsim_deesser.h), used by every batch that has the stage ---------------------------
 AF_HD void body_de_ra(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
     const CandidateParams& p = stream_params(a, s);
@@ -437,11 +437,10 @@ AF_HD void body_de_mb(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
                    col_at(a.w[3], a, ck, s, t0), col_at(a.w[4], a, ck, s, t0), col_at(a.w[5], a, ck, s, t0),
                    col_at(a.w[6], a, ck, s, t0), (size_t)a.stride, valid);
 }
-AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {  // R_c1
     const size_t stride = (size_t)a.stride;
-    const CandidateParams& p = stream_params(a, s);
-    DeEsserApply st;
-    st.init(p);
+    DeEsserTargets st;
+    st.init(stream_params(a, s));
     double* table = a.st_deesser + (size_t)kStateDeDetect * stride + s;
     if (ck.n0 != 0) {
         StateIO<false> io{table, stride};
@@ -452,8 +451,35 @@ AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging st
     const DeConst k{a.de_tab + s, stride};
     double* const w[7] = {col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s),
                           col_at(a.w[4], a, ck, s), col_at(a.w[5], a, ck, s), col_at(a.w[6], a, ck, s)};
-    st.run(col_at(a.buf_a, a, ck, s), w, stride, ck.n0, ck.len, a.fade_samples, k, &p, clk,
-           a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    st.run(w, stride, ck.n0, ck.len, k, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync(io);
+    }
+}
+AF_HD void body_de_mc2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid, kDeRebuildGroup)) return;
+    double* w[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) w[i] = col_at(a.w[i], a, ck, s, t0);
+    const DeConst k{a.de_tab + s, (size_t)a.stride};
+    deesser_rebuild(w, (size_t)a.stride, valid, k);
+}
+AF_HD void body_de_rc3(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    const CandidateParams& p = stream_params(a, s);
+    DeEsserFilter st;
+    st.init(p);
+    double* table = a.st_deesser + (size_t)(kStateDeDetect + kStateDeTargets) * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync(io);
+    }
+    double* w[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) w[i] = col_at(a.w[i], a, ck, s);
+    st.run(col_at(a.buf_a, a, ck, s), w, stride, ck.n0, ck.len, a.fade_samples, &p, stg);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync(io);

@@ -170,6 +170,8 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         st_comp(kStateCompressor * sp), st_lim(kStateLimiter * sp), st_tp(kStateTruePeak * sp), de_tab(DE_FIELDS * sp);
     std::vector<double> w0(static_cast<size_t>(a.ring_rows) * sp), w1(w0.size()), w2(w0.size()), w3(w0.size()), w4(w0.size()),
         w5(w0.size()), w6(w0.size());
+    std::vector<std::vector<double>> w_more(6, std::vector<double>(w0.size()));
+    for (int i = 0; i < 6; ++i) a.w[7 + i] = w_more[i].data();
     std::vector<float> buf_c(static_cast<size_t>(a.ring_rows) * sp), buf_p(buf_c.size());
     a.w[0] = w0.data();
     a.w[1] = w1.data();
@@ -269,13 +271,16 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     }
     if (a.structure & ST_DEESSER)
         for (int s = 0; s < S; ++s) body_expand_deesser(a, s);
-    std::vector<unsigned char> staging_bytes(std::max(kStagingBytesPerLane, kDeRcStagingBytesPerLane) + 64);
+    std::vector<unsigned char> staging_bytes(std::max(kStagingBytesPerLane, std::max(kDeRc1StagingBytesPerLane, kDeRc3StagingBytesPerLane)) + 64);
     auto run_deesser = [&](const ChunkArgs& ck) {
         const Staging st{(split & 8) ? nullptr : staging_bytes.data(), 1, 0, 0};  // split bit 3: direct (unstaged) loads
         for (int s = 0; s < S; ++s) body_de_ra(a, ck, s, st);
         for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
             for (int s = 0; s < S; ++s) body_de_mb(a, ck, s, g);
         for (int s = 0; s < S; ++s) body_de_rc(a, ck, s, st);
+        for (int g = (ck.len + kDeRebuildGroup - 1) / kDeRebuildGroup; g >= 0; --g)
+            for (int s = 0; s < S; ++s) body_de_mc2(a, ck, s, g);
+        for (int s = 0; s < S; ++s) body_de_rc3(a, ck, s, st);
     };
     const Staging stg{staging_bytes.data(), 1, 0, 0};
     const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
