@@ -62,7 +62,18 @@ __global__ void __launch_bounds__(kScanThreads) k_eqscan_scan(Bq c, int log2_len
     const size_t per = (n_seg + kScanThreads - 1) / kScanThreads;
     const size_t k0 = (size_t)t * per, k1 = k0 + per < n_seg ? k0 + per : n_seg;
     Affine2 comp = affine_identity();
-    for (size_t k = k0; k < k1; ++k) comp = affine_then(comp, Affine2{m[0], m[1], m[2], m[3], end[k], end[n_seg + k]});
+    constexpr int kPre = 8;  // this thread's end states, loaded together (per <= 8 up to 8192 segments)
+    double pe1[kPre], pe2[kPre];
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+        const size_t k = k0 + j;
+        pe1[j] = k < k1 ? end[k] : 0.0;
+        pe2[j] = k < k1 ? end[n_seg + k] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kPre; ++j)
+        if (k0 + j < k1) comp = affine_then(comp, Affine2{m[0], m[1], m[2], m[3], pe1[j], pe2[j]});
+    for (size_t k = k0 + kPre; k < k1; ++k) comp = affine_then(comp, Affine2{m[0], m[1], m[2], m[3], end[k], end[n_seg + k]});
     // inclusive Kogge-Stone scan inside the warp
     Affine2 incl = comp;
 #pragma unroll
@@ -87,7 +98,19 @@ __global__ void __launch_bounds__(kScanThreads) k_eqscan_scan(Bq c, int log2_len
     if (lane == 0) excl = affine_identity();
     if (warp > 0) excl = affine_then(warp_total[warp - 1], excl);
     double s1 = excl.v0, s2 = excl.v1;  // the passage starts from a zero state
-    for (size_t k = k0; k < k1; ++k) {
+#pragma unroll
+    for (int j = 0; j < kPre; ++j) {
+        const size_t k = k0 + j;
+        if (k < k1) {
+            init[k] = s1;
+            init[n_seg + k] = s2;
+            const double t1 = m[0] * s1 + m[1] * s2 + pe1[j];
+            const double t2 = m[2] * s1 + m[3] * s2 + pe2[j];
+            s1 = t1;
+            s2 = t2;
+        }
+    }
+    for (size_t k = k0 + kPre; k < k1; ++k) {
         init[k] = s1;
         init[n_seg + k] = s2;
         const double t1 = m[0] * s1 + m[1] * s2 + end[k];

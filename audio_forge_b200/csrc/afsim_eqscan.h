@@ -61,7 +61,23 @@ AF_HD void eqscan_segment(float* xt, size_t n_seg, size_t seg, int len, const Bq
                           double* e1, double* e2) {
     double z1 = s1, z2 = s2, n1 = 0.0, n2 = 0.0;
     float* p = xt + seg;
-    for (int i = 0; i < len; ++i) {
+    constexpr int U = 8;  // tiles of 8: the loads of a tile are issued together (segment lengths are multiples of 8)
+    int i = 0;
+    for (; i + U <= len; i += U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = p[(size_t)(i + u) * n_seg];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (APPLY) v[u] = (float)bq_step((double)v[u], cur, z1, z2);
+            if (LOCAL) (void)bq_step((double)v[u], nxt, n1, n2);
+        }
+        if (APPLY) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) p[(size_t)(i + u) * n_seg] = v[u];
+        }
+    }
+    for (; i < len; ++i) {
         float v = p[(size_t)i * n_seg];
         if (APPLY) {
             v = (float)bq_step((double)v, cur, z1, z2);
