@@ -1,5 +1,7 @@
-"""Is the chunk x stage wavefront host-launch bound?  Host wall time of sweep.launch() (issue only) next to the
-GPU time of the same launch, for the C2 shape, at the chunk size given by AFSIM_CHUNK."""
+"""Stage profile of a sweep in the live chunk x stage wavefront and in a serialised pass, plus the host wall time
+of sweep.launch() (issue only) next to the GPU time of the same launch.
+
+usage: profile_wavefront.py [candidates [seconds [c2|c3|c5 [passages]]]]   (AFSIM_CHUNK / AFSIM_SLOTS are honoured)"""
 import json
 import os
 import sys
