@@ -232,10 +232,11 @@ struct CompSplit : CompressorStage {
                 const double low_rms = sqrt(lsq[u]);
                 const double voiced_rms = fmax(sqrt(vsq[u]), 1e-8);
                 const double presence_rms = sqrt(psq[u]);
-                const double plosive = clampd(low_rms / voiced_rms, 0.0, 32.0);
+                const AfDivisor by_voiced = af_divisor(voiced_rms);  // one refined reciprocal for both ratios
+                const double plosive = clampd(af_div(low_rms, by_voiced), 0.0, 32.0);
                 const double amount = clampd(af_div_const(plosive - 1.25, 5.0 - 1.25, 1.0 / (5.0 - 1.25)), 0.0, 1.0);
                 const double penalty = 1.0 - amount * (1.0 - 0.35);
-                const double presence_ratio = clampd(presence_rms / voiced_rms, 0.0, 4.0);
+                const double presence_ratio = clampd(af_div(presence_rms, by_voiced), 0.0, 4.0);
                 const double pw = 1.0 + 0.18 * clampd(presence_ratio - 0.75, 0.0, 1.0);
                 wdb[u] = lin_to_db(clampd(penalty * pw, 0.35, 1.15), 1e-10);
             } else {
