@@ -683,6 +683,11 @@ int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle
         g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(err);
         return AFSIM_CUDA_ERROR;
     }
+    err = configure_kernels();
+    if (err != cudaSuccess) {
+        g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err);
+        return AFSIM_CUDA_ERROR;
+    }
     auto h = std::make_unique<AfsimHandle>();
     h->device = device_ordinal;
     if (cuda_stream) {

@@ -164,11 +164,12 @@ AF_HD void deesser_levels(double* w0, double* w1, double* w2, double* w3, double
         const double voice_db = lin_to_db(voice_level, 1e-10);
         const double narrowness = total_env > 1e-10 ? max_env / total_env : 0.0;
         double conf[3];
+        const DeConfShared shared = de_confidence_shared(voice_db, narrowness);
         const AfDivisor by_max = af_divisor(max_env);  // one refined reciprocal for the three dominance quotients
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             const double dominance = max_env > 1e-10 ? sqrt(af_div(env[b], by_max)) : 0.0;
-            conf[b] = clampd(de_confidence_target(level_db[b], voice_db, narrowness) * dominance, 0.0, 1.0);
+            conf[b] = clampd(de_confidence_target(level_db[b], voice_db, shared) * dominance, 0.0, 1.0);
         }
         voice[u] = voice_db;
         lv0[u] = level_db[0];

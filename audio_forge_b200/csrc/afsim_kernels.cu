@@ -472,13 +472,7 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         case SP_DE_MC2: k_de_mc2<<<mgrid, mb, 0, st>>>(a, ck); break;
         case SP_DE_RC3:
             if (a.stage_inputs) {
-                static bool attr_set = false;
-                if (!attr_set && rsm > 48 * 1024) {
-                    const cudaError_t err = cudaFuncSetAttribute(k_de_rc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-                    if (err != cudaSuccess) return err;
-                    attr_set = true;
-                }
-                k_de_rc3<<<rgrid, rb, rsm, st>>>(a, ck);
+                k_de_rc3<<<rgrid, rb, rsm, st>>>(a, ck);  // > 48 KB of staging: opted in by configure_kernels()
             } else {
                 k_de_rc3_direct<<<rgrid, rb, 0, st>>>(a, ck);
             }
@@ -486,6 +480,11 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+
+// Per-device kernel attributes (called by afsim_create with the device current).
+cudaError_t configure_kernels() {
+    return cudaFuncSetAttribute(k_de_rc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kDeRc3StagingBytesPerLane * kRBlock));
 }
 
 size_t finalize_workspace_bytes(int n_rows, int n_pad) { return finalize_workspace_floats(n_rows, n_pad) * sizeof(float); }

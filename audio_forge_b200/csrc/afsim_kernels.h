@@ -31,6 +31,7 @@ enum SplitOp {
     SP_DE_MC2, SP_DE_RC3  // de-esser: coefficient rebuild map, dynamic-EQ biquads (SP_DE_RC is R_c1)
 };
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
+cudaError_t configure_kernels();
 cudaError_t launch_finalize(const BatchArgs& a, cudaStream_t st);
 size_t finalize_workspace_bytes(int n_rows, int n_pad);
 cudaError_t launch_eq_response(const double* coeffs, const int* n_sections, const double* freqs, int n_freqs,

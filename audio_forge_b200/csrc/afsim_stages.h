@@ -353,17 +353,25 @@ AF_HD Bq design_peaking(double cs, double alpha, double gain_db) {  // dsp/biqua
 // norm_range(v, S, E) for literal bounds: the divisor E - S and its reciprocal are compile-time constants
 // (af_div_const: multiply + exact remainder + correction, bit-identical to the division; afsim_math.h)
 #define AF_NORM_RANGE_CONST(v, S, E) clampd(af_div_const((v) - (S), (E) - (S), 1.0 / ((E) - (S))), 0.0, 1.0)
-AF_HD double de_confidence_target(double level_db, double voice_db, double narrowness) {  // dsp/deesser.rs:171-219
+// The parts of the confidence target that do not depend on the band (evaluated once per sample by the map)
+struct DeConfShared {
+    double voice_conf, narrowness_gain;
+};
+AF_HD DeConfShared de_confidence_shared(double voice_db, double narrowness) {
+    DeConfShared r;
+    r.voice_conf = AF_NORM_RANGE_CONST(voice_db, -58.0, -34.0);
+    r.narrowness_gain = lerpd(0.35, 1.0, AF_NORM_RANGE_CONST(narrowness, 0.34, 0.68));
+    return r;
+}
+AF_HD double de_confidence_target(double level_db, double voice_db, const DeConfShared& sh) {  // dsp/deesser.rs:171-219
     const double ratio_db = fmax(level_db - voice_db, 0.0);
     const double ratio_conf = AF_NORM_RANGE_CONST(ratio_db, 1.5, 10.0);
     const double level_conf = AF_NORM_RANGE_CONST(level_db, -62.0, -24.0);
-    const double voice_conf = AF_NORM_RANGE_CONST(voice_db, -58.0, -34.0);
     const double narrow_support = (ratio_db > 6.0 && level_db > -45.0) ? 0.75 : 0.0;
-    const double voice_support = fmax(voice_conf, narrow_support);
+    const double voice_support = fmax(sh.voice_conf, narrow_support);
     const double balance_conf = ratio_conf > 0.12 ? fmax(ratio_conf, voice_support * 0.65) : ratio_conf;
     const double broadband_penalty = lerpd(0.35, 1.0, balance_conf);
-    const double narrowness_gain = lerpd(0.35, 1.0, AF_NORM_RANGE_CONST(narrowness, 0.34, 0.68));
-    return (0.62 * ratio_conf + 0.18 * level_conf + 0.20 * voice_support) * broadband_penalty * narrowness_gain;
+    return (0.62 * ratio_conf + 0.18 * level_conf + 0.20 * voice_support) * broadband_penalty * sh.narrowness_gain;
 }
 
 // Constants of the de-esser in the stream-minor table `base[field * stride]` (base already points
