@@ -13,6 +13,9 @@ first-safe-scale pick.
   e2e        same metric through the public API with HOST buffers (plan + H2D + render + D2H per step)
   roofline   dominant stage kernel: algorithmic bytes / its mean launch duration vs the measured HBM peak,
              plus `issue`: the FP64 / FP32 issue peaks measured in this run (the chain is issue bound)
+  stages     per stage kernel: share and mean launch duration in a serialised pass (CUDA events around every launch)
+  wavefront  the same batch in the LIVE wavefront: per-stage busy time under contention, the pipeline period and the
+             fraction of the GPU's instruction-issue capacity the sweep sustains (`issue_frac`)
   cpu_baseline  the CPU oracle port (the reference's Rust simulator cannot be built here) on all host
              threads, on a bounded sample of the same workload
 
@@ -379,7 +382,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                   "launch of 64 chunks); in the timed wavefront the stage kernels overlap",
                         "note": "the chain is FP64 / FP32 issue bound, not HBM bound (SURVEY 8(d)); see `issue` and profiles/",
                         "issue": {"fp64_peak_ginstr_s": fp64_peak, "fp32_fma_peak_ginstr_s": fp32_peak,
-                                  "unit": "1e9 warp-lane instructions/s, measured in this run"}}
+                                  "unit": "1e9 warp-lane instructions/s, measured in this run",
+                                  "wavefront_issue_frac": None}}
         wavefront = None
         if wave:
             periods = sorted(p for _, _, p in wave)
@@ -393,6 +397,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 instr = sum(NCU_WARP_INSTR.get(n, 0.0) for n, _, _ in wave)
                 wavefront["warp_instr_per_chunk"] = instr
                 wavefront["issue_frac"] = instr / (period_ms * 1e-3) / (148 * 4 * sm_clock)
+                if roofline:
+                    roofline["issue"]["wavefront_issue_frac"] = wavefront["issue_frac"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
