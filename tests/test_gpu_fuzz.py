@@ -1,0 +1,33 @@
+"""Randomised parity on the GPU: random sample rates, lengths (1 .. 40 000), typed / legacy bands and every settings
+key of the chain simulator through libafsim.so against the CPU oracle, on both kernel sets.  The generator is
+tools/fuzz_parity.py (a 4600-case soak of it ran clean on B200)."""
+import numpy as np
+import pytest
+
+from audio_forge_b200 import abi
+from oracle import pyoracle
+from tests.cases import audio_within_tolerance, metric_mismatches
+from tools.fuzz_parity import random_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from audio_forge_b200 import native
+    s = native.Simulator(0)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_random_chain_renders_match_the_oracle(sim, path, monkeypatch):
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
+    rng = np.random.default_rng(11 if path == "fused" else 12)
+    for i in range(48):
+        fs, x, bands, overrides = random_case(rng)
+        settings = abi.make_settings(**overrides)
+        m0, a0, _ = pyoracle.chain_render(x, fs, bands, settings, return_audio=True)
+        m1, a1 = sim.chain_render(x, fs, bands, settings, return_audio=True)
+        assert audio_within_tolerance(a0, a1) <= 0.0, (i, fs, x.size, overrides)
+        assert metric_mismatches(m0, m1, tol_db=0.01) == {}, (i, fs, x.size, overrides)
