@@ -106,6 +106,19 @@ def compressor_grid_candidates(n_candidates: int = 16384, seed: int = 0):
     return cands
 
 
+def default_preset_candidates(n_candidates: int = 1):
+    """C1 (default preset chain render): flat legacy EQ (with its 72-sample fade-in), compressor -20 dB / 4:1 /
+    10 ms / 200 ms (base release 50 ms, sidechain high-pass on), limiter -0.5 dB careful (-> -1.5 dB), de-esser
+    off (config_parts/settings.py:551-591), behind the live loop's DC block + 80 Hz high-pass."""
+    cands = (abi.AfCandidate * n_candidates)()
+    bands = abi.default_bands()
+    for i in range(n_candidates):
+        for b in range(10):
+            cands[i].bands[b] = bands[b]
+        cands[i].settings = abi.make_settings(input_stage="dc_hp80")
+    return cands
+
+
 def true_peak_candidates(n_candidates: int = 1):
     """C4 (batch true-peak detection + lookahead limiting): flat typed EQ, compressor off, limiter -1.5 dB /
     50 ms / 2 ms lookahead + true-peak limiter + detector."""

@@ -50,6 +50,8 @@ FS = workloads.FS
 
 # BASELINE.json configs.  c2 is the one the metric is quoted on at N = 1; the others are parity / scaling shapes.
 WORKLOADS = {
+    "c1": dict(kind="preset", candidates=1, passages=1, seconds=10.0, level=0.5,
+               name="C1 default preset chain render, single stream", chain="DC block + 80 Hz HP -> flat EQ -> compressor -> limiter -> true-peak"),
     "c2": dict(kind="headroom", candidates=4096, passages=1, seconds=30.0, level=0.5,
                name="C2 auto-eq headroom validation", chain="typed EQ -> compressor -> limiter -> true-peak"),
     "c3": dict(kind="compressor_grid", candidates=16384, passages=8, seconds=20.0, level=0.6,
@@ -159,7 +161,9 @@ def make_workload(args, rank: int):
     passages = [workloads.speech_like(n, seed=100 + 17 * rank + k, level=spec["level"]) for k in range(args.passages)]
     if kind == "full_chain":  # config 5: mains hum + harmonic injected at -26 dBFS
         passages = [workloads.add_hum(p, 50.37 + 0.11 * k) for k, p in enumerate(passages)]
-    if kind == "headroom":
+    if kind == "preset":
+        cands = workloads.default_preset_candidates(args.candidates)
+    elif kind == "headroom":
         cands = workloads.headroom_candidates(args.candidates, seed=1234 + rank)
     elif kind == "compressor_grid":
         cands = workloads.compressor_grid_candidates(args.candidates, seed=1234 + rank)
@@ -229,7 +233,7 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(threads, streams), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "candidates_per_s": value * 1e6 / n_samples,
         "note": "CPU oracle port of the reference's Rust chain simulator (no Rust toolchain in the image), one "
@@ -419,7 +423,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             threads = os.cpu_count() or 1
             n_sample = args.cpu_sample_streams or min(n_pairs, 4 * threads)
             cpu_value, cpu_s, streams = cpu_port_run(passages, cands, n_sample, threads)
-            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+            line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": min(threads, streams), "kind": "port",
                                     "sample": f"{streams} of {n_pairs} streams x the full passage, {cpu_s:.1f} s"}
         emit(line)
     sim.close()

@@ -48,7 +48,45 @@ def random_case(rng):
     return fs, x, bands, overrides
 
 
+def sweep_soak(rounds: int, seed: int):
+    """Random candidate x passage sweeps (mixed stage sets, lengths, shared passages) against the threaded oracle."""
+    from tests.cases import candidate_array
+    rng = np.random.default_rng(seed)
+    sim = native.Simulator(0)
+    failures, pairs_checked = [], 0
+    for r in range(rounds):
+        fs = 48000.0
+        lengths = [int(rng.integers(2000, 30000)) for _ in range(int(rng.integers(1, 4)))]
+        passages = [speech_like(n, seed=int(rng.integers(1 << 30)), level=float(rng.uniform(0.2, 1.1))) for n in lengths]
+        cand_list = []
+        for _ in range(int(rng.integers(8, 90))):
+            while True:
+                cfs, _, bands, overrides = random_case(rng)
+                if cfs == fs:
+                    break
+            c = abi.AfCandidate()
+            for b in range(abi.NUM_BANDS):
+                c.bands[b] = bands[b]
+            c.settings = abi.make_settings(**overrides)
+            cand_list.append(c)
+        cands = candidate_array(cand_list)
+        n_pass, n_cand = len(passages), len(cand_list)
+        pp = np.array([p for c in range(n_cand) for p in range(n_pass)], dtype=np.uint32)
+        pc = np.array([c for c in range(n_cand) for p in range(n_pass)], dtype=np.uint32)
+        got, _ = sim.chain_sweep(passages, fs, cands)
+        want = pyoracle.chain_sweep(passages, fs, cands, pp, pc, n_threads=16)
+        for i in range(pp.size):
+            bad = metric_mismatches(want[i], got[i], tol_db=0.01)
+            pairs_checked += 1
+            if bad:
+                failures.append({"round": r, "pair": i, "bad": {k: list(v) for k, v in bad.items()}})
+    print(json.dumps({"sweep_rounds": rounds, "seed": seed, "pairs": pairs_checked, "failures": len(failures), "first": failures[:3]}))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        sweep_soak(int(sys.argv[2]) if len(sys.argv) > 2 else 10, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+        return
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
