@@ -410,6 +410,10 @@ static int env_blocks_per_sm() {
     const char* v = getenv("AFSIM_MAP_BLOCKS_PER_SM");
     return v && *v ? atoi(v) : 0;
 }
+static int env_fir_blocks_per_sm() {
+    const char* v = getenv("AFSIM_FIR_BLOCKS_PER_SM");
+    return v && *v ? atoi(v) : -1;
+}
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -438,8 +442,16 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     static const int blocks_per_sm = env_blocks_per_sm();
     const unsigned gx = (unsigned)((a.n_streams + 31) / 32);
     unsigned gy = (unsigned)((n_groups + kMapWarps - 1) / kMapWarps);
-    if (blocks_per_sm > 0) {
-        const unsigned cap = (unsigned)((blocks_per_sm * sm_count() + (int)gx - 1) / (int)gx);
+    // The FP32 FIR maps and the limiter window map have so much instruction-level parallelism per warp that a few
+    // resident warps saturate the FMA issue; every further resident warp only takes issue slots from the serial
+    // kernels' warps on the same scheduler (round-robin among ready warps).  Their grids are capped (blocks loop
+    // over sample groups).  AFSIM_FIR_BLOCKS_PER_SM overrides the cap (0 = none).
+    static const int fir_blocks_env = env_fir_blocks_per_sm();
+    const bool fir_like = op == SP_TP_FIR_IN || op == SP_TP_FIR_OUT || op == SP_LIM_M;
+    int cap_per_sm = blocks_per_sm;
+    if (fir_like) cap_per_sm = fir_blocks_env >= 0 ? fir_blocks_env : kFirBlocksPerSm;
+    if (cap_per_sm > 0) {
+        const unsigned cap = (unsigned)((cap_per_sm * sm_count() + (int)gx - 1) / (int)gx);
         if (gy > cap) gy = cap < 1 ? 1 : cap;
     }
     const dim3 mgrid(gx, gy);

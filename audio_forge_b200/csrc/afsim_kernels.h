@@ -12,6 +12,7 @@ constexpr int kFinalizeThreads = 128;
 constexpr int kMapWarps = 4;  // warps per block of the map (M) kernels
 constexpr int kRBlock = 32;  // threads per block of the serial (R) kernels: one warp, so few-stream batches reach every SM
 constexpr size_t kFinalizeSmemLimit = 200 * 1024;
+constexpr int kFirBlocksPerSm = 8;  // grid cap of the FIR / limiter-window maps in blocks per SM (0 = none); see launch_split
 constexpr int kWarpPerStreamMax = 64;  // input cleanup: batches up to this many streams run one warp per stream (32x the warps: only where latency, not issue load, matters)
 
 cudaError_t launch_expand_deesser(const BatchArgs& a, cudaStream_t st);
