@@ -170,3 +170,19 @@ def test_gpu_reference_python_door_for_the_control_hook(sim):
     assert result["p99_block_runtime_ms"] >= 0.0
     with pytest.raises(ValueError, match="expected 3 VAD probabilities at the 10 ms control cadence, got 2"):
         mic_eq_core.simulate_auto_makeup_control(np.zeros(1440, dtype=np.float32), 48000.0, [0.0, 0.5], -50.0, 1.0)
+
+
+@pytest.mark.gpu
+def test_gpu_auto_makeup_sweep_with_shared_input(sim):
+    """72 auto-makeup candidates x one passage: whole-block chunks, the shared input stage and the split compressor
+    with R7 in one batch; a sample of the streams against the oracle."""
+    x = X[: 60000 + 321]
+    bands, overrides = CASES["legacy_eq"]
+    cand_list = [candidate(bands, **dict(overrides, input_stage="dc_hp80", compressor_threshold_db=-40.0 + 0.4 * i,
+                                         compressor_target_lufs=-22.0 + 0.1 * i, **{k: v for k, v in MAKEUP.items()
+                                                                                    if k != "compressor_target_lufs"}))
+                 for i in range(72)]
+    got, _ = sim.chain_sweep([x], FS, candidate_array(cand_list))
+    for i in (0, 17, 40, 71):
+        m0, _, _ = pyoracle.chain_render(x, FS, cand_list[i].bands, cand_list[i].settings)
+        assert metric_mismatches(m0, got[i], tol_db=0.01) == {}, i
