@@ -90,3 +90,20 @@ def gather_metrics(local_metrics, local_indices: np.ndarray, n_total: int, group
         rows = blob[: n * size].reshape(n, size)
         out.reshape(n_total, size)[idx] = rows
     return bytes_to_metrics(out)
+
+
+def sharded_chain_sweep(render, passages, sample_rate: float, candidates, pair_passage, pair_candidate, group=None):
+    """The whole multi-GPU step of a sweep: balance the streams over the ranks of ``group``, render this rank's shard
+    with ``render(passages, sample_rate, candidates, pair_passage, pair_candidate) -> AfChainMetrics array``
+    (``Simulator.chain_sweep``'s first result on a GPU rank), all-gather the metric structs.  Every rank returns the
+    AfChainMetrics of ALL pairs in caller order, so the final first-safe-scale / argmin pick is local and identical
+    on every rank."""
+    import torch.distributed as dist
+
+    pair_passage = np.asarray(pair_passage, dtype=np.uint32)
+    pair_candidate = np.asarray(pair_candidate, dtype=np.uint32)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    costs = stream_costs(candidates, pair_candidate, [len(passages[int(p)]) for p in pair_passage])
+    mine = shard_streams(costs, world)[rank]
+    local = render(passages, sample_rate, candidates, pair_passage[mine], pair_candidate[mine])
+    return gather_metrics(local, mine, pair_passage.size, group=group)

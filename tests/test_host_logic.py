@@ -128,10 +128,8 @@ def _worker(rank: int, world: int, port: int, tmp: str):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         passages, cands, pp, pc = _sweep_problem()
-        costs = sharding.stream_costs(cands, pc, [passages[p].size for p in pp])
-        mine = sharding.shard_streams(costs, world)[rank]
-        local = pyoracle.chain_sweep(passages, FS, cands, pp[mine], pc[mine])  # stands in for the rank's GPU render
-        full = sharding.gather_metrics(local, mine, pp.size)
+        # the oracle stands in for the rank's GPU render (Simulator.chain_sweep on a B200 rank)
+        full = sharding.sharded_chain_sweep(pyoracle.chain_sweep, passages, FS, cands, pp, pc)
         np.save(os.path.join(tmp, f"rank{rank}.npy"), sharding.metrics_to_bytes(full, pp.size))
     finally:
         dist.destroy_process_group()
