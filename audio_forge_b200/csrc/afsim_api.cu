@@ -107,7 +107,7 @@ struct DeviceBuffers {  // returns what it allocated to the handle's pool
     }
 };
 
-enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT };
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT, SK_EQ_SHARED };
 struct StageDesc {
     StageKind kind;
     int arg;  // SK_EQ: first section; SK_SPLIT: SplitOp
@@ -465,25 +465,57 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             if (!(a.structure & ST_DEESSER)) return;
             for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3}) batch->stages.push_back({SK_SPLIT, op});
         };
-        // Shared input stage: when several streams of the batch read the same passage (a candidate sweep), the input
-        // stage -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.
+        // Shared prefix: when several streams of the batch read the same passage (a candidate sweep), the input stage
+        // -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.  When the EQ
+        // is the first stage after it and the streams of a passage also share their EQ (a compressor grid over one
+        // EQ setting), the EQ runs on the distinct (passage, EQ) pairs as well and its output is what is fanned out.
+        bool shared_eq = false;
+        uint32_t shared_max_sections = 0;
         {
-            std::map<uint64_t, uint32_t> distinct;
-            std::vector<uint32_t> uidx(S_pad, 0);
-            std::vector<uint64_t> usrc;
-            std::vector<uint32_t> ucand;
-            for (int s = 0; s < S; ++s) {
-                auto it = distinct.find(src_off[s]);
-                if (it == distinct.end()) {
-                    it = distinct.emplace(src_off[s], static_cast<uint32_t>(usrc.size())).first;
-                    usrc.push_back(src_off[s]);
-                    ucand.push_back(cand[s]);
+            const bool eq_first = (a.structure & ST_EQ) && !(a.structure & ST_INPUT_TRUE_PEAK) &&
+                                  (!(a.structure & ST_DEESSER) || (a.structure & ST_EQ_BEFORE_DEESSER));
+            // EQ class of every candidate used by the batch: same sections, coefficients and fade flag
+            std::map<std::vector<unsigned char>, uint32_t> eq_classes;
+            std::vector<uint32_t> eq_class_of(plans.size(), 0);
+            if (eq_first) {
+                for (int s = 0; s < S; ++s) {
+                    const CandidateParams& p = plans[cand[s]].params;
+                    std::vector<unsigned char> key(sizeof p.eq + 8);
+                    std::memcpy(key.data(), p.eq, sizeof p.eq);
+                    const uint32_t meta[2] = {p.n_sections, p.flags & LF_EQ_FADE};
+                    std::memcpy(key.data() + sizeof p.eq, meta, 8);
+                    eq_class_of[cand[s]] = eq_classes.emplace(std::move(key), static_cast<uint32_t>(eq_classes.size())).first->second;
                 }
-                uidx[s] = it->second;
             }
+            auto distinct_streams = [&](bool with_eq, std::vector<uint32_t>& uidx, std::vector<uint64_t>& usrc,
+                                        std::vector<uint32_t>& ucand) {
+                std::map<std::pair<uint64_t, uint32_t>, uint32_t> distinct;
+                uidx.assign(S_pad, 0);
+                usrc.clear();
+                ucand.clear();
+                for (int s = 0; s < S; ++s) {
+                    const std::pair<uint64_t, uint32_t> key(src_off[s], with_eq ? eq_class_of[cand[s]] : 0u);
+                    auto it = distinct.find(key);
+                    if (it == distinct.end()) {
+                        it = distinct.emplace(key, static_cast<uint32_t>(usrc.size())).first;
+                        usrc.push_back(src_off[s]);
+                        ucand.push_back(cand[s]);
+                    }
+                    uidx[s] = it->second;
+                }
+            };
+            std::vector<uint32_t> uidx, ucand;
+            std::vector<uint64_t> usrc;
+            const int share_mode = env_int("AFSIM_SHARED_INPUT", 1);  // 1: input (+ EQ), 2: off, 3: input only
+            if (eq_first && share_mode == 1) {
+                distinct_streams(true, uidx, usrc, ucand);
+                shared_eq = S >= 64 && static_cast<int>(usrc.size()) * 4 <= S;
+            }
+            if (!shared_eq) distinct_streams(false, uidx, usrc, ucand);
             const int U = static_cast<int>(usrc.size());
-            if (S >= 64 && U * 4 <= S && env_int("AFSIM_SHARED_INPUT", 1) != 2) {
+            if (S >= 64 && U * 4 <= S && share_mode != 2) {
                 const int U_pad = round_up(U, 32);
+                for (int u = 0; u < U; ++u) shared_max_sections = std::max(shared_max_sections, plans[ucand[u]].params.n_sections);
                 usrc.resize(U_pad, 0);
                 ucand.resize(U_pad, 0);
                 BatchArgs& ua = batch->shared_input;
@@ -503,6 +535,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&d_urows, batch->shared_rows_elems));
                 AF_CUDA(h, sweep->mem.alloc(&d_uaccum, U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_ustate, static_cast<size_t>(kStateInput) * U_pad));
+                if (shared_eq) AF_CUDA(h, sweep->mem.alloc(&ua.st_eq, static_cast<size_t>(kStateEqPerSection * kMaxSections) * U_pad));
                 AF_CUDA(h, cudaMemcpyAsync(d_uidx, uidx.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_ucand, ucand.data(), U_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_usrc, usrc.data(), U_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
@@ -519,16 +552,23 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 a.in_rows = d_urows;
                 a.in_accum = d_uaccum;
                 a.in_stride = U_pad;
+            } else {
+                shared_eq = false;
             }
         }
         if (batch->shared_input.n_streams > 0) {
             batch->stages.push_back({SK_INPUT_SHARED, 0});
+            if (shared_eq)
+                for (uint32_t first = 0; first < shared_max_sections; first += batch->eq_k)
+                    batch->stages.push_back({SK_EQ_SHARED, static_cast<int>(first)});
             batch->stages.push_back({SK_INPUT_FANOUT, 0});
         } else {
             batch->stages.push_back({SK_INPUT, 0});
         }
         if (a.structure & ST_INPUT_TRUE_PEAK) batch->stages.push_back({SK_INPUT_TP, 0});
-        if (a.structure & ST_EQ_BEFORE_DEESSER) {
+        if (shared_eq) {
+            push_deesser();  // the EQ already ran on the distinct (passage, EQ) pairs
+        } else if (a.structure & ST_EQ_BEFORE_DEESSER) {
             push_eq();
             push_deesser();
         } else {
@@ -569,6 +609,7 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
         case SK_INPUT: return launch_input(b.args, ck, stream);
         case SK_INPUT_SHARED: return launch_input(b.shared_input, ck, stream);
         case SK_INPUT_FANOUT: return launch_input_fanout(b.args, ck, stream);
+        case SK_EQ_SHARED: return launch_eq(b.shared_input, ck, st.arg, b.eq_k, stream);
         case SK_INPUT_TP: return launch_input_true_peak(b.args, ck, stream);
         case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
@@ -887,7 +928,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
         return cuda_fail(h, err, "afsim_sweep_profile_stages");
     }
     static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT};
+                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ};
     for (int i = 0; i < n_stages; ++i) {
         double total = 0.0;
         for (int c = 0; c < timed_chunks; ++c) {
@@ -932,7 +973,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
     if (rc == AFSIM_OK && err != cudaSuccess) rc = cuda_fail(h, err, "afsim_sweep_profile_wavefront");
     if (rc == AFSIM_OK) {
         static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT};
+                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ};
         for (int i = 0; i < n_stages; ++i) {
             double busy = 0.0;
             for (int c = 0; c < tr.n; ++c) {

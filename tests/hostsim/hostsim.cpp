@@ -236,10 +236,18 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     std::vector<float> ubuf, urows;
     std::vector<double> ustate;
     std::vector<StreamAccum> uaccum;
+    const bool shared_eq = (split & 32) != 0;  // with bit 4: the EQ runs on the distinct (passage, EQ) pairs as well
+    std::vector<double> ust_eq;
+    uint32_t shared_max_sections = 0;
     if (split & 16) {
         for (int s = 0; s < S; ++s) {
             size_t u = 0;
-            while (u < usrc.size() && usrc[u] != src_off[s]) ++u;
+            while (u < usrc.size() &&
+                   !(usrc[u] == src_off[s] &&
+                     (!shared_eq || (std::memcmp(params[ucand[u]].eq, params[cand[s]].eq, sizeof params[0].eq) == 0 &&
+                                     params[ucand[u]].n_sections == params[cand[s]].n_sections &&
+                                     (params[ucand[u]].flags & LF_EQ_FADE) == (params[cand[s]].flags & LF_EQ_FADE)))))
+                ++u;
             if (u == usrc.size()) {
                 usrc.push_back(src_off[s]);
                 ucand.push_back(cand[s]);
@@ -247,6 +255,8 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
             uidx[s] = static_cast<uint32_t>(u);
         }
         const int U = static_cast<int>(usrc.size()), U_pad = (U + 31) / 32 * 32;
+        for (int u = 0; u < U; ++u) shared_max_sections = std::max(shared_max_sections, params[ucand[u]].n_sections);
+        ust_eq.assign(static_cast<size_t>(kStateEqPerSection * kMaxSections) * U_pad, 0.0);
         usrc.resize(U_pad, 0);
         ucand.resize(U_pad, 0);
         ubuf.assign(static_cast<size_t>(a.ring_rows) * U_pad, 0.0f);
@@ -263,6 +273,7 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         ua.rows = urows.data();
         ua.accum = uaccum.data();
         ua.st_input = ustate.data();
+        ua.st_eq = ust_eq.data();
         a.in_unique = uidx.data();
         a.in_src = ubuf.data();
         a.in_rows = urows.data();
@@ -305,6 +316,14 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
                 else
                     body_input(ua, ck, u);
             }
+            if (shared_eq)
+                for (uint32_t f = 0; f < shared_max_sections; f += eq_k)
+                    for (int u = 0; u < ua.n_streams; ++u) {
+                        if (eq_k == 10)
+                            body_eq<10>(ua, ck, u, static_cast<int>(f));
+                        else
+                            body_eq<5>(ua, ck, u, static_cast<int>(f));
+                    }
             for (int g = (ck.len + kFanoutGroup - 1) / kFanoutGroup; g >= 0; --g)
                 for (int s = 0; s < S; ++s) body_input_fanout(a, ck, s, g);
         } else {
@@ -315,7 +334,9 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
                     body_input(a, ck, s);
             }
         }
-        if (a.structure & ST_EQ_BEFORE_DEESSER) {
+        if ((split & 16) && shared_eq) {
+            if (a.structure & ST_DEESSER) run_deesser(ck);
+        } else if (a.structure & ST_EQ_BEFORE_DEESSER) {
             run_eq(ck);
             if (a.structure & ST_DEESSER) run_deesser(ck);
         } else {

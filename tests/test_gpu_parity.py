@@ -229,3 +229,27 @@ def test_shared_input_stage_is_bit_identical(sim, input_stage, monkeypatch):
     m0, a0, _ = pyoracle.chain_render(passages[1], FS, cand_list[5].bands, cand_list[5].settings, return_audio=True)
     assert audio_within_tolerance(a0, a_shared[5 * 2 + 1]) <= 0.0
     assert metric_mismatches(m0, m_shared[5 * 2 + 1], tol_db=TOL_DB) == {}
+
+
+@pytest.mark.parametrize("name", ["legacy_eq", "typed_worst_40_sections"])
+def test_shared_eq_prefix_is_bit_identical(sim, name, monkeypatch):
+    """A compressor grid over ONE EQ setting: the input stage and the EQ run once per distinct (passage, EQ) pair and
+    are fanned out; results identical, bit for bit, to every stream rendering its own prefix."""
+    passages = [speech_like(20000 + 123 * k, seed=60 + k, level=0.7) for k in range(2)]
+    passages[1] = passages[1][: passages[0].size].copy()
+    bands, overrides = CASES[name]
+    cand_list = [candidate(bands, **dict(overrides, compressor_threshold_db=-45.0 + 0.5 * i, compressor_ratio=2.0 + 0.05 * i))
+                 for i in range(40)]
+    cands = candidate_array(cand_list)
+    monkeypatch.setenv("AFSIM_SHARED_INPUT", "2")  # off
+    m_own, a_own = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    monkeypatch.setenv("AFSIM_SHARED_INPUT", "1")
+    m_shared, a_shared = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    for i in range(len(cand_list) * 2):
+        d0, d1 = abi.metrics_to_dict(m_own[i]), abi.metrics_to_dict(m_shared[i])
+        d0.pop("candidate_runtime_ms"), d1.pop("candidate_runtime_ms")
+        assert d0 == d1, i
+        assert np.array_equal(a_own[i], a_shared[i]), i
+    m0, a0, _ = pyoracle.chain_render(passages[0], FS, cand_list[7].bands, cand_list[7].settings, return_audio=True)
+    assert audio_within_tolerance(a0, a_shared[7 * 2]) <= 0.0
+    assert metric_mismatches(m0, m_shared[7 * 2], tol_db=TOL_DB) == {}

@@ -70,6 +70,23 @@ def test_shared_input_stage_fan_out(input_stage):
             assert np.array_equal(r0, rows[:, :, i].T), i
 
 
+def test_shared_input_and_eq_prefix_fan_out():
+    """A compressor grid over one EQ setting: input stage AND EQ run once per distinct (passage, EQ) pair (split bits
+    4 + 5); legacy EQ (72-sample fade-in) and typed EQ, EQ-first orders only."""
+    n = 3 * 960 + 411
+    passages = [speech_like(n, seed=40 + s, level=0.7) for s in range(2)]
+    for name, extra in (("legacy_eq", {}), ("typed_pass", {"deesser_enabled": False})):
+        bands, overrides = CASES[name]
+        cand_list = [candidate(bands, **dict(overrides, **extra, compressor_threshold_db=thr, compressor_ratio=ratio))
+                     for thr in (-35.0, -20.0) for ratio in (2.0, 5.0)]
+        cands = candidate_array(cand_list)
+        pp = np.array([p for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+        pc = np.array([c for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+        for split, chunk in ((48, 1000), (48 | 7, 512)):
+            got, audio, _ = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=chunk, slots=2, split=split, want_audio=True)
+            _check_pairs(passages, cand_list, pp, pc, got, audio)
+
+
 def _check_pairs(passages, cand_list, pp, pc, got, audio):
     for i in range(pp.size):
         m0, a0, _ = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings,
