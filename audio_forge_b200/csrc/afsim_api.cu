@@ -478,7 +478,10 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             std::map<std::vector<unsigned char>, uint32_t> eq_classes;
             std::vector<uint32_t> eq_class_of(plans.size(), 0);
             if (eq_first) {
+                std::vector<bool> classified(plans.size(), false);
                 for (int s = 0; s < S; ++s) {
+                    if (classified[cand[s]]) continue;  // once per candidate, not per stream
+                    classified[cand[s]] = true;
                     const CandidateParams& p = plans[cand[s]].params;
                     std::vector<unsigned char> key(sizeof p.eq + 8);
                     std::memcpy(key.data(), p.eq, sizeof p.eq);
