@@ -107,7 +107,7 @@ struct DeviceBuffers {  // returns what it allocated to the handle's pool
     }
 };
 
-enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT, SK_EQ_SHARED };
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT, SK_EQ_SHARED, SK_SPLIT_SHARED };
 struct StageDesc {
     StageKind kind;
     int arg;  // SK_EQ: first section; SK_SPLIT: SplitOp
@@ -469,7 +469,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         // -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.  When the EQ
         // is the first stage after it and the streams of a passage also share their EQ (a compressor grid over one
         // EQ setting), the EQ runs on the distinct (passage, EQ) pairs as well and its output is what is fanned out.
-        bool shared_eq = false;
+        bool shared_eq = false, shared_front = false;
         uint32_t shared_max_sections = 0;
         {
             const bool eq_first = (a.structure & ST_EQ) && !(a.structure & ST_INPUT_TRUE_PEAK) &&
@@ -485,7 +485,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                     const CandidateParams& p = plans[cand[s]].params;
                     std::vector<unsigned char> key(sizeof p.eq + 8);
                     std::memcpy(key.data(), p.eq, sizeof p.eq);
-                    const uint32_t meta[2] = {p.n_sections, p.flags & LF_EQ_FADE};
+                    const uint32_t meta[2] = {p.n_sections, p.flags & (LF_EQ_FADE | LF_C_SIDECHAIN)};
                     std::memcpy(key.data() + sizeof p.eq, meta, 8);
                     eq_class_of[cand[s]] = eq_classes.emplace(std::move(key), static_cast<uint32_t>(eq_classes.size())).first->second;
                 }
@@ -539,6 +539,13 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&d_uaccum, U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_ustate, static_cast<size_t>(kStateInput) * U_pad));
                 if (shared_eq) AF_CUDA(h, sweep->mem.alloc(&ua.st_eq, static_cast<size_t>(kStateEqPerSection * kMaxSections) * U_pad));
+                // the compressor front as well, when the compressor follows the EQ directly and runs fused per stream
+                shared_front = shared_eq && !split && !auto_makeup && (a.structure & ST_COMPRESSOR) && !(a.structure & ST_DEESSER) &&
+                               share_mode == 1;
+                if (shared_front) {
+                    for (int k = 0; k < 4; ++k) AF_CUDA(h, sweep->mem.alloc(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
+                    AF_CUDA(h, sweep->mem.alloc(&ua.st_comp, static_cast<size_t>(kStateCompressor) * U_pad));
+                }
                 AF_CUDA(h, cudaMemcpyAsync(d_uidx, uidx.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_ucand, ucand.data(), U_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_usrc, usrc.data(), U_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
@@ -549,7 +556,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 ua.rows = d_urows;
                 ua.accum = d_uaccum;
                 ua.st_input = d_ustate;
-                ua.stage_inputs = 0;
+                ua.stage_inputs = shared_front ? 1 : 0;  // R1 runs staged
+                if (shared_front) {
+                    a.in_det = ua.w[0];
+                    a.in_wdb = ua.w[1];
+                    a.in_ipk = ua.w[2];
+                }
                 a.in_unique = d_uidx;
                 a.in_src = d_ubuf;
                 a.in_rows = d_urows;
@@ -559,11 +571,16 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 shared_eq = false;
             }
         }
+        if (!shared_eq) shared_front = false;
         if (batch->shared_input.n_streams > 0) {
             batch->stages.push_back({SK_INPUT_SHARED, 0});
             if (shared_eq)
                 for (uint32_t first = 0; first < shared_max_sections; first += batch->eq_k)
                     batch->stages.push_back({SK_EQ_SHARED, static_cast<int>(first)});
+            if (shared_front) {
+                batch->stages.push_back({SK_SPLIT_SHARED, SP_COMP_R1});
+                batch->stages.push_back({SK_SPLIT_SHARED, SP_COMP_M2});
+            }
             batch->stages.push_back({SK_INPUT_FANOUT, 0});
         } else {
             batch->stages.push_back({SK_INPUT, 0});
@@ -613,6 +630,7 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
         case SK_INPUT_SHARED: return launch_input(b.shared_input, ck, stream);
         case SK_INPUT_FANOUT: return launch_input_fanout(b.args, ck, stream);
         case SK_EQ_SHARED: return launch_eq(b.shared_input, ck, st.arg, b.eq_k, stream);
+        case SK_SPLIT_SHARED: return launch_split(static_cast<SplitOp>(st.arg), b.shared_input, ck, stream);
         case SK_INPUT_TP: return launch_input_true_peak(b.args, ck, stream);
         case SK_EQ: return launch_eq(b.args, ck, st.arg, b.eq_k, stream);
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
@@ -931,7 +949,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
         return cuda_fail(h, err, "afsim_sweep_profile_stages");
     }
     static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ};
+                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0};
     for (int i = 0; i < n_stages; ++i) {
         double total = 0.0;
         for (int c = 0; c < timed_chunks; ++c) {
@@ -940,7 +958,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
             cudaEventElapsedTime(&ms, ev[e0], ev[e0 + 1]);
             total += ms;
         }
-        out_kind[i] = b.stages[i].kind == SK_SPLIT ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
+        out_kind[i] = (b.stages[i].kind == SK_SPLIT || b.stages[i].kind == SK_SPLIT_SHARED) ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
         out_ms[i] = static_cast<float>(total);
         out_launches[i] = timed_chunks;
     }
@@ -976,7 +994,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
     if (rc == AFSIM_OK && err != cudaSuccess) rc = cuda_fail(h, err, "afsim_sweep_profile_wavefront");
     if (rc == AFSIM_OK) {
         static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ};
+                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0};
         for (int i = 0; i < n_stages; ++i) {
             double busy = 0.0;
             for (int c = 0; c < tr.n; ++c) {
@@ -988,7 +1006,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
             float span = 0.0f;  // completion of the first traced chunk -> completion of the last one, on this stage
             cudaEventElapsedTime(&span, tr.ev[static_cast<size_t>(i) * 2 + 1],
                                  tr.ev[(static_cast<size_t>(tr.n - 1) * n_stages + i) * 2 + 1]);
-            out_kind[i] = b.stages[i].kind == SK_SPLIT ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
+            out_kind[i] = (b.stages[i].kind == SK_SPLIT || b.stages[i].kind == SK_SPLIT_SHARED) ? AF_STAGE_SPLIT_BASE + b.stages[i].arg : kind_map[b.stages[i].kind];
             out_busy_ms[i] = static_cast<float>(busy / tr.n);
             out_period_ms[i] = span / static_cast<float>(tr.n - 1);
         }

@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(128) k_compressor(BatchArgs a, ChunkArgs ck) {
     body_compressor(a, ck, s);
 }
 
+__global__ void __launch_bounds__(128) k_compressor_shared(BatchArgs a, ChunkArgs ck) {
+    AF_STREAM_INDEX();
+    body_compressor_shared(a, ck, s);
+}
+
 __global__ void __launch_bounds__(128) k_limiter(BatchArgs a, ChunkArgs ck) {
     AF_STREAM_INDEX();
     body_limiter(a, ck, s);
@@ -367,7 +372,7 @@ cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t s
     return cudaGetLastError();
 }
 cudaError_t launch_input_fanout(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
-    const int n_groups = (ck.len + kFanoutGroup - 1) / kFanoutGroup;
+    const int n_groups = a.in_det ? 1 : (ck.len + kFanoutGroup - 1) / kFanoutGroup;  // rows and statistics only
     const dim3 grid((unsigned)((a.n_streams + 31) / 32), (unsigned)((n_groups + kMapWarps - 1) / kMapWarps));
     k_input_fanout<<<grid, 32 * kMapWarps, 0, st>>>(a, ck);
     return cudaGetLastError();
@@ -384,7 +389,10 @@ cudaError_t launch_eq(const BatchArgs& a, const ChunkArgs& ck, int first, int k,
 }
 cudaError_t launch_compressor(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
     const int b = pick_block(a);
-    k_compressor<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    if (a.in_det)
+        k_compressor_shared<<<stream_grid(a, b), b, 0, st>>>(a, ck);
+    else
+        k_compressor<<<stream_grid(a, b), b, 0, st>>>(a, ck);
     return cudaGetLastError();
 }
 cudaError_t launch_limiter(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {

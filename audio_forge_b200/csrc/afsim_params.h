@@ -173,6 +173,12 @@ struct BatchArgs {
     const float* in_rows;         // [n_rows][in_stride] their input-level rows (row.0)
     const StreamAccum* in_accum;  // [in_stride] their input statistics
     int in_stride;
+    // shared compressor front (a compressor grid over one EQ setting): sidechain signal, detector weight (dB) and
+    // instantaneous peak (dB) of the distinct (passage, EQ) pairs -- what R1 + M2 produce -- read by every stream's
+    // compressor instead of being recomputed; the streams then also read the EQ output itself from in_src
+    const double* in_det;         // [ring_rows][in_stride], or nullptr
+    const double* in_wdb;
+    const double* in_ipk;
     const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
     const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)
     const struct CleanupConst* cleanup;  // sample-rate constants of the adaptive input cleanup (afsim_cleanup.h)

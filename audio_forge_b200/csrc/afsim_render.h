@@ -130,9 +130,11 @@ AF_HD void body_input_fanout(const BatchArgs& a, const ChunkArgs& ck, int s, int
     const uint32_t u = a.in_unique[s];
     const int t0 = g * kFanoutGroup;
     const int valid = ck.len - t0 < kFanoutGroup ? ck.len - t0 : kFanoutGroup;
-    const float* src = a.in_src + (size_t)(ck.row0 + t0) * ustride + u;
-    float* dst = a.buf_a + (size_t)(ck.row0 + t0) * stride + s;
-    for (int t = 0; t < valid; ++t) dst[(size_t)t * stride] = src[(size_t)t * ustride];
+    if (!a.in_det) {  // with a shared compressor front the streams read the shared EQ output in place
+        const float* src = a.in_src + (size_t)(ck.row0 + t0) * ustride + u;
+        float* dst = a.buf_a + (size_t)(ck.row0 + t0) * stride + s;
+        for (int t = 0; t < valid; ++t) dst[(size_t)t * stride] = src[(size_t)t * ustride];
+    }
     if (g != 0) return;
     const int end = ck.n0 + ck.len;  // analysis blocks that end inside this chunk
     for (int b = ck.n0 / a.block_samples; b < a.n_rows; ++b) {
@@ -182,6 +184,28 @@ AF_HD void body_compressor(const BatchArgs& a, const ChunkArgs& ck, int s) {
     clk.init(a.block_samples, a.n_samples, ck.n0);
     const Col io{a.buf_a + (size_t)ck.row0 * stride + s, stride};
     st.run(io, ck.n0, ck.len, clk, a.rows + (size_t)2 * a.n_rows * stride + s, stride);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> sio{a.st_comp + s, stride};
+        st.sync(sio);
+    }
+}
+
+// Compressor of a stream whose front (sidechain, detector weight, instantaneous peak) and input (the EQ output) come
+// from the shared render of its (passage, EQ) pair: shared rings -> buf_a.
+AF_HD void body_compressor_shared(const BatchArgs& a, const ChunkArgs& ck, int s) {
+    const size_t stride = (size_t)a.stride, ustride = (size_t)a.in_stride;
+    CompressorStage st;
+    st.init(stream_params(a, s));
+    if (ck.n0 != 0) {
+        StateIO<false> io{a.st_comp + s, stride};
+        st.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const size_t o = (size_t)ck.row0 * ustride + a.in_unique[s];
+    const Col out{a.buf_a + (size_t)ck.row0 * stride + s, stride};
+    st.run_shared(a.in_src + o, a.in_det + o, a.in_wdb + o, a.in_ipk + o, ustride, out, ck.n0, ck.len, clk,
+                  a.rows + (size_t)2 * a.n_rows * stride + s, stride);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> sio{a.st_comp + s, stride};
         st.sync(sio);

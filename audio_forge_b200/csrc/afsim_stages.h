@@ -462,6 +462,72 @@ struct CompressorStage {
         return factor * x * x / (2.0 * knee);
     }
 
+    // The same walk with the front of the stage (sidechain high-pass, band envelopes, detector weight, instantaneous
+    // peak: phases 1 - 2) taken from a shared render: xs / det / wdb / ipk are columns (pitch `ustride`) of the
+    // distinct (passage, EQ) pair this stream belongs to.  Phases 3 - 6 are those of `run`, value for value.
+    AF_HD void run_shared(const float* xs, const double* dcol, const double* wcol, const double* icol, size_t ustride,
+                          const Col& out, int n0, int len, BlockClock clk, float* rows_comp, size_t stride) {
+        constexpr int M = kCompMicro;
+        for (int t0 = 0; t0 < len; t0 += M) {
+            double x[M], det[M], wdb[M], ipk[M], pk[M], rms[M], tgt[M], grv[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const bool live = t0 + i < len;
+                const size_t o = (size_t)(t0 + i) * ustride;
+                x[i] = live ? (double)xs[o] : 0.0;
+                det[i] = live ? dcol[o] : 0.0;
+                wdb[i] = live ? wcol[o] : 0.0;
+                ipk[i] = live ? icol[o] : lin_to_db(0.0, 1e-10);
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // phase 3
+                const bool up = ipk[i] > peak_env;
+                peak_env = (up ? attack : det_release) * peak_env + (up ? one_m_attack : one_m_det_release) * ipk[i];
+                rms_env = rms_c * rms_env + one_m_rms * (det[i] * det[i]);
+                pk[i] = peak_env;
+                rms[i] = rms_env;
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // phase 4
+                const double blended = 0.6 * db_to_lin(pk[i]) + 0.4 * rms_linear(rms[i]);
+                tgt[i] = gain_computer(lin_to_db(blended, 1e-10) + wdb[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // phase 5
+                if (t0 + i < len) {
+                    const double target = tgt[i];
+                    if (!adaptive) {
+                        const bool up = target > gr;
+                        gr = (up ? attack : release) * gr + (up ? one_m_attack : one_m_release) * target;
+                    } else {
+                        if (target > gr)
+                            fast_env = attack * gr + one_m_attack * target;
+                        else
+                            fast_env = fast_c * fast_env + one_m_fast * target;
+                        if (target > 3.0)
+                            slow_env = charge_c * slow_env + one_m_charge * target;
+                        else
+                            slow_env *= slow_c;
+                        gr = fmax(fast_env, slow_env);
+                    }
+                }
+                grv[i] = gr;
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // phase 6
+                if (t0 + i < len) {
+                    const double gain = db_to_lin(-grv[i]) * makeup_lin;
+                    out.set(t0 + i, (float)(x[i] * gain));
+                    const int n = n0 + t0 + i;
+                    if (clk.at_end(n)) {
+                        rows_comp[(size_t)clk.blk * stride] = (float)grv[i];
+                        clk.advance();
+                    }
+                }
+            }
+        }
+    }
+
     // rows_comp: row.2 table of this stream.  Samples past `len` in the last micro-tile are padding:
     // they touch the recurrence state after the final real sample only, and are never stored.
     AF_HD void run(const Col& io, int n0, int len, BlockClock clk, float* rows_comp, size_t stride) {

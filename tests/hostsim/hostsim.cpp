@@ -237,6 +237,9 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     std::vector<double> ustate;
     std::vector<StreamAccum> uaccum;
     const bool shared_eq = (split & 32) != 0;  // with bit 4: the EQ runs on the distinct (passage, EQ) pairs as well
+    const bool shared_front = (split & 64) != 0 && shared_eq;  // ... and so does the compressor front (fused compressor)
+    std::vector<std::vector<double>> uw(4);
+    std::vector<double> ust_comp;
     std::vector<double> ust_eq;
     uint32_t shared_max_sections = 0;
     if (split & 16) {
@@ -246,7 +249,8 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
                    !(usrc[u] == src_off[s] &&
                      (!shared_eq || (std::memcmp(params[ucand[u]].eq, params[cand[s]].eq, sizeof params[0].eq) == 0 &&
                                      params[ucand[u]].n_sections == params[cand[s]].n_sections &&
-                                     (params[ucand[u]].flags & LF_EQ_FADE) == (params[cand[s]].flags & LF_EQ_FADE)))))
+                                     (params[ucand[u]].flags & (LF_EQ_FADE | LF_C_SIDECHAIN)) ==
+                                         (params[cand[s]].flags & (LF_EQ_FADE | LF_C_SIDECHAIN))))))
                 ++u;
             if (u == usrc.size()) {
                 usrc.push_back(src_off[s]);
@@ -274,6 +278,17 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         ua.accum = uaccum.data();
         ua.st_input = ustate.data();
         ua.st_eq = ust_eq.data();
+        if (shared_front) {
+            for (int k = 0; k < 4; ++k) {
+                uw[k].assign(static_cast<size_t>(a.ring_rows) * U_pad, 0.0);
+                ua.w[k] = uw[k].data();
+            }
+            ust_comp.assign(static_cast<size_t>(kStateCompressor) * U_pad, 0.0);
+            ua.st_comp = ust_comp.data();
+            a.in_det = ua.w[0];
+            a.in_wdb = ua.w[1];
+            a.in_ipk = ua.w[2];
+        }
         a.in_unique = uidx.data();
         a.in_src = ubuf.data();
         a.in_rows = urows.data();
@@ -324,6 +339,12 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
                         else
                             body_eq<5>(ua, ck, u, static_cast<int>(f));
                     }
+            if (shared_front) {
+                const Staging ust{staging_bytes.data(), 1, 0, 0};
+                for (int u = 0; u < ua.n_streams; ++u) body_comp_r1(ua, ck, u, ust);
+                for (int g = (ck.len + kCompMapGroup - 1) / kCompMapGroup; g >= 0; --g)
+                    for (int u = 0; u < ua.n_streams; ++u) body_comp_m2(ua, ck, u, g);
+            }
             for (int g = (ck.len + kFanoutGroup - 1) / kFanoutGroup; g >= 0; --g)
                 for (int s = 0; s < S; ++s) body_input_fanout(a, ck, s, g);
         } else {
@@ -360,6 +381,8 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
                     const Staging st7{(split & 8) ? nullptr : staging_bytes.data(), 1, 0, 0};
                     for (int s = 0; s < S; ++s) body_comp_r7(a, ck, s, st7);
                 }
+            } else if ((split & 16) && shared_front) {
+                for (int s = 0; s < S; ++s) body_compressor_shared(a, ck, s);
             } else {
                 for (int s = 0; s < S; ++s) body_compressor(a, ck, s);
             }

@@ -231,10 +231,13 @@ def test_shared_input_stage_is_bit_identical(sim, input_stage, monkeypatch):
     assert metric_mismatches(m0, m_shared[5 * 2 + 1], tol_db=TOL_DB) == {}
 
 
+@pytest.mark.parametrize("path", ["fused", "split"])
 @pytest.mark.parametrize("name", ["legacy_eq", "typed_worst_40_sections"])
-def test_shared_eq_prefix_is_bit_identical(sim, name, monkeypatch):
+def test_shared_eq_prefix_is_bit_identical(sim, name, path, monkeypatch):
     """A compressor grid over ONE EQ setting: the input stage and the EQ run once per distinct (passage, EQ) pair and
-    are fanned out; results identical, bit for bit, to every stream rendering its own prefix."""
+    are fanned out -- with the fused kernels also the compressor front (sidechain, detector weight, instantaneous
+    peak); results identical, bit for bit, to every stream rendering its own prefix."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
     passages = [speech_like(20000 + 123 * k, seed=60 + k, level=0.7) for k in range(2)]
     passages[1] = passages[1][: passages[0].size].copy()
     bands, overrides = CASES[name]
