@@ -116,6 +116,7 @@ struct StageDesc {
 struct Batch {
     BatchArgs args{};
     BatchArgs shared_input{};       // the distinct passages' input stage (n_streams == 0: every stream renders its own)
+    bool shared_deesser = false;    // ... followed by the de-esser's detector front
     size_t shared_rows_elems = 0;
     std::vector<StageDesc> stages;
     std::vector<uint32_t> members;  // caller's pair index of stream s
@@ -461,15 +462,17 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             for (uint32_t first = 0; first < max_sections; first += batch->eq_k)
                 batch->stages.push_back({SK_EQ, static_cast<int>(first)});
         };
+        bool shared_de_flag = false;  // set below, before the stage list is built
         auto push_deesser = [&]() {
             if (!(a.structure & ST_DEESSER)) return;
-            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3}) batch->stages.push_back({SK_SPLIT, op});
+            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3})
+                if (!(shared_de_flag && (op == SP_DE_RA || op == SP_DE_MB))) batch->stages.push_back({SK_SPLIT, op});
         };
         // Shared prefix: when several streams of the batch read the same passage (a candidate sweep), the input stage
         // -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.  When the EQ
         // is the first stage after it and the streams of a passage also share their EQ (a compressor grid over one
         // EQ setting), the EQ runs on the distinct (passage, EQ) pairs as well and its output is what is fanned out.
-        bool shared_eq = false, shared_front = false;
+        bool shared_eq = false, shared_front = false, shared_de = false;
         uint32_t shared_max_sections = 0;
         {
             const bool eq_first = (a.structure & ST_EQ) && !(a.structure & ST_INPUT_TRUE_PEAK) &&
@@ -488,6 +491,25 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                     const uint32_t meta[2] = {p.n_sections, p.flags & (LF_EQ_FADE | LF_C_SIDECHAIN)};
                     std::memcpy(key.data() + sizeof p.eq, meta, 8);
                     eq_class_of[cand[s]] = eq_classes.emplace(std::move(key), static_cast<uint32_t>(eq_classes.size())).first->second;
+                }
+            }
+            // de-esser first: its detector front (R_a + M_b) depends on the band split and the fixed detector time
+            // constants only -- classify those
+            const bool de_first = (a.structure & ST_DEESSER) && !(a.structure & ST_EQ_BEFORE_DEESSER) &&
+                                  !(a.structure & ST_INPUT_TRUE_PEAK);
+            if (de_first) {
+                std::map<std::vector<unsigned char>, uint32_t> de_classes;
+                std::vector<bool> classified(plans.size(), false);
+                for (int s = 0; s < S; ++s) {
+                    if (classified[cand[s]]) continue;
+                    classified[cand[s]] = true;
+                    const CandidateParams& p = plans[cand[s]].params;
+                    std::vector<unsigned char> key(30 * 8 + 2 * 8 + sizeof p.de_det0);
+                    std::memcpy(key.data(), p.de + DE_DET, 30 * 8);
+                    std::memcpy(key.data() + 240, p.de + DE_DET_ATTACK, 8);
+                    std::memcpy(key.data() + 248, p.de + DE_DET_RELEASE, 8);
+                    std::memcpy(key.data() + 256, p.de_det0, sizeof p.de_det0);
+                    eq_class_of[cand[s]] = de_classes.emplace(std::move(key), static_cast<uint32_t>(de_classes.size())).first->second;
                 }
             }
             auto distinct_streams = [&](bool with_eq, std::vector<uint32_t>& uidx, std::vector<uint64_t>& usrc,
@@ -514,7 +536,11 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 distinct_streams(true, uidx, usrc, ucand);
                 shared_eq = S >= 64 && static_cast<int>(usrc.size()) * 4 <= S;
             }
-            if (!shared_eq) distinct_streams(false, uidx, usrc, ucand);
+            if (de_first && share_mode == 1) {
+                distinct_streams(true, uidx, usrc, ucand);
+                shared_de = S >= 64 && static_cast<int>(usrc.size()) * 4 <= S;
+            }
+            if (!shared_eq && !shared_de) distinct_streams(false, uidx, usrc, ucand);
             const int U = static_cast<int>(usrc.size());
             if (S >= 64 && U * 4 <= S && share_mode != 2) {
                 const int U_pad = round_up(U, 32);
@@ -546,6 +572,13 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                     for (int k = 0; k < 4; ++k) AF_CUDA(h, sweep->mem.alloc(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
                     AF_CUDA(h, sweep->mem.alloc(&ua.st_comp, static_cast<size_t>(kStateCompressor) * U_pad));
                 }
+                if (shared_de) {  // detector front of the de-esser on the distinct (passage, detector) pairs
+                    for (int k = 0; k < 7; ++k) AF_CUDA(h, sweep->mem.alloc(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
+                    AF_CUDA(h, sweep->mem.alloc(&ua.st_deesser, static_cast<size_t>(kStateDeEsser) * U_pad));
+                    double* u_de_tab = nullptr;
+                    AF_CUDA(h, sweep->mem.alloc(&u_de_tab, static_cast<size_t>(DE_FIELDS) * U_pad));
+                    ua.de_tab = u_de_tab;
+                }
                 AF_CUDA(h, cudaMemcpyAsync(d_uidx, uidx.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_ucand, ucand.data(), U_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_usrc, usrc.data(), U_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
@@ -556,12 +589,14 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 ua.rows = d_urows;
                 ua.accum = d_uaccum;
                 ua.st_input = d_ustate;
-                ua.stage_inputs = shared_front ? 1 : 0;  // R1 runs staged
+                ua.stage_inputs = (shared_front || shared_de) ? 1 : 0;  // the shared serial kernels run staged
                 if (shared_front) {
                     a.in_det = ua.w[0];
                     a.in_wdb = ua.w[1];
                     a.in_ipk = ua.w[2];
                 }
+                if (shared_de)
+                    for (int k = 0; k < 7; ++k) a.in_de[k] = ua.w[k];
                 a.in_unique = d_uidx;
                 a.in_src = d_ubuf;
                 a.in_rows = d_urows;
@@ -569,9 +604,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 a.in_stride = U_pad;
             } else {
                 shared_eq = false;
+                shared_de = false;
             }
         }
         if (!shared_eq) shared_front = false;
+        batch->shared_deesser = shared_de;
+        shared_de_flag = shared_de;
         if (batch->shared_input.n_streams > 0) {
             batch->stages.push_back({SK_INPUT_SHARED, 0});
             if (shared_eq)
@@ -580,6 +618,10 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             if (shared_front) {
                 batch->stages.push_back({SK_SPLIT_SHARED, SP_COMP_R1});
                 batch->stages.push_back({SK_SPLIT_SHARED, SP_COMP_M2});
+            }
+            if (shared_de) {
+                batch->stages.push_back({SK_SPLIT_SHARED, SP_DE_RA});
+                batch->stages.push_back({SK_SPLIT_SHARED, SP_DE_MB});
             }
             batch->stages.push_back({SK_INPUT_FANOUT, 0});
         } else {
@@ -614,7 +656,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         if (static_cast<int>(batch->stages.size()) > kMaxStages) return set_error(h, AFSIM_UNSUPPORTED, "too many stages");
         batch->events.resize(batch->stages.size() * static_cast<size_t>(slots));
         for (cudaEvent_t& e : batch->events) AF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        sweep->kernels_per_launch += static_cast<int>(batch->stages.size()) * n_chunks + 1 + ((a.structure & ST_DEESSER) ? 1 : 0);
+        sweep->kernels_per_launch += static_cast<int>(batch->stages.size()) * n_chunks + 1 + ((a.structure & ST_DEESSER) ? 1 : 0) + (shared_de ? 1 : 0);
         sweep->batches.push_back(std::move(batch));
     }
     AF_CUDA(h, cudaEventCreate(&sweep->ev_start));
@@ -659,6 +701,7 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
         AF_CUDA(h, cudaMemsetAsync(b.shared_input.rows, 0, b.shared_rows_elems * sizeof(float), h->stream));
     }
     if (a.structure & ST_DEESSER) AF_CUDA(h, launch_expand_deesser(a, h->stream));
+    if (b.shared_deesser) AF_CUDA(h, launch_expand_deesser(b.shared_input, h->stream));
     if (a.mk_ring) AF_CUDA(h, cudaMemsetAsync(a.mk_ring, 0, b.mk_ring_elems * sizeof(double), h->stream));
     if (a.mk_rows) AF_CUDA(h, cudaMemsetAsync(a.mk_rows, 0, static_cast<size_t>(3) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream));
     if (T > 0) {
@@ -666,7 +709,7 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
         auto stream_of = [&](int i) {
             const StageDesc& sd = b.stages[i];
             if (sd.kind == SK_INPUT_FANOUT) return h->stage_stream_map[i];
-            const bool is_map = sd.kind == SK_SPLIT && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
+            const bool is_map = (sd.kind == SK_SPLIT || sd.kind == SK_SPLIT_SHARED) && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
                                                         sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT ||
                                                         sd.arg == SP_DE_MB || sd.arg == SP_DE_MC2);
             return is_map ? h->stage_stream_map[i] : h->stage_stream[i];
@@ -925,6 +968,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
     if (err == cudaSuccess)
         err = cudaMemsetAsync(a.rows, 0, static_cast<size_t>(4) * std::max(a.n_rows, 1) * a.stride * sizeof(float), h->stream);
     if (err == cudaSuccess && (a.structure & ST_DEESSER)) err = launch_expand_deesser(a, h->stream);
+    if (err == cudaSuccess && b.shared_deesser) err = launch_expand_deesser(b.shared_input, h->stream);
     if (err == cudaSuccess && a.mk_ring) err = cudaMemsetAsync(a.mk_ring, 0, b.mk_ring_elems * sizeof(double), h->stream);
     for (int c = 0; c < n_chunks && err == cudaSuccess; ++c) {
         ChunkArgs ck;

@@ -306,10 +306,11 @@ struct DeEsserTargets {  // R_c1
         return mask;
     }
 
-    // w[0..6]: ring columns at chunk start (voice dB, 3 level dB, 3 confidence targets); on return w[0] holds the
-    // rebuild masks and w[4..6] the gains
-    AF_HD void run(double* const (&w)[7], size_t stride, int n0, int len, const DeConst& table, BlockClock clk, float* rows_de,
-                   Staging stg) {
+    // in[0..6]: columns at chunk start (pitch in_stride) of voice dB, 3 level dB, 3 confidence targets -- the stream's
+    // own rings, or the shared front of its (passage, detector) pair; on return w[0] holds the rebuild masks and
+    // w[4..6] the gains (the stream's rings, pitch stride)
+    AF_HD void run(const double* const (&in)[7], size_t in_stride, double* const (&w)[7], size_t stride, int n0, int len,
+                   const DeConst& table, BlockClock clk, float* rows_de, Staging stg) {
         constexpr int U = kGroup;
         DeApplyConst k;
         k.load(table);
@@ -324,9 +325,9 @@ struct DeEsserTargets {  // R_c1
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (FULL || t0 + u < len) {
-                    const size_t o = (size_t)(t0 + u) * stride;
+                    const size_t o = (size_t)(t0 + u) * in_stride;
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, w[i] + o);
+                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, in[i] + o);
                 }
             }
         };
@@ -338,10 +339,10 @@ struct DeEsserTargets {  // R_c1
 #pragma unroll 2
             for (int u = 0; u < U; ++u) {
                 if (FULL || u < valid) {
-                    const size_t o = (size_t)(t0 + u) * stride;
-                    const double voice_db = sw[0].get(kt, u, w[0] + o);
-                    const double lv[3] = {sw[1].get(kt, u, w[1] + o), sw[2].get(kt, u, w[2] + o), sw[3].get(kt, u, w[3] + o)};
-                    const double ct[3] = {sw[4].get(kt, u, w[4] + o), sw[5].get(kt, u, w[5] + o), sw[6].get(kt, u, w[6] + o)};
+                    const size_t o = (size_t)(t0 + u) * stride, oi = (size_t)(t0 + u) * in_stride;
+                    const double voice_db = sw[0].get(kt, u, in[0] + oi);
+                    const double lv[3] = {sw[1].get(kt, u, in[1] + oi), sw[2].get(kt, u, in[2] + oi), sw[3].get(kt, u, in[3] + oi)};
+                    const double ct[3] = {sw[4].get(kt, u, in[4] + oi), sw[5].get(kt, u, in[5] + oi), sw[6].get(kt, u, in[6] + oi)};
                     double gains[3];
                     const unsigned mask = sample(voice_db, lv, ct, k, conf_lo, conf_div, gains);
                     w[0][o] = (double)mask;
@@ -420,8 +421,10 @@ struct DeEsserFilter {
         }
     }
 
-    AF_HD void run(float* x, double* const (&w)[13], size_t stride, int n0, int len, int fade_total, const CandidateParams* p,
-                   Staging stg) {
+    // xin: input signal column at chunk start (pitch xin_stride): the stream's own buf_a column (in place) or the
+    // shared input stage output of its passage; x: output column (pitch stride)
+    AF_HD void run(const float* xin, size_t xin_stride, float* x, double* const (&w)[13], size_t stride, int n0, int len,
+                   int fade_total, const CandidateParams* p, Staging stg) {
         constexpr int U = kGroup;
         int t_head = 0;
         if (n0 < fade_total) {  // head of the render: the configuration crossfade (deesser.rs:312-327), sample by sample
@@ -430,7 +433,7 @@ struct DeEsserFilter {
                 const int n = n0 + t_head;
                 const size_t o = (size_t)t_head * stride;
                 const unsigned mask = (unsigned)w[0][o];
-                float processed = x[o];
+                float processed = xin[(size_t)t_head * xin_stride];
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
                     if (mask & (1u << b)) {
@@ -458,6 +461,7 @@ struct DeEsserFilter {
             }
         }
         float* xs = x + (size_t)t_head * stride;
+        const float* xis = xin + (size_t)t_head * xin_stride;
         const double* ws[13];
 #pragma unroll
         for (int i = 0; i < 13; ++i) ws[i] = w[i] + (size_t)t_head * stride;
@@ -473,7 +477,7 @@ struct DeEsserFilter {
             for (int u = 0; u < U; ++u) {
                 if (FULL || t0 + u < m) {
                     const size_t o = (size_t)(t0 + u) * stride;
-                    sx.fetch(kt, u, xs + o);
+                    sx.fetch(kt, u, xis + (size_t)(t0 + u) * xin_stride);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) sw[i].fetch(kt, u, ws[i] + o);
                 }
@@ -490,7 +494,7 @@ struct DeEsserFilter {
                 if (FULL || u < valid) {
                     const size_t o = (size_t)(t0 + u) * stride;
                     const unsigned mask = (unsigned)sw[0].get(kt, u, ws[0] + o);
-                    float processed = sx.get(kt, u, xs + o);
+                    float processed = sx.get(kt, u, xis + (size_t)(t0 + u) * xin_stride);
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
                         if (mask & (1u << b)) {

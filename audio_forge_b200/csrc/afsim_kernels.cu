@@ -372,7 +372,7 @@ cudaError_t launch_input(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t s
     return cudaGetLastError();
 }
 cudaError_t launch_input_fanout(const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st) {
-    const int n_groups = a.in_det ? 1 : (ck.len + kFanoutGroup - 1) / kFanoutGroup;  // rows and statistics only
+    const int n_groups = (a.in_det || a.in_de[0]) ? 1 : (ck.len + kFanoutGroup - 1) / kFanoutGroup;  // rows and statistics only
     const dim3 grid((unsigned)((a.n_streams + 31) / 32), (unsigned)((n_groups + kMapWarps - 1) / kMapWarps));
     k_input_fanout<<<grid, 32 * kMapWarps, 0, st>>>(a, ck);
     return cudaGetLastError();

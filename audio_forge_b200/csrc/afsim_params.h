@@ -176,6 +176,9 @@ struct BatchArgs {
     // shared compressor front (a compressor grid over one EQ setting): sidechain signal, detector weight (dB) and
     // instantaneous peak (dB) of the distinct (passage, EQ) pairs -- what R1 + M2 produce -- read by every stream's
     // compressor instead of being recomputed; the streams then also read the EQ output itself from in_src
+    // shared de-esser front (de-esser first, one detector configuration per passage): voice dB, 3 band levels dB and
+    // 3 confidence targets of the distinct (passage, detector) pairs -- what R_a + M_b produce
+    const double* in_de[7];       // [ring_rows][in_stride] each, or nullptr
     const double* in_det;         // [ring_rows][in_stride], or nullptr
     const double* in_wdb;
     const double* in_ipk;

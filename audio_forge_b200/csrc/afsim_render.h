@@ -130,7 +130,7 @@ AF_HD void body_input_fanout(const BatchArgs& a, const ChunkArgs& ck, int s, int
     const uint32_t u = a.in_unique[s];
     const int t0 = g * kFanoutGroup;
     const int valid = ck.len - t0 < kFanoutGroup ? ck.len - t0 : kFanoutGroup;
-    if (!a.in_det) {  // with a shared compressor front the streams read the shared EQ output in place
+    if (!a.in_det && !a.in_de[0]) {  // with a shared compressor / de-esser front the streams read the shared signal in place
         const float* src = a.in_src + (size_t)(ck.row0 + t0) * ustride + u;
         float* dst = a.buf_a + (size_t)(ck.row0 + t0) * stride + s;
         for (int t = 0; t < valid; ++t) dst[(size_t)t * stride] = src[(size_t)t * ustride];
@@ -475,7 +475,15 @@ AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging st
     const DeConst k{a.de_tab + s, stride};
     double* const w[7] = {col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s),
                           col_at(a.w[4], a, ck, s), col_at(a.w[5], a, ck, s), col_at(a.w[6], a, ck, s)};
-    st.run(w, stride, ck.n0, ck.len, k, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    if (a.in_de[0]) {  // levels and confidence targets of the shared front
+        const size_t o = (size_t)ck.row0 * (size_t)a.in_stride + a.in_unique[s];
+        const double* const in[7] = {a.in_de[0] + o, a.in_de[1] + o, a.in_de[2] + o, a.in_de[3] + o,
+                                     a.in_de[4] + o, a.in_de[5] + o, a.in_de[6] + o};
+        st.run(in, (size_t)a.in_stride, w, stride, ck.n0, ck.len, k, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    } else {
+        const double* const in[7] = {w[0], w[1], w[2], w[3], w[4], w[5], w[6]};
+        st.run(in, stride, w, stride, ck.n0, ck.len, k, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    }
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync(io);
@@ -503,7 +511,12 @@ AF_HD void body_de_rc3(const BatchArgs& a, const ChunkArgs& ck, int s, Staging s
     double* w[13];
 #pragma unroll
     for (int i = 0; i < 13; ++i) w[i] = col_at(a.w[i], a, ck, s);
-    st.run(col_at(a.buf_a, a, ck, s), w, stride, ck.n0, ck.len, a.fade_samples, &p, stg);
+    float* x = col_at(a.buf_a, a, ck, s);
+    if (a.in_de[0])  // the de-esser is the first stage: its input is the shared input stage output of the passage
+        st.run(a.in_src + (size_t)ck.row0 * (size_t)a.in_stride + a.in_unique[s], (size_t)a.in_stride, x, w, stride, ck.n0, ck.len,
+               a.fade_samples, &p, stg);
+    else
+        st.run(x, stride, x, w, stride, ck.n0, ck.len, a.fade_samples, &p, stg);
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync(io);

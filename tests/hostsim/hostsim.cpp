@@ -238,8 +238,9 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     std::vector<StreamAccum> uaccum;
     const bool shared_eq = (split & 32) != 0;  // with bit 4: the EQ runs on the distinct (passage, EQ) pairs as well
     const bool shared_front = (split & 64) != 0 && shared_eq;  // ... and so does the compressor front (fused compressor)
-    std::vector<std::vector<double>> uw(4);
-    std::vector<double> ust_comp;
+    const bool shared_de = (split & 128) != 0;  // with bit 4: the de-esser's detector front runs on the distinct pairs
+    std::vector<std::vector<double>> uw(7);
+    std::vector<double> ust_comp, ust_de, ude_tab;
     std::vector<double> ust_eq;
     uint32_t shared_max_sections = 0;
     if (split & 16) {
@@ -247,6 +248,10 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
             size_t u = 0;
             while (u < usrc.size() &&
                    !(usrc[u] == src_off[s] &&
+                     (!shared_de || (std::memcmp(params[ucand[u]].de + DE_DET, params[cand[s]].de + DE_DET, 30 * 8) == 0 &&
+                                     params[ucand[u]].de[DE_DET_ATTACK] == params[cand[s]].de[DE_DET_ATTACK] &&
+                                     params[ucand[u]].de[DE_DET_RELEASE] == params[cand[s]].de[DE_DET_RELEASE] &&
+                                     std::memcmp(params[ucand[u]].de_det0, params[cand[s]].de_det0, sizeof params[0].de_det0) == 0)) &&
                      (!shared_eq || (std::memcmp(params[ucand[u]].eq, params[cand[s]].eq, sizeof params[0].eq) == 0 &&
                                      params[ucand[u]].n_sections == params[cand[s]].n_sections &&
                                      (params[ucand[u]].flags & (LF_EQ_FADE | LF_C_SIDECHAIN)) ==
@@ -289,6 +294,18 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
             a.in_wdb = ua.w[1];
             a.in_ipk = ua.w[2];
         }
+        if (shared_de) {
+            for (int k = 0; k < 7; ++k) {
+                uw[k].assign(static_cast<size_t>(a.ring_rows) * U_pad, 0.0);
+                ua.w[k] = uw[k].data();
+                a.in_de[k] = ua.w[k];
+            }
+            ust_de.assign(static_cast<size_t>(kStateDeEsser) * U_pad, 0.0);
+            ude_tab.assign(static_cast<size_t>(DE_FIELDS) * U_pad, 0.0);
+            ua.st_deesser = ust_de.data();
+            ua.de_tab = ude_tab.data();
+            for (int u = 0; u < U; ++u) body_expand_deesser(ua, u);
+        }
         a.in_unique = uidx.data();
         a.in_src = ubuf.data();
         a.in_rows = urows.data();
@@ -300,9 +317,15 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     std::vector<unsigned char> staging_bytes(std::max(kStagingBytesPerLane, std::max(kDeRc1StagingBytesPerLane, kDeRc3StagingBytesPerLane)) + 64);
     auto run_deesser = [&](const ChunkArgs& ck) {
         const Staging st{(split & 8) ? nullptr : staging_bytes.data(), 1, 0, 0};  // split bit 3: direct (unstaged) loads
-        for (int s = 0; s < S; ++s) body_de_ra(a, ck, s, st);
-        for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
-            for (int s = 0; s < S; ++s) body_de_mb(a, ck, s, g);
+        if ((split & 16) && shared_de) {
+            for (int u = 0; u < ua.n_streams; ++u) body_de_ra(ua, ck, u, st);
+            for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
+                for (int u = 0; u < ua.n_streams; ++u) body_de_mb(ua, ck, u, g);
+        } else {
+            for (int s = 0; s < S; ++s) body_de_ra(a, ck, s, st);
+            for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
+                for (int s = 0; s < S; ++s) body_de_mb(a, ck, s, g);
+        }
         for (int s = 0; s < S; ++s) body_de_rc(a, ck, s, st);
         for (int g = (ck.len + kDeRebuildGroup - 1) / kDeRebuildGroup; g >= 0; --g)
             for (int s = 0; s < S; ++s) body_de_mc2(a, ck, s, g);

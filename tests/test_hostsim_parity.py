@@ -87,6 +87,27 @@ def test_shared_input_and_eq_prefix_fan_out():
             _check_pairs(passages, cand_list, pp, pc, got, audio)
 
 
+def test_shared_deesser_front_fan_out():
+    """De-esser first with one detector configuration: its detector biquads / envelopes / levels / confidence targets
+    (R_a + M_b) run once per distinct passage (split bits 4 + 7); per-stream targets, rebuilds and filters read them."""
+    n = 40 * 480 - 77
+    passages = [golden_chain_input(blocks=40)[:n].copy(), speech_like(n, seed=71, level=0.8)]
+    bands, overrides = CASES["golden_like"]  # de-esser auto mode, de-esser before the EQ
+    cand_list = [candidate(bands, **dict(overrides, deesser_auto_amount=amount, deesser_max_reduction_db=red,
+                                         compressor_threshold_db=-30.0 + 4 * i))
+                 for i, (amount, red) in enumerate([(0.3, 6.0), (0.9, 12.0), (0.6, 3.0)])]
+    cand_list.append(candidate(bands, **dict(overrides, deesser_auto_enabled=False, deesser_threshold_db=-45.0)))
+    cands = candidate_array(cand_list)
+    pp = np.array([p for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+    pc = np.array([c for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
+    for split, chunk in ((16 | 128, 1000), (16 | 128 | 7, 520), (16 | 128 | 8, 1024)):
+        got, audio, rows = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=chunk, slots=2, split=split, want_audio=True,
+                                               want_rows=True)
+        _check_pairs(passages, cand_list, pp, pc, got, audio)
+    de_max = max(got[i].deesser_gain_reduction_db for i in range(pp.size))
+    assert de_max > 0.05  # the de-esser really worked on these passages
+
+
 def _check_pairs(passages, cand_list, pp, pc, got, audio):
     for i in range(pp.size):
         m0, a0, _ = pyoracle.chain_render(passages[pp[i]], FS, cand_list[pc[i]].bands, cand_list[pc[i]].settings,
