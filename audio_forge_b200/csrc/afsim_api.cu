@@ -565,8 +565,9 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&d_uaccum, U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_ustate, static_cast<size_t>(kStateInput) * U_pad));
                 if (shared_eq) AF_CUDA(h, sweep->mem.alloc(&ua.st_eq, static_cast<size_t>(kStateEqPerSection * kMaxSections) * U_pad));
-                // the compressor front as well, when the compressor follows the EQ directly and runs fused per stream
-                shared_front = shared_eq && !split && !auto_makeup && (a.structure & ST_COMPRESSOR) && !(a.structure & ST_DEESSER) &&
+                // the compressor front as well, when the compressor follows the EQ directly (the makeup stage R7 works in
+                // place on the stream's own signal: auto-makeup batches keep their own front)
+                shared_front = shared_eq && !auto_makeup && (a.structure & ST_COMPRESSOR) && !(a.structure & ST_DEESSER) &&
                                share_mode == 1;
                 if (shared_front) {
                     for (int k = 0; k < 4; ++k) AF_CUDA(h, sweep->mem.alloc(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
@@ -640,7 +641,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         if (a.structure & ST_COMPRESSOR) {
             if (split || auto_makeup) {
                 for (int op : {SP_COMP_R1, SP_COMP_M2, SP_COMP_R3, SP_COMP_M4, SP_COMP_R5, SP_COMP_M6})
-                    batch->stages.push_back({SK_SPLIT, op});
+                    if (!(shared_front && (op == SP_COMP_R1 || op == SP_COMP_M2)))  // rendered once per (passage, EQ) pair
+                        batch->stages.push_back({SK_SPLIT, op});
                 if (auto_makeup) batch->stages.push_back({SK_SPLIT, SP_COMP_R7});
             } else {
                 batch->stages.push_back({SK_COMPRESSOR, 0});

@@ -375,7 +375,13 @@ AF_HD void body_comp_r3(const BatchArgs& a, const ChunkArgs& ck, int s, Staging 
         StateIO<false> io{table, stride};
         st.sync_r3(io);
     }
-    st.run_r3(col_at(a.w[0], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride, ck.len, stg);
+    if (a.in_det) {  // sidechain signal and instantaneous peak of the shared compressor front
+        const size_t o = (size_t)ck.row0 * (size_t)a.in_stride + a.in_unique[s];
+        st.run_r3(a.in_det + o, a.in_ipk + o, (size_t)a.in_stride, col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride, ck.len, stg);
+    } else {
+        st.run_r3(col_at(a.w[0], a, ck, s), col_at(a.w[2], a, ck, s), stride, col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s), stride,
+                  ck.len, stg);
+    }
     if (ck.n0 + ck.len < a.n_samples) {
         StateIO<true> io{table, stride};
         st.sync_r3(io);
@@ -386,7 +392,12 @@ AF_HD void body_comp_m4(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
     st.init(stream_params(a, s));
-    st.map_m4(col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
+    double* w1 = col_at(a.w[1], a, ck, s, t0);
+    if (a.in_det)
+        st.map_m4(a.in_wdb + (size_t)(ck.row0 + t0) * (size_t)a.in_stride + a.in_unique[s], (size_t)a.in_stride, w1,
+                  col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
+    else
+        st.map_m4(w1, (size_t)a.stride, w1, col_at(a.w[2], a, ck, s, t0), col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
 }
 AF_HD void body_comp_r5(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
@@ -413,7 +424,14 @@ AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     if (a.structure & ST_AUTO_MAKEUP)
         st.map_m6_gain(col_at(a.w[1], a, ck, s, t0), (size_t)a.stride, valid);
     else
-        st.map_m6(col_at(a.w[1], a, ck, s, t0), col_at(a.buf_a, a, ck, s, t0), (size_t)a.stride, valid);
+    {
+        float* x = col_at(a.buf_a, a, ck, s, t0);
+        if (a.in_det)  // the compressor's input is the shared EQ output
+            st.map_m6(col_at(a.w[1], a, ck, s, t0), a.in_src + (size_t)(ck.row0 + t0) * (size_t)a.in_stride + a.in_unique[s],
+                      (size_t)a.in_stride, x, (size_t)a.stride, valid);
+        else
+            st.map_m6(col_at(a.w[1], a, ck, s, t0), x, (size_t)a.stride, x, (size_t)a.stride, valid);
+    }
 }
 // R7 (auto-makeup batches): apply gain reduction x makeup, run the loudness meter, step the makeup at block ends
 AF_HD void body_comp_r7(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {

@@ -248,8 +248,10 @@ struct CompSplit : CompressorStage {
         store_tile(w2, stride, valid, ipk);
     }
 
-    // R3: peak (dB domain) and RMS envelopes.  (w0 det, w2 ipk) -> w2 = peak_env, w3 = rms_env
-    AF_HD void run_r3(const double* w0, double* w2, double* w3, size_t stride, int len, Staging stg) {
+    // R3: peak (dB domain) and RMS envelopes.  (det, ipk: the stream's w0 / w2 columns, or the shared compressor front
+    // of its (passage, EQ) pair, pitch in_stride) -> w2 = peak_env, w3 = rms_env
+    AF_HD void run_r3(const double* det_in, const double* ipk_in, size_t in_stride, double* w2, double* w3, size_t stride, int len,
+                      Staging stg) {
         constexpr int U = kGroup;
         const StageRing<double> sdet = stg.ring<double>();
         const StageRing<double> sipk = stg.ring<double>();
@@ -259,8 +261,8 @@ struct CompSplit : CompressorStage {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (FULL || t0 + u < len) {
-                    async_copy(sdet.at(k, u), w0 + (size_t)(t0 + u) * stride);
-                    async_copy(sipk.at(k, u), (const double*)w2 + (size_t)(t0 + u) * stride);
+                    async_copy(sdet.at(k, u), det_in + (size_t)(t0 + u) * in_stride);
+                    async_copy(sipk.at(k, u), ipk_in + (size_t)(t0 + u) * in_stride);
                 }
             }
         };
@@ -290,12 +292,14 @@ struct CompSplit : CompressorStage {
         pipelined_tiles(len, issue, body);
     }
 
-    // M4: blended detector (:681-686) + gain computer (:657-678).  (w2 pk, w3 rms, w1 wdb) -> w1 = target GR
-    AF_HD void map_m4(double* w1, const double* w2, const double* w3, size_t stride, int valid) const {
+    // M4: blended detector (:681-686) + gain computer (:657-678).  (w2 pk, w3 rms, wdb) -> w1 = target GR
+    // (wdb_in: the stream's w1 column or the shared front's, pitch wdb_stride)
+    AF_HD void map_m4(const double* wdb_in, size_t wdb_stride, double* w1, const double* w2, const double* w3, size_t stride,
+                      int valid) const {
         double pk[kCompMapGroup], rms[kCompMapGroup], wdb[kCompMapGroup], tgt[kCompMapGroup];
         load_tile(w2, stride, valid, pk);
         load_tile(w3, stride, valid, rms);
-        load_tile((const double*)w1, stride, valid, wdb);
+        load_tile(wdb_in, wdb_stride, valid, wdb);
 #pragma unroll
         for (int u = 0; u < kCompMapGroup; ++u) {
             tgt[u] = gain_computer(lin_to_db(0.6 * db_to_lin(pk[u]) + 0.4 * rms_linear(rms[u]), 1e-10) + wdb[u]);
@@ -358,12 +362,12 @@ struct CompSplit : CompressorStage {
         pipelined_tiles(len, issue, body);
     }
 
-    // M6: apply gain.  (w1 gr, x) -> x
-    AF_HD void map_m6(const double* w1, float* x, size_t stride, int valid) const {
+    // M6: apply gain.  (w1 gr, x_in: the stream's own column or the shared EQ output, pitch x_stride) -> x
+    AF_HD void map_m6(const double* w1, const float* x_in, size_t x_stride, float* x, size_t stride, int valid) const {
         double grv[kCompMapGroup];
         float xin[kCompMapGroup], y[kCompMapGroup];
         load_tile(w1, stride, valid, grv);
-        load_tile((const float*)x, stride, valid, xin);
+        load_tile(x_in, x_stride, valid, xin);
 #pragma unroll
         for (int u = 0; u < kCompMapGroup; ++u) {
             const double gain = db_to_lin(-grv[u]) * makeup_lin;

@@ -390,10 +390,12 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         const int n_groups = (ck.len + kGroup - 1) / kGroup + 1;  // one empty group past the end on purpose
         if (a.structure & ST_COMPRESSOR) {
             if ((split & 1) || auto_makeup) {
-                for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s, stg);
                 const int n_cgroups = (ck.len + kCompMapGroup - 1) / kCompMapGroup + 1;
-                for (int g = n_cgroups - 1; g >= 0; --g)  // any order: the maps are independent
-                    for (int s = 0; s < S; ++s) body_comp_m2(a, ck, s, g);
+                if (!((split & 16) && shared_front)) {  // else: the shared front already ran on the distinct pairs
+                    for (int s = 0; s < S; ++s) body_comp_r1(a, ck, s, stg);
+                    for (int g = n_cgroups - 1; g >= 0; --g)  // any order: the maps are independent
+                        for (int s = 0; s < S; ++s) body_comp_m2(a, ck, s, g);
+                }
                 for (int s = 0; s < S; ++s) body_comp_r3(a, ck, s, stg);
                 for (int g = 0; g < n_cgroups; ++g)
                     for (int s = 0; s < S; ++s) body_comp_m4(a, ck, s, g);

@@ -82,7 +82,7 @@ def test_shared_input_and_eq_prefix_fan_out():
         cands = candidate_array(cand_list)
         pp = np.array([p for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
         pc = np.array([c for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
-        for split, chunk in ((48, 1000), (48 | 7, 512), (112, 1000), (112 | 6, 520)):  # 112: + shared compressor front
+        for split, chunk in ((48, 1000), (48 | 7, 512), (112, 1000), (112 | 6, 520), (112 | 7, 1024), (112 | 15, 264)):  # 112: + shared compressor front
             got, audio, _ = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=chunk, slots=2, split=split, want_audio=True)
             _check_pairs(passages, cand_list, pp, pc, got, audio)
 
