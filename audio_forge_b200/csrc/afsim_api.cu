@@ -12,8 +12,10 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/afsim.h"
@@ -292,10 +294,92 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         const CandidatePlan& pl = plans[candidate_of(i)];
         groups[Key(pl.structure, pl.lookahead, pl.input_stage, sweep->pair_len[i])].push_back(static_cast<uint32_t>(i));
     }
-    for (auto& kv : groups) {
+    // EQ class of a candidate: same sections, coefficients, fade flag (and sidechain flag, for the compressor front)
+    auto eq_class_key = [](const CandidateParams& p) {
+        std::vector<unsigned char> key(sizeof p.eq + 8);
+        std::memcpy(key.data(), p.eq, sizeof p.eq);
+        const uint32_t meta[2] = {p.n_sections, p.flags & (LF_EQ_FADE | LF_C_SIDECHAIN)};
+        std::memcpy(key.data() + sizeof p.eq, meta, 8);
+        return key;
+    };
+    // Large compressor grids over few (passage, EQ) pairs are cut into pieces of up to AFSIM_SUBBATCH streams: a piece
+    // runs the R/M split kernels with the shared EQ + compressor front, which is faster than the fused kernels on the
+    // whole group (C3, 131072 streams: 19.9 -> see DESIGN section 6).  The pieces run one after another (run_batch
+    // joins on the handle's stream), so they share one set of ring buffers (`ring_scratch`).
+    struct Piece {
+        Key key;
+        std::vector<uint32_t> members;
+        bool share_rings = false, first = false;
+    };
+    std::vector<Piece> pieces;
+    {
+        const int sub = env_int("AFSIM_SUBBATCH", 16384);
+        const int split_mode = env_int("AFSIM_SPLIT", 0);
+        for (auto& kv : groups) {
+            std::vector<uint32_t>& members = kv.second;
+            const uint32_t structure = std::get<0>(kv.first);
+            const int S = static_cast<int>(members.size());
+            bool cut = S > sub && sub <= 16384 && split_mode != 1 && env_int("AFSIM_SHARED_INPUT", 1) == 1 &&
+                       (structure & ST_COMPRESSOR) && (structure & ST_EQ) &&
+                       !(structure & (ST_DEESSER | ST_AUTO_MAKEUP | ST_INPUT_TRUE_PEAK));
+            if (cut) {  // few distinct (passage, EQ) pairs?
+                std::map<std::vector<unsigned char>, uint32_t> classes;
+                std::vector<int64_t> class_of(plans.size(), -1);
+                std::set<std::pair<uint32_t, uint32_t>> distinct;
+                for (uint32_t i : members) {
+                    const uint32_t c = candidate_of(i);
+                    if (class_of[c] < 0)
+                        class_of[c] = classes.emplace(eq_class_key(plans[c].params), static_cast<uint32_t>(classes.size())).first->second;
+                    distinct.emplace(passage_of(i), static_cast<uint32_t>(class_of[c]));
+                    if (distinct.size() * 4 > static_cast<size_t>(sub)) break;
+                }
+                cut = distinct.size() * 4 <= static_cast<size_t>(sub);
+            }
+            if (!cut) {
+                pieces.push_back({kv.first, std::move(members), false, false});
+                continue;
+            }
+            // the streams of a passage stay together (so that a piece shares as much as the group did)
+            std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) { return passage_of(x) < passage_of(y); });
+            const int n_pieces = (S + sub - 1) / sub;
+            const int piece_len = round_up((S + n_pieces - 1) / n_pieces, 32);
+            for (int first = 0; first < S; first += piece_len) {
+                Piece pc;
+                pc.key = kv.first;
+                pc.members.assign(members.begin() + first, members.begin() + std::min(S, first + piece_len));
+                pc.share_rings = true;
+                pc.first = first == 0;
+                pieces.push_back(std::move(pc));
+            }
+        }
+    }
+    std::vector<std::pair<size_t, void*>> ring_scratch;  // ring buffers shared by the pieces of one cut group
+    size_t ring_next = 0;
+    for (Piece& piece : pieces) {
         // Streams with the same EQ section count share warps: an EQ slice past a warp's last section is skipped
         // by the whole warp (body_eq returns early), instead of running as a predicated pass-through.
-        std::vector<uint32_t>& members = kv.second;
+        std::vector<uint32_t>& members = piece.members;
+        const Key& piece_key = piece.key;
+        if (piece.first) ring_scratch.clear();
+        ring_next = 0;
+        const bool share_rings = piece.share_rings;
+        auto alloc_ring = [&](auto** out, size_t count) -> cudaError_t {
+            typedef typename std::remove_pointer<typename std::remove_pointer<decltype(out)>::type>::type T;
+            if (!share_rings) return sweep->mem.alloc(out, count);
+            const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+            if (ring_next < ring_scratch.size() && ring_scratch[ring_next].first >= bytes) {
+                *out = static_cast<T*>(ring_scratch[ring_next++].second);
+                return cudaSuccess;
+            }
+            const cudaError_t err = sweep->mem.alloc(out, count);
+            if (err != cudaSuccess) return err;
+            if (ring_next < ring_scratch.size())
+                ring_scratch[ring_next] = std::make_pair(bytes, static_cast<void*>(*out));
+            else
+                ring_scratch.emplace_back(bytes, static_cast<void*>(*out));
+            ++ring_next;
+            return cudaSuccess;
+        };
         std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) {
             return plans[candidate_of(x)].params.n_sections < plans[candidate_of(y)].params.n_sections;
         });
@@ -303,10 +387,10 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         BatchArgs& a = batch->args;
         const int S = static_cast<int>(members.size());
         const int S_pad = round_up(S, 32);
-        const int T = static_cast<int>(std::get<3>(kv.first));
-        a.structure = std::get<0>(kv.first);
-        a.lookahead = static_cast<int>(std::get<1>(kv.first));
-        a.input_stage = static_cast<int>(std::get<2>(kv.first));
+        const int T = static_cast<int>(std::get<3>(piece_key));
+        a.structure = std::get<0>(piece_key);
+        a.lookahead = static_cast<int>(std::get<1>(piece_key));
+        a.input_stage = static_cast<int>(std::get<2>(piece_key));
         a.n_streams = S;
         a.stride = S_pad;
         a.n_samples = T;
@@ -373,6 +457,15 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         AF_CUDA(h, cudaMemcpyAsync(d_src, src_off.data(), S_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
         AF_CUDA(h, cudaMemcpyAsync(d_aoff, audio_off.data(), S_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
         AF_CUDA(h, cudaStreamSynchronize(h->stream));
+        {  // the map kernels' constants, stream-minor (MapField)
+            std::vector<double> tab(static_cast<size_t>(MT_FIELDS) * S_pad);
+            for (int s = 0; s < S_pad; ++s) fill_map_tab(tab.data(), S_pad, s, plans[cand[s]].params);
+            double* d_tab = nullptr;
+            AF_CUDA(h, sweep->mem.alloc(&d_tab, tab.size()));
+            AF_CUDA(h, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            AF_CUDA(h, cudaStreamSynchronize(h->stream));
+            a.map_tab = d_tab;
+        }
         a.cand = d_cand;
         a.pair = d_pair;
         a.src_off = d_src;
@@ -384,13 +477,13 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         const int split_mode = env_int("AFSIM_SPLIT", 0);
         const bool split = split_mode == 2 || (split_mode != 1 && S <= 16384);
         const size_t ring_elems = static_cast<size_t>(a.ring_rows) * sp;
-        AF_CUDA(h, sweep->mem.alloc(&a.buf_a, ring_elems));
+        AF_CUDA(h, alloc_ring(&a.buf_a, ring_elems));
         if (a.structure & ST_LIMITER) {
-            AF_CUDA(h, sweep->mem.alloc(&a.buf_b, ring_elems));
+            AF_CUDA(h, alloc_ring(&a.buf_b, ring_elems));
             AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
             if (split) {
-                AF_CUDA(h, sweep->mem.alloc(&a.buf_c, ring_elems));
-                AF_CUDA(h, sweep->mem.alloc(&a.buf_p, ring_elems));
+                AF_CUDA(h, alloc_ring(&a.buf_c, ring_elems));
+                AF_CUDA(h, alloc_ring(&a.buf_p, ring_elems));
             } else {
                 AF_CUDA(h, sweep->mem.alloc(&a.lim_sfx, static_cast<size_t>(a.lookahead + 1) * sp));
             }
@@ -401,7 +494,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             if (split && (a.structure & ST_LIMITER)) n_w = 1;
             if ((split || auto_makeup) && (a.structure & ST_COMPRESSOR)) n_w = 4;
             if (a.structure & ST_DEESSER) n_w = 13;  // the de-esser is always R/M split (afsim_deesser.h)
-            for (int k = 0; k < n_w; ++k) AF_CUDA(h, sweep->mem.alloc(&a.w[k], ring_elems));
+            for (int k = 0; k < n_w; ++k) AF_CUDA(h, alloc_ring(&a.w[k], ring_elems));
         }
         AF_CUDA(h, sweep->mem.alloc(&a.st_input, kStateInput * sp));
         AF_CUDA(h, sweep->mem.alloc(&a.st_tp, kStateTruePeak * sp));
@@ -485,12 +578,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 for (int s = 0; s < S; ++s) {
                     if (classified[cand[s]]) continue;  // once per candidate, not per stream
                     classified[cand[s]] = true;
-                    const CandidateParams& p = plans[cand[s]].params;
-                    std::vector<unsigned char> key(sizeof p.eq + 8);
-                    std::memcpy(key.data(), p.eq, sizeof p.eq);
-                    const uint32_t meta[2] = {p.n_sections, p.flags & (LF_EQ_FADE | LF_C_SIDECHAIN)};
-                    std::memcpy(key.data() + sizeof p.eq, meta, 8);
-                    eq_class_of[cand[s]] = eq_classes.emplace(std::move(key), static_cast<uint32_t>(eq_classes.size())).first->second;
+                    eq_class_of[cand[s]] = eq_classes.emplace(eq_class_key(plans[cand[s]].params), static_cast<uint32_t>(eq_classes.size())).first->second;
                 }
             }
             // de-esser first: its detector front (R_a + M_b) depends on the band split and the fixed detector time
@@ -560,7 +648,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 AF_CUDA(h, sweep->mem.alloc(&d_uidx, S_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_ucand, U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_usrc, U_pad));
-                AF_CUDA(h, sweep->mem.alloc(&d_ubuf, static_cast<size_t>(a.ring_rows) * U_pad));
+                AF_CUDA(h, alloc_ring(&d_ubuf, static_cast<size_t>(a.ring_rows) * U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_urows, batch->shared_rows_elems));
                 AF_CUDA(h, sweep->mem.alloc(&d_uaccum, U_pad));
                 AF_CUDA(h, sweep->mem.alloc(&d_ustate, static_cast<size_t>(kStateInput) * U_pad));
@@ -570,7 +658,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 shared_front = shared_eq && !auto_makeup && (a.structure & ST_COMPRESSOR) && !(a.structure & ST_DEESSER) &&
                                share_mode == 1;
                 if (shared_front) {
-                    for (int k = 0; k < 4; ++k) AF_CUDA(h, sweep->mem.alloc(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
+                    for (int k = 0; k < 4; ++k) AF_CUDA(h, alloc_ring(&ua.w[k], static_cast<size_t>(a.ring_rows) * U_pad));
                     AF_CUDA(h, sweep->mem.alloc(&ua.st_comp, static_cast<size_t>(kStateCompressor) * U_pad));
                 }
                 if (shared_de) {  // detector front of the de-esser on the distinct (passage, detector) pairs
@@ -580,6 +668,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                     AF_CUDA(h, sweep->mem.alloc(&u_de_tab, static_cast<size_t>(DE_FIELDS) * U_pad));
                     ua.de_tab = u_de_tab;
                 }
+                std::vector<double> utab(static_cast<size_t>(MT_FIELDS) * U_pad);
+                for (int u = 0; u < U_pad; ++u) fill_map_tab(utab.data(), U_pad, u, plans[ucand[u]].params);
+                double* d_utab = nullptr;
+                AF_CUDA(h, sweep->mem.alloc(&d_utab, utab.size()));
+                AF_CUDA(h, cudaMemcpyAsync(d_utab, utab.data(), utab.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                ua.map_tab = d_utab;
                 AF_CUDA(h, cudaMemcpyAsync(d_uidx, uidx.data(), S_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_ucand, ucand.data(), U_pad * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
                 AF_CUDA(h, cudaMemcpyAsync(d_usrc, usrc.data(), U_pad * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));

@@ -88,6 +88,21 @@ struct CandidateParams {
     double in_hp[5];
 };
 
+// Constants the MAP kernels need, stream-minor ([MT_FIELDS][S_pad] doubles; the float / flag fields are exactly
+// representable): a map thread handles a few samples, so gathering its constants from the candidate's 2.5 KB
+// CandidateParams (one 32-byte sector per lane and field) costs as much L1 / L2 traffic as its samples do; from
+// this table the loads coalesce.  The serial kernels read CandidateParams once per chunk and keep doing so.
+enum MapField { MT_THRESHOLD, MT_FACTOR, MT_KNEE, MT_MAKEUP_LIN, MT_L_CEIL, MT_TP_CEIL, MT_FLAGS, MT_FIELDS };
+inline void fill_map_tab(double* tab, size_t stride, size_t s, const CandidateParams& p) {
+    tab[MT_THRESHOLD * stride + s] = p.c_threshold;
+    tab[MT_FACTOR * stride + s] = p.c_factor;
+    tab[MT_KNEE * stride + s] = p.c_knee;
+    tab[MT_MAKEUP_LIN * stride + s] = p.c_makeup_lin;
+    tab[MT_L_CEIL * stride + s] = p.l_ceil;
+    tab[MT_TP_CEIL * stride + s] = static_cast<double>(p.tp_ceil);
+    tab[MT_FLAGS * stride + s] = static_cast<double>(p.flags);
+}
+
 // Stage set of a batch; every stream of a batch shares it.
 enum StructureFlag : uint32_t {
     ST_DEESSER = 1u << 0,
@@ -184,6 +199,7 @@ struct BatchArgs {
     const double* in_ipk;
     const double* eq_default;     // [10][5] constructor coefficients of the default bands (dsp/eq.rs:125-140)
     const double* de_tab;         // [DE_FIELDS][S_pad] de-esser constants, stream-minor (coalesced reads)
+    const double* map_tab;        // [MT_FIELDS][S_pad] constants of the map kernels, stream-minor (MapField)
     const struct CleanupConst* cleanup;  // sample-rate constants of the adaptive input cleanup (afsim_cleanup.h)
     void* metrics;                // AfChainMetrics[n_pairs of the sweep], indexed by pair[s]
     float* fin_scratch;           // per-block finalize workspace when it does not fit shared memory

@@ -362,7 +362,7 @@ AF_HD void body_comp_m2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
     if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
-    st.init(stream_params(a, s));
+    st.init_map(a.map_tab + s, (size_t)a.stride);
     st.map_m2(col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
               col_at(a.w[3], a, ck, s, t0), (size_t)a.stride, valid);
 }
@@ -391,7 +391,7 @@ AF_HD void body_comp_m4(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
     if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
-    st.init(stream_params(a, s));
+    st.init_map(a.map_tab + s, (size_t)a.stride);
     double* w1 = col_at(a.w[1], a, ck, s, t0);
     if (a.in_det)
         st.map_m4(a.in_wdb + (size_t)(ck.row0 + t0) * (size_t)a.in_stride + a.in_unique[s], (size_t)a.in_stride, w1,
@@ -420,7 +420,7 @@ AF_HD void body_comp_m6(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
     if (!group_span(ck, g, &t0, &valid, kCompMapGroup)) return;
     CompSplit st;
-    st.init(stream_params(a, s));
+    st.init_map(a.map_tab + s, (size_t)a.stride);
     if (a.structure & ST_AUTO_MAKEUP)
         st.map_m6_gain(col_at(a.w[1], a, ck, s, t0), (size_t)a.stride, valid);
     else
@@ -545,7 +545,7 @@ AF_HD void body_lim_m(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
     if (!group_span(ck, g, &t0, &valid, kLimGroup)) return;
     limiter_targets(a.buf_a + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, a.lookahead,
-                    stream_params(a, s).l_ceil, col_at(a.w[0], a, ck, s, t0));
+                    a.map_tab[(size_t)MT_L_CEIL * a.stride + s], col_at(a.w[0], a, ck, s, t0));
 }
 AF_HD void body_lim_r(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
     const size_t stride = (size_t)a.stride;
@@ -576,7 +576,7 @@ AF_HD void body_tp_fir_in(const BatchArgs& a, const ChunkArgs& ck, int s, int g,
     fir_group_peaks(a.buf_b + s, (size_t)a.stride, a.ring_rows, ck.row0, t0, ck.n0 + t0, valid, fir, pk);
     // feed-forward part of dsp/true_peak.rs:349-354: the target gain of every sample, and the running
     // maximum of the input true peak (order independent -> atomic)
-    const float ceil_lin = stream_params(a, s).tp_ceil;
+    const float ceil_lin = (float)a.map_tab[(size_t)MT_TP_CEIL * a.stride + s];
     float tgt[kFirChunk];
     float m = 0.0f;
 #pragma unroll

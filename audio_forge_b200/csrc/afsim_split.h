@@ -217,6 +217,18 @@ struct CompSplit : CompressorStage {
         pipelined_tiles(len, issue, body);
     }
 
+    // The constants the maps use (gain computer, makeup, sidechain flag) from the batch's stream-minor table
+    // (`tab` points at the stream's column of BatchArgs::map_tab); the other members stay unset.
+    AF_HD void init_map(const double* tab, size_t stride) {
+        threshold = tab[MT_THRESHOLD * stride];
+        factor = tab[MT_FACTOR * stride];
+        knee = tab[MT_KNEE * stride];
+        knee_start = threshold - knee / 2.0;
+        knee_end = threshold + knee / 2.0;
+        makeup_lin = tab[MT_MAKEUP_LIN * stride];
+        sidechain = (static_cast<uint32_t>(tab[MT_FLAGS * stride]) & LF_C_SIDECHAIN) != 0;
+    }
+
     // M2: detector weight in dB and instantaneous peak in dB.  w1 <- wdb, w2 <- ipk
     AF_HD void map_m2(const double* w0, double* w1, double* w2, const double* w3, size_t stride, int valid) const {
         double det[kCompMapGroup], lsq[kCompMapGroup], vsq[kCompMapGroup], psq[kCompMapGroup], wdb[kCompMapGroup], ipk[kCompMapGroup];

@@ -227,6 +227,9 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     a.eq_default = &rate.eq_default[0][0];
     a.cleanup = &rate.cleanup;
     a.de_tab = de_tab.data();
+    std::vector<double> map_tab(static_cast<size_t>(MT_FIELDS) * sp);
+    for (size_t s = 0; s < sp; ++s) fill_map_tab(map_tab.data(), sp, s, params[cand[s]]);
+    a.map_tab = map_tab.data();
     a.metrics = metrics.data();
 
     // shared input stage (split bit 4): one render per distinct passage + fan-out, as build_sweep does for sweeps
@@ -240,7 +243,7 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
     const bool shared_front = (split & 64) != 0 && shared_eq;  // ... and so does the compressor front (fused compressor)
     const bool shared_de = (split & 128) != 0;  // with bit 4: the de-esser's detector front runs on the distinct pairs
     std::vector<std::vector<double>> uw(7);
-    std::vector<double> ust_comp, ust_de, ude_tab;
+    std::vector<double> ust_comp, ust_de, ude_tab, umap_tab;
     std::vector<double> ust_eq;
     uint32_t shared_max_sections = 0;
     if (split & 16) {
@@ -277,6 +280,9 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
         ua.n_streams = U;
         ua.stride = U_pad;
         ua.cand = ucand.data();
+        umap_tab.assign(static_cast<size_t>(MT_FIELDS) * U_pad, 0.0);
+        for (int u = 0; u < U_pad; ++u) fill_map_tab(umap_tab.data(), U_pad, u, params[ucand[u]]);
+        ua.map_tab = umap_tab.data();
         ua.src_off = usrc.data();
         ua.buf_a = ubuf.data();
         ua.rows = urows.data();

@@ -256,3 +256,34 @@ def test_shared_eq_prefix_is_bit_identical(sim, name, path, monkeypatch):
     m0, a0, _ = pyoracle.chain_render(passages[0], FS, cand_list[7].bands, cand_list[7].settings, return_audio=True)
     assert audio_within_tolerance(a0, a_shared[7 * 2]) <= 0.0
     assert metric_mismatches(m0, m_shared[7 * 2], tol_db=TOL_DB) == {}
+
+
+@pytest.mark.parametrize("path", ["by_size", "split"])
+def test_cut_compressor_grid_is_bit_identical(sim, path, monkeypatch):
+    """A large compressor grid over few (passage, EQ) pairs is cut into pieces of AFSIM_SUBBATCH streams that run
+    one after another on shared ring buffers: metrics and audio identical, bit for bit, to the uncut batch, on the
+    first launch and on a relaunch of the resident sweep."""
+    if path == "split":
+        monkeypatch.setenv("AFSIM_SPLIT", "2")
+    passages = [speech_like(9000 + 7, seed=80 + k, level=0.7) for k in range(4)]
+    bands, overrides = CASES["legacy_eq"]
+    cand_list = [candidate(bands, **dict(overrides, compressor_threshold_db=-45.0 + 0.4 * i, compressor_ratio=2.0 + 0.04 * i,
+                                         compressor_adaptive_release=bool(i % 2))) for i in range(50)]
+    cands = candidate_array(cand_list)
+    monkeypatch.setenv("AFSIM_SUBBATCH", "100000")
+    m_whole, a_whole = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    monkeypatch.setenv("AFSIM_SUBBATCH", "64")  # 200 streams -> pieces of 64 / 64 / 64 / 8 (the last one too small to share)
+    sweep = sim.prepare_sweep(passages, FS, cands, want_audio=True)
+    for _ in range(2):
+        sweep.launch()
+        m_cut = sweep.collect()
+        a_cut = [sweep.collect_audio(i) for i in range(sweep.n_pairs)]
+        for i in range(len(cand_list) * 4):
+            d0, d1 = abi.metrics_to_dict(m_whole[i]), abi.metrics_to_dict(m_cut[i])
+            d0.pop("candidate_runtime_ms"), d1.pop("candidate_runtime_ms")
+            assert d0 == d1, i
+            assert np.array_equal(a_whole[i], a_cut[i]), i
+    sweep.release()
+    m0, a0, _ = pyoracle.chain_render(passages[3], FS, cand_list[11].bands, cand_list[11].settings, return_audio=True)
+    assert audio_within_tolerance(a0, a_cut[11 * 4 + 3]) <= 0.0
+    assert metric_mismatches(m0, m_cut[11 * 4 + 3], tol_db=TOL_DB) == {}

@@ -37,8 +37,11 @@ def _check_sample(passages, cands, metrics, n_check, seed):
     return picks
 
 
-def test_c3_compressor_grid_fused_path(sim):
-    """4096 grid candidates x 8 passages = 32768 streams (fused kernels), 1 s each."""
+@pytest.mark.parametrize("subbatch", ["16384", "1000000"])
+def test_c3_compressor_grid_fused_path(sim, subbatch, monkeypatch):
+    """4096 grid candidates x 8 passages = 32768 streams, 1 s each: cut into two 16384-stream pieces on the R/M split
+    kernels with the shared compressor front (the default), and whole on the fused kernels."""
+    monkeypatch.setenv("AFSIM_SUBBATCH", subbatch)
     passages = [workloads.speech_like(48000, seed=300 + k, level=0.6) for k in range(8)]
     cands = workloads.compressor_grid_candidates(4096)
     sweep = sim.prepare_sweep(passages, FS, cands)
