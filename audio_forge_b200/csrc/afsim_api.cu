@@ -556,10 +556,19 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 batch->stages.push_back({SK_EQ, static_cast<int>(first)});
         };
         bool shared_de_flag = false;  // set below, before the stage list is built
+        // AFSIM_DE_CUT: 1 = never, 2 = always, else for the batches that take the R/M split kernels
+        const int de_cut_mode = env_int("AFSIM_DE_CUT", 0);
+        const bool de_cut = de_cut_mode == 2 || (de_cut_mode != 1 && split);
         auto push_deesser = [&]() {
             if (!(a.structure & ST_DEESSER)) return;
-            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3})
-                if (!(shared_de_flag && (op == SP_DE_RA || op == SP_DE_MB))) batch->stages.push_back({SK_SPLIT, op});
+            for (int op : {SP_DE_RA, SP_DE_MB, SP_DE_RC, SP_DE_MC2, SP_DE_RC3}) {
+                if (shared_de_flag && (op == SP_DE_RA || op == SP_DE_MB)) continue;
+                if (op == SP_DE_RC && de_cut) {  // few streams: R_c1 as two short serial kernels around a map
+                    for (int cut_op : {SP_DE_RC1A, SP_DE_MC1B, SP_DE_RC1C}) batch->stages.push_back({SK_SPLIT, cut_op});
+                    continue;
+                }
+                batch->stages.push_back({SK_SPLIT, op});
+            }
         };
         // Shared prefix: when several streams of the batch read the same passage (a candidate sweep), the input stage
         // -- identical for all of them -- runs once per distinct passage and a copy kernel fans it out.  When the EQ
@@ -807,7 +816,7 @@ int run_batch(AfsimHandle* h, Batch& b, WavefrontTrace* trace = nullptr) {
             if (sd.kind == SK_INPUT_FANOUT) return h->stage_stream_map[i];
             const bool is_map = (sd.kind == SK_SPLIT || sd.kind == SK_SPLIT_SHARED) && (sd.arg == SP_COMP_M2 || sd.arg == SP_COMP_M4 || sd.arg == SP_COMP_M6 ||
                                                         sd.arg == SP_LIM_M || sd.arg == SP_TP_FIR_IN || sd.arg == SP_TP_FIR_OUT ||
-                                                        sd.arg == SP_DE_MB || sd.arg == SP_DE_MC2);
+                                                        sd.arg == SP_DE_MB || sd.arg == SP_DE_MC2 || sd.arg == SP_DE_MC1B);
             return is_map ? h->stage_stream_map[i] : h->stage_stream[i];
         };
         for (int i = 0; i < n_stages; ++i) AF_CUDA(h, cudaStreamWaitEvent(stream_of(i), h->ev_fork, 0));

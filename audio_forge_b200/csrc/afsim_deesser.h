@@ -361,6 +361,216 @@ struct DeEsserTargets {  // R_c1
 };
 constexpr size_t kDeRc1StagingBytesPerLane = (size_t)kDeRcDepth * 8 * (7 * 8);
 
+// ---- R_c1 cut three ways (few-stream batches) ---------------------------------------------------------------------------------
+// In a few-stream batch R_c1 is the wavefront's slowest stage: one warp per 32 streams walks ~440 dependent-issue
+// instructions per sample, of which only the three smoothers (confidence, baseline, reduction) and the rebuild
+// hysteresis carry state from sample to sample.  The cut keeps those in two short serial kernels and moves the
+// feed-forward middle (normalised confidence, over-threshold, target, the max-reduction rescale: two divisions per
+// sample) into a map over (stream, sample group):
+//   R_c1a  conf[b], base[b] smoothed      (voice, level[3], conf target[3]) -> w7..w9 = conf, w10..w12 = base
+//   M_c1b  target[b], rescaled            (voice, level[3], w7..w12)        -> w7..w9 = target
+//   R_c1c  red[b] smoothed, hysteresis    (w7..w9)                          -> w0 = rebuild mask, w4..w6 = gains
+// w7..w12 are free at this point (M_c2 writes its coefficients there afterwards).  Every expression is the one
+// `DeEsserTargets::sample` evaluates, in the same order: the results are identical bit for bit.  The state table
+// keeps R_c1's layout (conf, base, red, built per band, then current); each kernel parks its own slots.
+struct DeEsserConfBase {  // R_c1a
+    double conf[3], base[3];
+    bool auto_mode;
+    AF_HD void init(const CandidateParams& p) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) conf[b] = base[b] = 0.0;
+        auto_mode = (p.flags & LF_DE_AUTO) != 0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            io.f64(conf[b]);
+            io.f64(base[b]);
+            io.skip(2);
+        }
+    }
+    // in[0..6] as for DeEsserTargets::run; out[0..5]: the stream's w7..w12 columns at chunk start (pitch stride)
+    AF_HD void run(const double* const (&in)[7], size_t in_stride, double* const (&out)[6], size_t stride, int len,
+                   const DeConst& table, Staging stg) {
+        constexpr int U = kGroup;
+        DeApplyConst k;
+        k.load(table);
+        StageRing<double, kDeRcDepth> sw[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sw[i] = stg.ring<double, kDeRcDepth>();
+        auto issue = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || t0 + u < len) {
+                    const size_t o = (size_t)(t0 + u) * in_stride;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) sw[i].fetch(kt, u, in[i] + o);
+                }
+            }
+        };
+        auto body = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+            const int valid = FULL ? U : len - t0;
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) {
+                if (FULL || u < valid) {
+                    const size_t o = (size_t)(t0 + u) * stride, oi = (size_t)(t0 + u) * in_stride;
+                    const double voice_db = sw[0].get(kt, u, in[0] + oi);
+                    const double lv[3] = {sw[1].get(kt, u, in[1] + oi), sw[2].get(kt, u, in[2] + oi), sw[3].get(kt, u, in[3] + oi)};
+                    const double ct[3] = {sw[4].get(kt, u, in[4] + oi), sw[5].get(kt, u, in[5] + oi), sw[6].get(kt, u, in[6] + oi)};
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        conf[b] = smooth_ar(conf[b], ct[b], k.det_attack, k.det_release);
+                        if (auto_mode) {
+                            const double ratio_db = fmax(lv[b] - voice_db, 0.0);
+                            const bool voice_active = voice_db > -55.0 || lv[b] > -55.0;
+                            if (voice_active) {
+                                const double base_target = clampd(ratio_db * 0.45, 0.0, 24.0);
+                                const double c = base_target < base[b] ? k.base_fall : k.base_rise;
+                                base[b] = c * base[b] + (1.0 - c) * base_target;
+                            } else {
+                                base[b] *= k.base_inactive;
+                            }
+                        }
+                        out[b][o] = conf[b];
+                        out[3 + b][o] = base[b];
+                    }
+                }
+            }
+        };
+        pipelined_tiles_depth<kDeRcDepth>(len, issue, body);
+    }
+};
+
+constexpr size_t kDeRc1cStagingBytesPerLane = (size_t)kDeRcDepth * 8 * (3 * 8);
+
+// M_c1b: in[0..3] voice / level columns at the group's first sample (pitch in_stride), w[0..5] the stream's w7..w12 there
+constexpr int kDeTargetGroup = 2;
+AF_HD void deesser_targets(const double* const (&in)[4], size_t in_stride, double* const (&w)[6], size_t stride, int valid,
+                           const DeConst& table, bool auto_mode) {
+    constexpr int G = kDeTargetGroup;
+    DeApplyConst k;
+    k.load(table);
+    const double conf_lo = auto_mode ? k.conf_floor : 0.22;
+    const AfDivisor conf_div = af_divisor(1.0 - conf_lo);
+    double voice[G], lv[3][G], conf[3][G], base[3][G], target[3][G];
+    load_tile(in[0], in_stride, valid, voice);
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        load_tile(in[1 + b], in_stride, valid, lv[b]);
+        load_tile((const double*)w[b], stride, valid, conf[b]);
+        load_tile((const double*)w[3 + b], stride, valid, base[b]);
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+        double target_sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double ratio_db = fmax(lv[b][u] - voice[u], 0.0);
+            double tr = 0.0;
+            if (auto_mode) {
+                const double conf_gain = clampd(af_div(conf[b][u] - conf_lo, conf_div), 0.0, 1.0);
+                const double over_db = fmax(ratio_db - base[b][u] - k.trigger, 0.0);
+                tr = clampd(over_db * k.slope * conf_gain, 0.0, k.cap);
+            } else if (lv[b][u] > k.threshold) {
+                const double level_over = lv[b][u] - k.threshold;
+                const double ratio_over = ratio_db - k.ratio_thr;
+                if (ratio_over > 0.0) {
+                    const double over_db = fmin(level_over, ratio_over);
+                    const double conf_gain = clampd(af_div(conf[b][u] - conf_lo, conf_div), 0.0, 1.0);
+                    tr = clampd(k.ratio_factor * over_db * conf_gain, 0.0, k.manual_cap);
+                }
+            }
+            target[b][u] = tr;
+            target_sum += tr;
+        }
+        if (target_sum > k.max_red && target_sum > 0.0) {
+            const double scale = k.max_red / target_sum;
+#pragma unroll
+            for (int b = 0; b < 3; ++b) target[b][u] *= scale;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) store_tile(w[b], stride, valid, target[b]);
+}
+
+struct DeEsserReduction {  // R_c1c
+    double red[3], built_gain[3];
+    double current;
+    AF_HD void init() {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) red[b] = built_gain[b] = 0.0;
+        current = 0.0;
+    }
+    template <class IO>
+    AF_HD void sync(IO& io) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            io.skip(2);
+            io.f64(red[b]);
+            io.f64(built_gain[b]);
+        }
+        io.f64(current);
+    }
+    // tg[0..2]: the stream's w7..w9 columns at chunk start; mask_out = w0, gain_out[0..2] = w4..w6 (pitch stride)
+    AF_HD void run(const double* const (&tg)[3], double* mask_out, double* const (&gain_out)[3], size_t stride, int n0, int len,
+                   const DeConst& table, BlockClock clk, float* rows_de, Staging stg) {
+        constexpr int U = kGroup;
+        const double attack = table(DE_ATTACK), release = table(DE_RELEASE), max_red = table(DE_MAX_RED);
+        StageRing<double, kDeRcDepth> sw[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sw[i] = stg.ring<double, kDeRcDepth>();
+        auto issue = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (FULL || t0 + u < len) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) sw[i].fetch(kt, u, tg[i] + o);
+                }
+            }
+        };
+        auto body = [&](int kt, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            const int t0 = kt * U;
+            const int valid = FULL ? U : len - t0;
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) {
+                if (FULL || u < valid) {
+                    const size_t o = (size_t)(t0 + u) * stride;
+                    const double target[3] = {sw[0].get(kt, u, tg[0] + o), sw[1].get(kt, u, tg[1] + o), sw[2].get(kt, u, tg[2] + o)};
+                    unsigned mask = 0;
+                    double total_red = 0.0;
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        red[b] = smooth_ar(red[b], target[b], attack, release);
+                        total_red += red[b];
+                        const double dyn_gain = -red[b];
+                        gain_out[b][o] = dyn_gain;
+                        if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate rebuilds the filter
+                            built_gain[b] = dyn_gain;
+                            mask |= 1u << b;
+                        }
+                    }
+                    current = fmin(total_red, max_red);
+                    mask_out[o] = (double)mask;
+                    if (clk.at_end(n0 + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
+                        rows_de[(size_t)clk.blk * stride] = (float)current;
+                        clk.advance();
+                    }
+                }
+            }
+        };
+        pipelined_tiles_depth<kDeRcDepth>(len, issue, body);
+    }
+};
+
 // ---- M_c2: coefficients of the rebuilt filters ------------------------------------------------------------------------
 // coefficient rings of band b: w[kDeCoefRing[b][i]], i = b0 b1 b2 a2
 AF_HD int de_coef_ring(int band, int i) { return band == 0 ? (i < 3 ? 1 + i : 7) : (band == 1 ? 8 + i : (i < 1 ? 12 : 3 + i)); }

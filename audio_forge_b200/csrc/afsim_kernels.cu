@@ -173,6 +173,10 @@ AF_R_KERNEL_DIRECT(k_de_ra_direct, body_de_ra, 1)
 // de-esser R_c1 (targets, hysteresis) and R_c3 (time-varying biquads): staged and direct variants
 AF_R_KERNEL(k_de_rc, body_de_rc)
 AF_R_KERNEL_DIRECT(k_de_rc_direct, body_de_rc, 4)
+AF_R_KERNEL(k_de_rc1a, body_de_rc1a)
+AF_R_KERNEL_DIRECT(k_de_rc1a_direct, body_de_rc1a, 4)
+AF_R_KERNEL(k_de_rc1c, body_de_rc1c)
+AF_R_KERNEL_DIRECT(k_de_rc1c_direct, body_de_rc1c, 4)
 AF_R_KERNEL(k_de_rc3, body_de_rc3)
 AF_R_KERNEL_DIRECT(k_de_rc3_direct, body_de_rc3, 4)
 
@@ -195,6 +199,7 @@ AF_M_KERNEL(k_comp_m4, kCompMapGroup, body_comp_m4(a, ck, s, g))
 AF_M_KERNEL(k_comp_m6, kCompMapGroup, body_comp_m6(a, ck, s, g))
 AF_M_KERNEL(k_de_mb, kDeMapGroup, body_de_mb(a, ck, s, g))
 AF_M_KERNEL(k_de_mc2, kDeRebuildGroup, body_de_mc2(a, ck, s, g))
+AF_M_KERNEL(k_de_mc1b, kDeTargetGroup, body_de_mc1b(a, ck, s, g))
 AF_M_KERNEL(k_lim_m, kLimGroup, body_lim_m(a, ck, s, g))
 AF_M_KERNEL(k_tp_fir_in, kGroup, body_tp_fir_in(a, ck, s, g, c_fir))
 AF_M_KERNEL(k_tp_fir_out, kGroup, body_tp_fir_out(a, ck, s, g, c_fir))
@@ -438,11 +443,13 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     // 128-thread blocks reading global memory directly when the batch itself fills the GPU
     const int rb = a.stage_inputs ? kRBlock : 128;
     const dim3 rgrid = stream_grid(a, rb);
-    const size_t lane_bytes = op == SP_DE_RC ? kDeRc1StagingBytesPerLane : (op == SP_DE_RC3 ? kDeRc3StagingBytesPerLane : kStagingBytesPerLane);
+    const size_t lane_bytes = (op == SP_DE_RC || op == SP_DE_RC1A) ? kDeRc1StagingBytesPerLane
+                              : (op == SP_DE_RC1C ? kDeRc1cStagingBytesPerLane
+                                                  : (op == SP_DE_RC3 ? kDeRc3StagingBytesPerLane : kStagingBytesPerLane));
     const size_t rsm = a.stage_inputs ? lane_bytes * kRBlock : 0;
     const int mb = 32 * kMapWarps;
     const int group = (op == SP_COMP_M2 || op == SP_COMP_M4 || op == SP_COMP_M6) ? kCompMapGroup
-                      : (op == SP_LIM_M ? kLimGroup : (op == SP_DE_MB ? kDeMapGroup : (op == SP_DE_MC2 ? kDeRebuildGroup : kGroup)));
+                      : (op == SP_LIM_M ? kLimGroup : (op == SP_DE_MB ? kDeMapGroup : (op == SP_DE_MC2 ? kDeRebuildGroup : (op == SP_DE_MC1B ? kDeTargetGroup : kGroup))));
     const int n_groups = (ck.len + group - 1) / group;
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
@@ -487,6 +494,19 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
                 k_de_rc<<<rgrid, rb, rsm, st>>>(a, ck);
             else
                 k_de_rc_direct<<<rgrid, rb, 0, st>>>(a, ck);
+            break;
+        case SP_DE_RC1A:
+            if (a.stage_inputs)
+                k_de_rc1a<<<rgrid, rb, rsm, st>>>(a, ck);
+            else
+                k_de_rc1a_direct<<<rgrid, rb, 0, st>>>(a, ck);
+            break;
+        case SP_DE_MC1B: k_de_mc1b<<<mgrid, mb, 0, st>>>(a, ck); break;
+        case SP_DE_RC1C:
+            if (a.stage_inputs)
+                k_de_rc1c<<<rgrid, rb, rsm, st>>>(a, ck);
+            else
+                k_de_rc1c_direct<<<rgrid, rb, 0, st>>>(a, ck);
             break;
         case SP_COMP_R7: k_comp_r7<<<rgrid, rb, rsm, st>>>(a, ck); break;
         case SP_DE_MC2: k_de_mc2<<<mgrid, mb, 0, st>>>(a, ck); break;

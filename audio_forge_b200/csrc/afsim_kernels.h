@@ -29,7 +29,8 @@ enum SplitOp {
     SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT,
     SP_DE_RA, SP_DE_MB, SP_DE_RC,
     SP_COMP_R7,  // auto makeup (after M6)
-    SP_DE_MC2, SP_DE_RC3  // de-esser: coefficient rebuild map, dynamic-EQ biquads (SP_DE_RC is R_c1)
+    SP_DE_MC2, SP_DE_RC3,  // de-esser: coefficient rebuild map, dynamic-EQ biquads (SP_DE_RC is R_c1)
+    SP_DE_RC1A, SP_DE_MC1B, SP_DE_RC1C  // R_c1 cut three ways for few-stream batches (afsim_deesser.h)
 };
 cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cudaStream_t st);
 cudaError_t configure_kernels();

@@ -507,6 +507,72 @@ AF_HD void body_de_rc(const BatchArgs& a, const ChunkArgs& ck, int s, Staging st
         st.sync(io);
     }
 }
+// R_c1 cut three ways (afsim_deesser.h): R_c1a -> M_c1b -> R_c1c, same state table as body_de_rc
+AF_HD void body_de_rc1a(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    DeEsserConfBase st;
+    st.init(stream_params(a, s));
+    double* table = a.st_deesser + (size_t)kStateDeDetect * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync(io);
+    }
+    const DeConst k{a.de_tab + s, stride};
+    double* const out[6] = {col_at(a.w[7], a, ck, s),  col_at(a.w[8], a, ck, s),  col_at(a.w[9], a, ck, s),
+                            col_at(a.w[10], a, ck, s), col_at(a.w[11], a, ck, s), col_at(a.w[12], a, ck, s)};
+    if (a.in_de[0]) {  // levels and confidence targets of the shared front
+        const size_t o = (size_t)ck.row0 * (size_t)a.in_stride + a.in_unique[s];
+        const double* const in[7] = {a.in_de[0] + o, a.in_de[1] + o, a.in_de[2] + o, a.in_de[3] + o,
+                                     a.in_de[4] + o, a.in_de[5] + o, a.in_de[6] + o};
+        st.run(in, (size_t)a.in_stride, out, stride, ck.len, k, stg);
+    } else {
+        const double* const in[7] = {col_at(a.w[0], a, ck, s), col_at(a.w[1], a, ck, s), col_at(a.w[2], a, ck, s), col_at(a.w[3], a, ck, s),
+                                     col_at(a.w[4], a, ck, s), col_at(a.w[5], a, ck, s), col_at(a.w[6], a, ck, s)};
+        st.run(in, stride, out, stride, ck.len, k, stg);
+    }
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync(io);
+    }
+}
+AF_HD void body_de_mc1b(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
+    int t0, valid;
+    if (!group_span(ck, g, &t0, &valid, kDeTargetGroup)) return;
+    const size_t stride = (size_t)a.stride;
+    const DeConst k{a.de_tab + s, stride};
+    const bool auto_mode = (static_cast<uint32_t>(a.map_tab[(size_t)MT_FLAGS * stride + s]) & LF_DE_AUTO) != 0;
+    double* const w[6] = {col_at(a.w[7], a, ck, s, t0),  col_at(a.w[8], a, ck, s, t0),  col_at(a.w[9], a, ck, s, t0),
+                          col_at(a.w[10], a, ck, s, t0), col_at(a.w[11], a, ck, s, t0), col_at(a.w[12], a, ck, s, t0)};
+    if (a.in_de[0]) {
+        const size_t o = (size_t)(ck.row0 + t0) * (size_t)a.in_stride + a.in_unique[s];
+        const double* const in[4] = {a.in_de[0] + o, a.in_de[1] + o, a.in_de[2] + o, a.in_de[3] + o};
+        deesser_targets(in, (size_t)a.in_stride, w, stride, valid, k, auto_mode);
+    } else {
+        const double* const in[4] = {col_at(a.w[0], a, ck, s, t0), col_at(a.w[1], a, ck, s, t0), col_at(a.w[2], a, ck, s, t0),
+                                     col_at(a.w[3], a, ck, s, t0)};
+        deesser_targets(in, stride, w, stride, valid, k, auto_mode);
+    }
+}
+AF_HD void body_de_rc1c(const BatchArgs& a, const ChunkArgs& ck, int s, Staging stg) {
+    const size_t stride = (size_t)a.stride;
+    DeEsserReduction st;
+    st.init();
+    double* table = a.st_deesser + (size_t)kStateDeDetect * stride + s;
+    if (ck.n0 != 0) {
+        StateIO<false> io{table, stride};
+        st.sync(io);
+    }
+    BlockClock clk;
+    clk.init(a.block_samples, a.n_samples, ck.n0);
+    const DeConst k{a.de_tab + s, stride};
+    const double* const tg[3] = {col_at(a.w[7], a, ck, s), col_at(a.w[8], a, ck, s), col_at(a.w[9], a, ck, s)};
+    double* const gains[3] = {col_at(a.w[4], a, ck, s), col_at(a.w[5], a, ck, s), col_at(a.w[6], a, ck, s)};
+    st.run(tg, col_at(a.w[0], a, ck, s), gains, stride, ck.n0, ck.len, k, clk, a.rows + (size_t)3 * a.n_rows * stride + s, stg);
+    if (ck.n0 + ck.len < a.n_samples) {
+        StateIO<true> io{table, stride};
+        st.sync(io);
+    }
+}
 AF_HD void body_de_mc2(const BatchArgs& a, const ChunkArgs& ck, int s, int g) {
     int t0, valid;
     if (!group_span(ck, g, &t0, &valid, kDeRebuildGroup)) return;

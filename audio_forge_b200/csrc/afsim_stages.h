@@ -88,6 +88,7 @@ struct StateIO {
         if (STORE) *p = v ? 1.0 : 0.0; else v = *p != 0.0;
         p += stride;
     }
+    AF_HD void skip(int n) { p += (size_t)n * stride; }  // slots another kernel of the same stage owns
 };
 
 // Analysis-block clock (python_api.rs:512-513): block b ends after sample (b+1)*block-1 or T-1.

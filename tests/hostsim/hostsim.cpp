@@ -332,7 +332,14 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
             for (int g = (ck.len + kDeMapGroup - 1) / kDeMapGroup; g >= 0; --g)
                 for (int s = 0; s < S; ++s) body_de_mb(a, ck, s, g);
         }
-        for (int s = 0; s < S; ++s) body_de_rc(a, ck, s, st);
+        if (split & 256) {  // R_c1 cut three ways (afsim_deesser.h)
+            for (int s = 0; s < S; ++s) body_de_rc1a(a, ck, s, st);
+            for (int g = (ck.len + kDeTargetGroup - 1) / kDeTargetGroup; g >= 0; --g)
+                for (int s = 0; s < S; ++s) body_de_mc1b(a, ck, s, g);
+            for (int s = 0; s < S; ++s) body_de_rc1c(a, ck, s, st);
+        } else {
+            for (int s = 0; s < S; ++s) body_de_rc(a, ck, s, st);
+        }
         for (int g = (ck.len + kDeRebuildGroup - 1) / kDeRebuildGroup; g >= 0; --g)
             for (int s = 0; s < S; ++s) body_de_mc2(a, ck, s, g);
         for (int s = 0; s < S; ++s) body_de_rc3(a, ck, s, st);

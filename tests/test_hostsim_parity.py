@@ -100,7 +100,9 @@ def test_shared_deesser_front_fan_out():
     cands = candidate_array(cand_list)
     pp = np.array([p for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
     pc = np.array([c for c in range(len(cand_list)) for p in range(2)], dtype=np.uint32)
-    for split, chunk in ((16 | 128, 1000), (16 | 128 | 7, 520), (16 | 128 | 8, 1024)):
+    # 256: R_c1 cut into conf / baseline smoothers -> target map -> reduction smoothers + hysteresis
+    for split, chunk in ((16 | 128, 1000), (16 | 128 | 7, 520), (16 | 128 | 8, 1024), (256, 1000), (256 | 7, 264),
+                         (16 | 128 | 256, 520), (16 | 128 | 256 | 15, 1024)):
         got, audio, rows = hostsim.chain_sweep(passages, FS, cands, pp, pc, chunk=chunk, slots=2, split=split, want_audio=True,
                                                want_rows=True)
         _check_pairs(passages, cand_list, pp, pc, got, audio)
