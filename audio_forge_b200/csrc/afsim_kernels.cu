@@ -153,13 +153,13 @@ extern __shared__ __align__(16) unsigned char stage_smem[];
 #define AF_R_KERNEL(name, body)                                                         \
     __global__ void __launch_bounds__(kRBlock) name(BatchArgs a, ChunkArgs ck) {        \
         AF_STREAM_INDEX();                                                              \
-        const Staging stg{stage_smem, kRBlock, (int)threadIdx.x, 0};                    \
+        const Staging stg{stage_smem, kRBlock, (int)threadIdx.x, 0, 1};                 \
         body(a, ck, s, stg);                                                            \
     }
 #define AF_R_KERNEL_DIRECT(name, body, minblocks)                                       \
     __global__ void __launch_bounds__(128, minblocks) name(BatchArgs a, ChunkArgs ck) { \
         AF_STREAM_INDEX();                                                              \
-        const Staging stg{nullptr, 128, (int)threadIdx.x, 0};                           \
+        const Staging stg{nullptr, 128, (int)threadIdx.x, 0, 0};                        \
         body(a, ck, s, stg);                                                            \
     }
 AF_R_KERNEL(k_comp_r1, body_comp_r1)

@@ -71,22 +71,29 @@ template <typename T, int DEPTH = kPipeDepth>
 struct StageRing {  // one staged input stream of one thread
     T* p;           // this thread's element of (tile slot 0, sample 0); nullptr = direct mode (no staging)
     int lanes;      // threads sharing the staging area (element pitch)
+    bool on;        // staged (a compile-time constant in the kernels: the accessors below fold to one path)
     AF_HD T* at(int tile, int u) const { return p + (size_t)((tile % DEPTH) * kGroup + u) * lanes; }
     // direct-mode aware accessors: big batches have enough warps per SM to hide the latency themselves, and
     // the staging area would only cost them occupancy
     AF_HD void fetch(int tile, int u, const T* g) const {
-        if (p) async_copy(at(tile, u), g);
+        if (on) async_copy(at(tile, u), g);
     }
-    AF_HD T get(int tile, int u, const T* g) const { return p ? *at(tile, u) : *g; }
+    AF_HD T get(int tile, int u, const T* g) const { return on ? *at(tile, u) : *g; }
 };
 struct Staging {  // the staging area of a block (shared memory) / of one call (host); base == nullptr: direct mode
     unsigned char* base;
     int lanes, lane;
     size_t used;
+    // 1 / 0: staged / direct, spelled out by the kernels so that it is a compile-time constant there (a shared-memory
+    // address cannot be proven non-null: every staged access would carry a pointer test and both code paths);
+    // -1: decided by `base` at run time (the host harness)
+    int mode = -1;
+    AF_HD bool staged() const { return mode < 0 ? base != nullptr : mode != 0; }
     template <typename T, int DEPTH = kPipeDepth>
     AF_HD StageRing<T, DEPTH> ring() {
         StageRing<T, DEPTH> r;
-        r.p = base ? reinterpret_cast<T*>(base + used) + lane : nullptr;
+        r.on = staged();
+        r.p = r.on ? reinterpret_cast<T*>(base + used) + lane : nullptr;
         r.lanes = lanes;
         used += sizeof(T) * (size_t)DEPTH * kGroup * (size_t)lanes;
         return r;
