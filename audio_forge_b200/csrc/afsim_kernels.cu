@@ -67,21 +67,40 @@ __global__ void __launch_bounds__(32) k_input_cleanup_warp(BatchArgs a, ChunkArg
     BlockClock clk;
     clk.init(a.block_samples, a.n_samples, ck.n0);
     const Col out{a.buf_a + (size_t)ck.row0 * stride + s, stride};
-    const float* src = a.signals + a.src_off[s];
+    const float* src = a.signals + a.src_off[s] + ck.n0;
     float* rows_in = a.rows + s;
+    // The block's samples go through shared memory, and the NEXT block's are already in flight (a coalesced load into
+    // registers) while this one is walked: with a global load per sample in the two serial loops below, the warp
+    // paid an exposed L2 / DRAM latency twice per sample -- 0.69 ms per 1440-sample chunk alone and 2.6x that inside
+    // the wavefront, where the memory system is busy, which made this stage the wavefront's period.
+    constexpr int kPerLane = (kInputBlock + 31) / 32;
+    __shared__ float blk[kInputBlock];
+    float next[kPerLane];
+    auto prefetch = [&](int b0) {
+        const int blen = ck.len - b0 < kInputBlock ? ck.len - b0 : kInputBlock;
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+            const int t = i * 32 + lane;
+            next[i] = t < blen ? src[b0 + t] : 0.0f;
+        }
+    };
+    prefetch(0);
     for (int b0 = 0; b0 < ck.len; b0 += kInputBlock) {
         const int blen = ck.len - b0 < kInputBlock ? ck.len - b0 : kInputBlock;
-        for (int t = 0; t < blen; ++t) {  // analyze_input on the raw (sanitised) block
-            float v = src[ck.n0 + b0 + t];
-            if (!af_finite(v)) v = 0.0f;
-            cl.analyze(v, k, gentle);
+        __syncwarp();  // the previous block has been walked by every lane
+#pragma unroll
+        for (int i = 0; i < kPerLane; ++i) {
+            const int t = i * 32 + lane;
+            if (t < kInputBlock) blk[t] = af_finite(next[i]) ? next[i] : 0.0f;  // sanitised once
         }
+        __syncwarp();
+        if (b0 + kInputBlock < ck.len) prefetch(b0 + kInputBlock);
+        for (int t = 0; t < blen; ++t) cl.analyze(blk[t], k, gentle);  // analyze_input on the raw (sanitised) block
         bool hum_detected;
         cl.begin_block(k, gentle, &hum_detected);
         for (int t = 0; t < blen; ++t) {
             const int n = ck.n0 + b0 + t;
-            float in = src[n];
-            if (!af_finite(in)) in = 0.0f;
+            const float in = blk[t];
             const float dc = in - st.x1 + 0.995f * st.y1;  // routing.rs:832-836
             st.x1 = in;
             st.y1 = dc;
