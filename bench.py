@@ -67,18 +67,19 @@ WORKLOADS = {
 STAGE_BYTES = {"input": 8, "eq": 8, "deesser": 8, "compressor": 8, "limiter": 20, "output": 4,
                "comp_r1": 36, "comp_m2": 48, "comp_r3": 32, "comp_m4": 32, "comp_r5": 16, "comp_m6": 16,
                "lim_m": 12, "lim_r": 16, "tp_fir_in": 8, "tp_r": 12, "tp_fir_out": 4,
-               "de_ra": 36, "de_mb": 88, "de_rc": 88, "de_mc2": 128, "de_rc3": 112, "comp_r7": 16, "input_fanout": 8}
+               "de_ra": 36, "de_mb": 88, "de_rc": 88, "de_mc2": 128, "de_rc3": 112, "comp_r7": 16, "input_fanout": 8,
+               "de_rc1a": 104, "de_mc1b": 104, "de_rc1c": 56}
 
 
 # DRAM traffic per launch (MB, dram__bytes_read.sum + dram__bytes_write.sum) of each stage kernel from the committed
-# `ncu --set full` capture of the default workload shape (profiles/r01_v10_ncu_kernels.md: 4096 streams, chunk 1024).
-NCU_TRAFFIC_MB = {"input": 0.1, "input_fanout": 0.2, "eq": 16.5, "comp_r1": 92.3, "comp_m2": 161.3, "comp_r3": 81.4,
-                  "comp_m4": 110.5, "comp_r5": 35.0, "comp_m6": 51.0, "lim_m": 19.1, "lim_r": 51.6, "tp_fir_in": 18.1,
+# `ncu --set full` capture of the default workload shape (profiles/r01_v11_ncu_kernels.md: 4096 streams, chunk 1024).
+NCU_TRAFFIC_MB = {"input": 0.1, "input_fanout": 0.2, "eq": 16.5, "comp_r1": 92.9, "comp_m2": 160.1, "comp_r3": 82.4,
+                  "comp_m4": 109.4, "comp_r5": 35.1, "comp_m6": 50.5, "lim_m": 18.5, "lim_r": 51.6, "tp_fir_in": 17.6,
                   "tp_r": 34.4, "tp_fir_out": 17.5}
 # warp-level instructions per launch of the same capture (smsp__inst_executed.sum), for the issue-rate fraction
-NCU_WARP_INSTR = {"input": 1.75e4, "input_fanout": 1.7e6, "eq": 8.53e6, "comp_r1": 6.32e6, "comp_m2": 4.32e7,
-                  "comp_r3": 4.65e6, "comp_m4": 2.92e7, "comp_r5": 3.71e6, "comp_m6": 1.15e7, "lim_m": 9.4e6,
-                  "lim_r": 8.34e6, "tp_fir_in": 2.53e7, "tp_r": 7.84e6, "tp_fir_out": 2.36e7}
+NCU_WARP_INSTR = {"input": 1.75e4, "input_fanout": 1.73e6, "eq": 8.53e6, "comp_r1": 6.42e6, "comp_m2": 4.18e7,
+                  "comp_r3": 4.75e6, "comp_m4": 2.95e7, "comp_r5": 3.79e6, "comp_m6": 1.18e7, "lim_m": 9.41e6,
+                  "lim_r": 8.34e6, "tp_fir_in": 2.41e7, "tp_r": 7.88e6, "tp_fir_out": 2.25e7}
 
 
 def parse_args():
