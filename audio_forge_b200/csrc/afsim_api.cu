@@ -322,33 +322,33 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             bool cut = S > sub && sub <= 16384 && split_mode != 1 && env_int("AFSIM_SHARED_INPUT", 1) == 1 &&
                        (structure & ST_COMPRESSOR) && (structure & ST_EQ) &&
                        !(structure & (ST_DEESSER | ST_AUTO_MAKEUP | ST_INPUT_TRUE_PEAK));
-            if (cut) {  // few distinct (passage, EQ) pairs?
-                std::map<std::vector<unsigned char>, uint32_t> classes;
-                std::vector<int64_t> class_of(plans.size(), -1);
-                std::set<std::pair<uint32_t, uint32_t>> distinct;
-                for (uint32_t i : members) {
-                    const uint32_t c = candidate_of(i);
-                    if (class_of[c] < 0)
-                        class_of[c] = classes.emplace(eq_class_key(plans[c].params), static_cast<uint32_t>(classes.size())).first->second;
-                    distinct.emplace(passage_of(i), static_cast<uint32_t>(class_of[c]));
-                    if (distinct.size() * 4 > static_cast<size_t>(sub)) break;
-                }
-                cut = distinct.size() * 4 <= static_cast<size_t>(sub);
-            }
             if (!cut) {
                 pieces.push_back({kv.first, std::move(members), false, false});
                 continue;
             }
-            // the streams of a passage stay together (so that a piece shares as much as the group did)
-            std::stable_sort(members.begin(), members.end(), [&](uint32_t x, uint32_t y) { return passage_of(x) < passage_of(y); });
-            const int n_pieces = (S + sub - 1) / sub;
-            const int piece_len = round_up((S + n_pieces - 1) / n_pieces, 32);
-            for (int first = 0; first < S; first += piece_len) {
+            // EQ class of every stream; few distinct (passage, EQ) pairs -> pieces (afsim_plan.cpp)
+            std::map<std::vector<unsigned char>, uint32_t> classes;
+            std::vector<int64_t> class_of(plans.size(), -1);
+            std::vector<uint32_t> m_passage(S), m_class(S);
+            for (int k = 0; k < S; ++k) {
+                const uint32_t c = candidate_of(members[k]);
+                if (class_of[c] < 0)
+                    class_of[c] = classes.emplace(eq_class_key(plans[c].params), static_cast<uint32_t>(classes.size())).first->second;
+                m_passage[k] = passage_of(members[k]);
+                m_class[k] = static_cast<uint32_t>(class_of[c]);
+            }
+            const std::vector<std::vector<uint32_t>> cuts = cut_stream_group(m_passage, m_class, sub);
+            if (cuts.size() == 1) {
+                pieces.push_back({kv.first, std::move(members), false, false});
+                continue;
+            }
+            for (size_t k = 0; k < cuts.size(); ++k) {
                 Piece pc;
                 pc.key = kv.first;
-                pc.members.assign(members.begin() + first, members.begin() + std::min(S, first + piece_len));
+                pc.members.reserve(cuts[k].size());
+                for (uint32_t pos : cuts[k]) pc.members.push_back(members[pos]);
                 pc.share_rings = true;
-                pc.first = first == 0;
+                pc.first = k == 0;
                 pieces.push_back(std::move(pc));
             }
         }

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <set>
+#include <utility>
 
 namespace afsim {
 
@@ -604,6 +606,32 @@ void default_bands(AfBand out[AFSIM_NUM_BANDS]) {  // dsp/eq.rs:11-23,125-140
         out[i].slope_db_per_octave = 12;
         out[i].enabled = 1;
     }
+}
+
+std::vector<std::vector<uint32_t>> cut_stream_group(const std::vector<uint32_t>& passage, const std::vector<uint32_t>& eq_class,
+                                                    int max_streams) {
+    const size_t S = passage.size();
+    std::vector<uint32_t> order(S);
+    for (size_t i = 0; i < S; ++i) order[i] = static_cast<uint32_t>(i);
+    std::vector<std::vector<uint32_t>> pieces;
+    bool cut = max_streams >= 32 && S > static_cast<size_t>(max_streams) && eq_class.size() == S;
+    if (cut) {
+        std::set<std::pair<uint32_t, uint32_t>> distinct;
+        for (size_t i = 0; i < S && distinct.size() * 4 <= static_cast<size_t>(max_streams); ++i)
+            distinct.emplace(passage[i], eq_class[i]);
+        cut = distinct.size() * 4 <= static_cast<size_t>(max_streams);
+    }
+    if (!cut) {
+        pieces.push_back(std::move(order));
+        return pieces;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return passage[x] < passage[y]; });
+    const size_t n_pieces = (S + max_streams - 1) / max_streams;
+    const size_t piece_len = ((S + n_pieces - 1) / n_pieces + 31) / 32 * 32;  // <= max_streams when that is a multiple of 32
+    const size_t len = std::min(piece_len, static_cast<size_t>(max_streams));
+    for (size_t first = 0; first < S; first += len)
+        pieces.emplace_back(order.begin() + first, order.begin() + std::min(S, first + len));
+    return pieces;
 }
 
 }  // namespace afsim

@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/afsim.h"
 #include "afsim_cleanup.h"
@@ -55,6 +56,14 @@ int plan_makeup_control(const AfAutoMakeupSettings& settings, double sample_rate
 // number of sections per band.
 void plan_eq_sections(const AfBand bands[AFSIM_NUM_BANDS], bool typed, double sample_rate, double coeffs[kMaxSections][5],
                       int band_sections[AFSIM_NUM_BANDS]);
+
+// Large compressor grids (afsim_api.cu, build_sweep): the streams of one batch (`passage[i]`, `eq_class[i]` per
+// stream, any order) are cut into pieces of at most `max_streams` when they cover few distinct (passage, EQ class)
+// pairs (4 x pairs <= max_streams, so that every piece still shares its prefix).  The streams of a passage stay
+// together (stable order otherwise), pieces are balanced and a multiple of 32 streams long (the last one may be
+// shorter).  Returns the pieces as lists of stream positions; one piece = not cut.
+std::vector<std::vector<uint32_t>> cut_stream_group(const std::vector<uint32_t>& passage, const std::vector<uint32_t>& eq_class,
+                                                    int max_streams);
 
 void chain_settings_default(AfChainSettings* out);
 void default_bands(AfBand out[AFSIM_NUM_BANDS]);

@@ -33,6 +33,7 @@ def lib() -> C.CDLL:
         L.hostsim_makeup_control.argtypes = [f32p, C.c_size_t, C.c_double, C.POINTER(C.c_double), C.c_size_t, C.c_double,
                                              C.c_double, C.POINTER(abi.AfAutoMakeupSettings), C.c_int, C.c_int, C.c_int,
                                              f32p, f32p]
+        L.hostsim_cut_group.argtypes = [u32p, u32p, C.c_size_t, C.c_int, u32p, u32p]
         L.hostsim_eq_scan.argtypes = [f32p, C.c_size_t, C.c_double, C.POINTER(abi.AfBand), C.c_int, f32p]
         _lib = L
     return _lib
@@ -97,3 +98,15 @@ def eq_scan(audio, sample_rate, bands, log2_len=6):
     if rc != abi.AFSIM_OK:
         raise HostsimError(lib().hostsim_last_error().decode())
     return out
+
+
+def cut_group(passage, eq_class, max_streams):
+    """-> (piece index, position inside the piece) of every stream, number of pieces (cut_stream_group, afsim_plan.cpp)."""
+    p = np.ascontiguousarray(passage, dtype=np.uint32)
+    c = np.ascontiguousarray(eq_class, dtype=np.uint32)
+    piece = np.full(p.size, 0xFFFFFFFF, dtype=np.uint32)
+    pos = np.full(p.size, 0xFFFFFFFF, dtype=np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    n = lib().hostsim_cut_group(p.ctypes.data_as(u32p), c.ctypes.data_as(u32p), p.size, int(max_streams),
+                                piece.ctypes.data_as(u32p), pos.ctypes.data_as(u32p))
+    return piece, pos, n

@@ -466,6 +466,19 @@ int run_hostsim(const std::vector<CandidatePlan>& plans, const float* const* pas
 
 extern "C" {
 
+// Piece index of every stream of a batch (afsim_plan.cpp, cut_stream_group); returns the number of pieces.
+int hostsim_cut_group(const uint32_t* passage, const uint32_t* eq_class, size_t n, int max_streams, uint32_t* out_piece,
+                      uint32_t* out_position) {
+    const std::vector<uint32_t> p(passage, passage + n), c(eq_class, eq_class + n);
+    const std::vector<std::vector<uint32_t>> pieces = cut_stream_group(p, c, max_streams);
+    for (size_t k = 0; k < pieces.size(); ++k)
+        for (size_t j = 0; j < pieces[k].size(); ++j) {
+            out_piece[pieces[k][j]] = static_cast<uint32_t>(k);
+            out_position[pieces[k][j]] = static_cast<uint32_t>(j);
+        }
+    return static_cast<int>(pieces.size());
+}
+
 // Planner outputs, for coefficient-level tests against the oracle.
 int hostsim_plan(const AfBand* bands, const AfChainSettings* settings, double fs, CandidateParams* out, uint32_t* structure,
                  uint32_t* lookahead) {

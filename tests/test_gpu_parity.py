@@ -287,3 +287,33 @@ def test_cut_compressor_grid_is_bit_identical(sim, path, monkeypatch):
     m0, a0, _ = pyoracle.chain_render(passages[3], FS, cand_list[11].bands, cand_list[11].settings, return_audio=True)
     assert audio_within_tolerance(a0, a_cut[11 * 4 + 3]) <= 0.0
     assert metric_mismatches(m0, m_cut[11 * 4 + 3], tol_db=TOL_DB) == {}
+
+
+@pytest.mark.parametrize("path", ["fused", "split"])
+def test_deesser_target_stage_cut_is_bit_identical(sim, path, monkeypatch):
+    """The de-esser's R_c1 as one serial kernel and cut three ways (R_c1a -> M_c1b -> R_c1c, AFSIM_DE_CUT): metrics
+    and audio identical bit for bit, auto and manual mode, staged and direct kernel variants, own and shared
+    detector front (72 streams over two passages share it)."""
+    monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
+    n = 30 * 480 + 211
+    passages = [golden_chain_input(blocks=31)[:n].copy(), speech_like(n, seed=91, level=0.8)]
+    bands, overrides = CASES["golden_like"]  # de-esser auto mode, de-esser before the EQ
+    cand_list = [candidate(bands, **dict(overrides, deesser_auto_amount=0.2 + 0.02 * i, deesser_max_reduction_db=3.0 + 0.3 * i))
+                 for i in range(30)]
+    cand_list += [candidate(bands, **dict(overrides, deesser_auto_enabled=False, deesser_threshold_db=-50.0 + i,
+                                          deesser_max_reduction_db=4.0 + i)) for i in range(6)]
+    cands = candidate_array(cand_list)
+    monkeypatch.setenv("AFSIM_DE_CUT", "1")
+    m_one, a_one = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    monkeypatch.setenv("AFSIM_DE_CUT", "2")
+    m_cut, a_cut = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    for i in range(len(cand_list) * 2):
+        d0, d1 = abi.metrics_to_dict(m_one[i]), abi.metrics_to_dict(m_cut[i])
+        d0.pop("candidate_runtime_ms"), d1.pop("candidate_runtime_ms")
+        assert d0 == d1, i
+        assert np.array_equal(a_one[i], a_cut[i]), i
+    assert max(m_cut[i].deesser_gain_reduction_db for i in range(len(cand_list) * 2)) > 0.05
+    for c, p in ((3, 0), (32, 1)):
+        m0, a0, _ = pyoracle.chain_render(passages[p], FS, cand_list[c].bands, cand_list[c].settings, return_audio=True)
+        assert audio_within_tolerance(a0, a_cut[c * 2 + p]) <= 0.0
+        assert metric_mismatches(m0, m_cut[c * 2 + p], tol_db=TOL_DB) == {}

@@ -107,6 +107,35 @@ def test_abstain_when_no_scale_is_safe():
     assert r["validation_confidence"] == 0.42 and r["analysis_confidence"] == 0.58
 
 
+def test_large_compressor_grids_are_cut_along_passages():
+    """build_sweep's piece planner (cut_stream_group): every stream lands in exactly one piece, pieces hold at most
+    the limit and whole multiples of 32 streams (but the last), a passage's streams stay together and in order, and
+    groups that are small or do not share their prefix stay whole."""
+    from tests import hostsim
+    n_pass, n_cand = 8, 1000  # pair i = candidate i // n_pass, passage i % n_pass, as in a full cross product
+    passage = np.arange(n_pass * n_cand, dtype=np.uint32) % n_pass
+    one_eq = np.zeros(passage.size, dtype=np.uint32)
+    piece, pos, n = hostsim.cut_group(passage, one_eq, 2048)
+    assert n == 4 and piece.max() == 3 and (pos != 0xFFFFFFFF).all()
+    sizes = np.bincount(piece)
+    assert sizes.sum() == passage.size and sizes.max() <= 2048 and all(k % 32 == 0 for k in sizes[:-1])
+    order = np.lexsort((pos, piece))  # streams in execution order
+    assert (np.diff(passage[order].astype(np.int64)) >= 0).all()  # passage by passage
+    for p in range(n_pass):
+        mine = order[passage[order] == p]
+        assert (np.diff(mine.astype(np.int64)) > 0).all()  # stable inside a passage
+    # at most two pieces see a given passage boundary: a piece spans few passages, so it shares as much as the group
+    assert max(len(set(passage[piece == k])) for k in range(n)) <= 3
+    # small group / every stream its own EQ / no limit: one piece in the caller's order
+    for args in ((passage[:1500], one_eq[:1500], 2048), (passage, np.arange(passage.size, dtype=np.uint32), 2048),
+                 (passage, one_eq, 1 << 30)):
+        piece, pos, n = hostsim.cut_group(*args)
+        assert n == 1 and (piece == 0).all() and (pos == np.arange(args[0].size)).all()
+    # a limit that is not a multiple of 32 still bounds the pieces
+    piece, pos, n = hostsim.cut_group(passage, one_eq, 1000)
+    assert np.bincount(piece).max() <= 1000 and np.bincount(piece).sum() == passage.size
+
+
 def test_shard_streams_is_balanced_and_complete():
     rng = np.random.default_rng(0)
     costs = rng.choice([50.0, 56.0, 80.0], size=1000) * 480000
