@@ -141,12 +141,14 @@ def simulate_auto_eq_chain(audio, sample_rate: float, bands, settings: Mapping[s
 
 
 def simulate_auto_eq_chain_batch(passages, sample_rate: float, candidates, *, pair_passage=None, pair_candidate=None,
-                                 device: int = 0) -> list[dict[str, Any]]:
+                                 return_output_audio: bool = False, device: int = 0) -> list[dict[str, Any]]:
     """Batched form: ``candidates`` = sequence of ``(bands, settings)`` as simulate_auto_eq_chain takes them.
 
     Default pairing is the full cross product, candidate-major (pair = candidate * n_passages + passage).
     What apply_headroom_validation (headroom.py:306-320) and _calibrate_compressor_threshold
-    (voice_setup.py:916-966) evaluate one call at a time."""
+    (voice_setup.py:916-966) evaluate one call at a time.  With ``return_output_audio`` every dict carries
+    ``"output_audio"`` (python_api.rs:701-712) -- as a float32 array, not a list: the callers
+    (voice_setup.py:1535-1536) pass it to ``np.asarray(..., dtype=np.float32)`` either way."""
     sample_rate = float(sample_rate)
     _check_rate_chain(sample_rate)
     arrs = [_audio_1d(p) for p in passages]
@@ -159,9 +161,14 @@ def simulate_auto_eq_chain_batch(passages, sample_rate: float, candidates, *, pa
             cands[i].bands[b] = band_arr[b]
         cands[i].settings = st
     cands_view = (abi.AfCandidate * len(candidates)).from_buffer(cands) if len(candidates) else cands
-    metrics, _ = simulator(device).chain_sweep(arrs, sample_rate, cands_view, pair_passage, pair_candidate)
+    metrics, audio = simulator(device).chain_sweep(arrs, sample_rate, cands_view, pair_passage, pair_candidate,
+                                                   return_audio=bool(return_output_audio))
     n = len(arrs) * len(candidates) if pair_passage is None else len(pair_passage)
-    return [abi.metrics_to_dict(metrics[i]) for i in range(n)]
+    out = [abi.metrics_to_dict(metrics[i]) for i in range(n)]
+    if return_output_audio:
+        for i in range(n):
+            out[i]["output_audio"] = audio[i]
+    return out
 
 
 _MAKEUP_F64 = ("threshold_db", "ratio", "attack_ms", "release_ms", "makeup_gain_db", "target_lufs", "vad_reliability")
