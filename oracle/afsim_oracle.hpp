@@ -11,7 +11,13 @@
 //
 // Parity pin: reproduces the reference's golden vector
 // rust-core/src/audio/processor/tests.rs:1784-1885 and the known-answer tests
-// listed in DESIGN.md (tests/test_oracle_*.py).  The auto-makeup loudness meter
+// listed in DESIGN.md (tests/test_oracle_*.py), and three evaluation reports the
+// real reference published from its native core (evaluation/processing-order-,
+// dynamics-aliasing-, limiter-lookahead-report.json: de-esser / EQ order over the
+// generated 96-clip corpus, compressor at 48 / 192 kHz, limiter lookaheads) when
+// the reference's own tool code runs with this oracle as its native core -- bit
+// for bit but for two f32 log10 conversions one ulp apart
+// (tests/test_oracle_reference_report.py).  The auto-makeup loudness meter
 // restates the third-party `ebur128` crate 0.1.10 (absent from the reference
 // tree): that sub-path is "parity unpinned".
 //
