@@ -56,6 +56,23 @@ def test_limiter_and_dynamics_studies_match_the_published_values():
         assert entry["oracle"]["reference_peak_gain_reduction_db"] == entry["published"]["reference_peak_gain_reduction_db"]
 
 
+def test_eq_filter_types_study_matches_the_published_values():
+    """Response renderer and simulate_eq_v2 (evaluation/eq-filter-types-report.json, analytic + headroom prediction):
+    notch probes, the maximum over 250 random 10-band typed settings (rng 0xE041) and the measured gain of a 12 dB
+    bell through simulate_eq_v2 identical; the Butterworth cutoffs within 2e-15 dB (libm ulps of another platform)."""
+    g = json.loads((GOLDEN / "reference_reports.json").read_text())["eq_filter_types"]
+    pub, ours = g["published"], g["oracle"]
+    assert ours["analytic"]["notch"]["response_db"] == pub["analytic"]["notch"]["response_db"]
+    assert ours["analytic"]["random_boundary_stress"] == pub["analytic"]["random_boundary_stress"]
+    assert pub["analytic"]["random_boundary_stress"]["max_absolute_response_db"] == 1206.650162779802
+    assert ours["analytic"]["default_response_max_absolute_delta_db"] == pub["analytic"]["default_response_max_absolute_delta_db"] == 0.0
+    for a, b in zip(pub["analytic"]["cutoff"], ours["analytic"]["cutoff"]):
+        assert (a["filter_type"], a["slope_db_per_octave"]) == (b["filter_type"], b["slope_db_per_octave"])
+        assert abs(a["measured_db"] - b["measured_db"]) <= 4e-15
+    for key in ("predicted_gain_db", "measured_gain_db", "absolute_error_db", "reported_max_response_db"):
+        assert ours["headroom_prediction"][key] == pub["headroom_prediction"][key], key
+
+
 @pytest.mark.skipif(not (REF / "python" / "tools" / "evaluate_dynamics_aliasing.py").exists(),
                     reason="reference tree not present (only in the build container)")
 def test_live_recomputation_with_the_reference_tool_code():

@@ -9,6 +9,10 @@ with the oracle standing in for the native core (`mic_eq/__init__.py:38-46` pick
   the compressor (0.5 ms attack, 8:1) at 48 kHz and 192 kHz: peak gain reduction at both rates, alignment lag,
   waveform / folded error of the 48 kHz render against the decimated 192 kHz render.
 
+* `python/tools/evaluate_eq_filter_types.py` -> `evaluation/eq-filter-types-report.json`, analytic measurements
+  and headroom prediction: `eq_magnitude_response(_v2)` on the default bands, every Butterworth slope at its cutoff,
+  a notch, 250 random typed 10-band settings, and `simulate_eq_v2` on a 2 s sine through a 12 dB bell.
+
 Run in the build container (imports the reference tree, copies nothing).  Writes tests/golden/reference_reports.json:
 the published values beside the oracle's; tests/test_oracle_reference_report.py checks them.
 """
@@ -39,6 +43,23 @@ def oracle_simulate_auto_eq_chain(audio, sample_rate, bands, settings=None):
     return result
 
 
+def oracle_eq_magnitude_response(frequencies_hz, bands, sample_rate):
+    return pyoracle.eq_response(list(frequencies_hz), abi.legacy_bands(bands), float(sample_rate), typed=False).tolist()
+
+
+def oracle_eq_magnitude_response_v2(frequencies_hz, bands, sample_rate):
+    return pyoracle.eq_response(list(frequencies_hz), abi.typed_bands(bands), float(sample_rate), typed=True).tolist()
+
+
+def oracle_simulate_eq_v2(audio, sample_rate, bands, return_output_audio=False):
+    st, out = pyoracle.eq_render(np.asarray(audio, dtype=np.float32), float(sample_rate), abi.typed_bands(bands),
+                                 return_audio=return_output_audio)
+    result = {name: getattr(st, name) for name, _ in st._fields_}
+    if return_output_audio:
+        result["output_audio"] = out
+    return result
+
+
 def install_shim():
     shim = types.ModuleType("mic_eq_core")
     shim.AudioProcessor = type("AudioProcessor", (), {})
@@ -46,6 +67,9 @@ def install_shim():
     shim.list_input_devices = lambda: []
     shim.list_output_devices = lambda: []
     shim.simulate_auto_eq_chain = oracle_simulate_auto_eq_chain
+    shim.eq_magnitude_response = oracle_eq_magnitude_response
+    shim.eq_magnitude_response_v2 = oracle_eq_magnitude_response_v2
+    shim.simulate_eq_v2 = oracle_simulate_eq_v2
     sys.modules["mic_eq_core"] = shim
     sys.path.insert(0, str(REF / "python"))
     sys.path.insert(0, str(REF / "python" / "tools"))
@@ -81,9 +105,38 @@ def dynamics_study():
     return out
 
 
+def eq_filter_types_study():
+    """evaluate_eq_filter_types.py: the analytic measurements (response renderer: default bands legacy vs typed, the
+    -3.01 dB cutoff of every Butterworth slope, the notch, 250 random 10-band settings from rng 0xE041) and the
+    headroom prediction (a 12 dB bell at 1 kHz: response renderer against simulate_eq_v2 on a 2 s sine)."""
+    tool = importlib.import_module("evaluate_eq_filter_types")
+    report = json.loads((REF / "evaluation" / "eq-filter-types-report.json").read_text())["measurements"]
+    published = {"analytic": report["analytic"], "headroom_prediction": report["headroom_prediction"]}
+    cases = int(report["analytic"]["random_boundary_stress"]["cases"])
+    ours = {"analytic": tool._analytic_measurements(cases), "headroom_prediction": tool._headroom_prediction_measurement()}
+    return {"published": published, "oracle": ours}
+
+
+def _flatten(obj, prefix=""):
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            yield from _flatten(v, f"{prefix}{k}.")
+    elif isinstance(obj, list):
+        for i, v in enumerate(obj):
+            yield from _flatten(v, f"{prefix}{i}.")
+    else:
+        yield prefix[:-1], obj
+
+
 def main():
     install_shim()
-    result = {"limiter_lookahead_controlled": limiter_study(), "dynamics_aliasing": dynamics_study()}
+    result = {"limiter_lookahead_controlled": limiter_study(), "dynamics_aliasing": dynamics_study(),
+              "eq_filter_types": eq_filter_types_study()}
+    pub, ours = dict(_flatten(result["eq_filter_types"]["published"])), dict(_flatten(result["eq_filter_types"]["oracle"]))
+    for k, v in pub.items():
+        if isinstance(v, str):
+            continue
+        print(f"eq types {k:58s} published {v!r:24} oracle {ours.get(k)!r:24} |diff| {abs(float(ours[k]) - float(v)):.3e}")
     (ROOT / "tests" / "golden" / "reference_reports.json").write_text(json.dumps(result, indent=1) + "\n")
     worst = 0.0
     for key, entry in result["limiter_lookahead_controlled"].items():
