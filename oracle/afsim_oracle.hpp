@@ -19,7 +19,9 @@
 // for bit but for two f32 log10 conversions one ulp apart
 // (tests/test_oracle_reference_report.py).  The auto-makeup loudness meter
 // restates the third-party `ebur128` crate 0.1.10 (absent from the reference
-// tree): that sub-path is "parity unpinned".
+// tree): that sub-path is "parity unpinned" at source level; nine of the eleven
+// numbers of the reference's published auto-makeup benchmark are reproduced to nine
+// decimals (tests/test_oracle_auto_makeup_benchmark.py).
 //
 // Every class cites the reference file:line it follows (paths relative to the
 // reference checkout, rust-core/src/...).

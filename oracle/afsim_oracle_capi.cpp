@@ -516,6 +516,14 @@ void orc_comp_process_block(void* c, float* buf, size_t n) { static_cast<Compres
 void orc_comp_process_samples(void* c, float* buf, size_t n) {
     for (size_t i = 0; i < n; ++i) buf[i] = static_cast<Compressor*>(c)->process_sample(buf[i]);
 }
+void orc_comp_set_target_lufs(void* c, double t) { static_cast<Compressor*>(c)->set_target_lufs(t); }
+void orc_comp_set_noise_reference_reliability(void* c, double r) { static_cast<Compressor*>(c)->set_noise_reference_reliability(r); }
+// process_block_inplace_with_activity_control (compressor.rs:700-722): evidence = Some(..) when has_evidence
+void orc_comp_process_block_with_activity(void* c, float* buf, size_t n, int has_evidence, double vad_probability,
+                                          double vad_reliability, double noise_floor_db, double live_noise_reliability) {
+    const AutoMakeupActivityInput ev{vad_probability, vad_reliability, noise_floor_db, live_noise_reliability};
+    static_cast<Compressor*>(c)->process_block_with_activity(buf, n, has_evidence ? &ev : nullptr);
+}
 double orc_comp_gain_reduction(void* c) { return static_cast<Compressor*>(c)->current_gain_reduction(); }
 double orc_comp_makeup_gain(void* c) { return static_cast<Compressor*>(c)->current_makeup_gain(); }
 double orc_comp_plosive_ratio(void* c) { return static_cast<Compressor*>(c)->plosive_ratio(); }

@@ -89,6 +89,10 @@ def lib() -> C.CDLL:
             getattr(L, f"orc_comp_{name}").argtypes = [C.c_void_p, C.c_int]
         L.orc_comp_process_block.argtypes = [C.c_void_p, f32p, C.c_size_t]
         L.orc_comp_process_samples.argtypes = [C.c_void_p, f32p, C.c_size_t]
+        L.orc_comp_set_target_lufs.argtypes = [C.c_void_p, C.c_double]
+        L.orc_comp_set_noise_reference_reliability.argtypes = [C.c_void_p, C.c_double]
+        L.orc_comp_process_block_with_activity.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_int, C.c_double, C.c_double,
+                                                           C.c_double, C.c_double]
         for name in ("gain_reduction", "makeup_gain", "plosive_ratio"):
             getattr(L, f"orc_comp_{name}").restype = C.c_double
             getattr(L, f"orc_comp_{name}").argtypes = [C.c_void_p]
