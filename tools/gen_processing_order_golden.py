@@ -44,13 +44,12 @@ def oracle_door(audio, sample_rate, bands, settings):
 
 
 def study(door):
+    import importlib
+
     from mic_eq.analysis.deesser_corpus import CORPUS_CASES, generate_deesser_case
 
-    def band_energy(audio, sample_rate, low, high):  # evaluate_processing_order.py:362-366
-        spectrum = np.fft.rfft(audio * np.hanning(audio.size))
-        frequencies = np.fft.rfftfreq(audio.size, 1.0 / sample_rate)
-        mask = (frequencies >= low) & (frequencies <= high)
-        return float(np.sum(np.square(np.abs(spectrum[mask]))))
+    sys.path.insert(0, str(REF / "python" / "tools"))
+    band_energy = importlib.import_module("evaluate_processing_order")._band_energy  # the tool's own measure (:362-366)
 
     rows = []
     for spec in CORPUS_CASES:
