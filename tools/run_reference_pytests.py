@@ -8,7 +8,7 @@ name, so `from mic_eq import simulate_auto_eq_chain, ...` in the reference's tes
 reference is copied; the files are collected where they lie under /root/reference (PyQt6 is absent, hence
 --noconftest).
 
-usage: python tools/run_reference_pytests.py [--door oracle|gpu] [extra pytest args]
+usage: python tools/run_reference_pytests.py [--door oracle|gpu] [--fast] [extra pytest args]
 """
 import sys
 from pathlib import Path
@@ -55,8 +55,15 @@ class OracleSimulator:
         return (pyoracle.eq_response(freqs, bands, sample_rate, typed=typed),)
 
 
+FAST = FILES[:4]  # seconds; the voice-setup and Auto-EQ files render hundreds of passages through the CPU oracle
+
+
 def main(argv):
     door = "oracle"
+    files_to_run = FILES
+    if "--fast" in argv:
+        argv.remove("--fast")
+        files_to_run = FAST
     if "--door" in argv:
         i = argv.index("--door")
         door = argv[i + 1]
@@ -72,7 +79,7 @@ def main(argv):
     import pytest
 
     tests = REF / "python" / "tests"
-    files = [str(tests / f) for f in FILES]
+    files = [str(tests / f) for f in files_to_run]
     skip = "not (" + " or ".join(d.split("::")[1] for d in DESELECT) + ")"
     return pytest.main(["--noconftest", "-p", "no:cacheprovider", "--rootdir", "/tmp", "-q", "-k", skip, *files, *argv])
 
