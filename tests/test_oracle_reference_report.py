@@ -40,6 +40,11 @@ def test_processing_order_study_matches_the_published_medians_bit_for_bit():
 
 def test_limiter_and_dynamics_studies_match_the_published_values():
     g = json.loads((GOLDEN / "reference_reports.json").read_text())
+    # the reports were produced from exactly the sources of this reference tree (limiter.rs, true_peak.rs, biquad.rs,
+    # eq.rs, lib.rs, python_api.rs and the tools themselves)
+    assert g["report_source_hashes"]["limiter-lookahead-report.json"] is True
+    assert g["report_source_hashes"]["eq-filter-types-report.json"] is True
+    assert "rust-core/src/dsp/true_peak.rs" in g["report_source_hashes"]["limiter-lookahead-report.json:files"]
     assert sorted(g["limiter_lookahead_controlled"]) == ["0.5", "1.0", "2.0"]
     exact = 0
     for key, entry in g["limiter_lookahead_controlled"].items():

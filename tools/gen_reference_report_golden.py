@@ -117,6 +117,18 @@ def eq_filter_types_study():
     return {"published": published, "oracle": ours}
 
 
+def source_hashes_match():
+    """The reports that record hashes of the sources they were produced from: are those this tree's files?"""
+    import hashlib
+    out = {}
+    for name in ("limiter-lookahead-report.json", "eq-filter-types-report.json"):
+        hashes = json.loads((REF / "evaluation" / name).read_text())["source_sha256"]
+        out[name] = all((REF / rel).exists() and hashlib.sha256((REF / rel).read_bytes()).hexdigest() == digest
+                        for rel, digest in hashes.items())
+        out[name + ":files"] = sorted(hashes)
+    return out
+
+
 def _flatten(obj, prefix=""):
     if isinstance(obj, dict):
         for k, v in obj.items():
@@ -131,7 +143,7 @@ def _flatten(obj, prefix=""):
 def main():
     install_shim()
     result = {"limiter_lookahead_controlled": limiter_study(), "dynamics_aliasing": dynamics_study(),
-              "eq_filter_types": eq_filter_types_study()}
+              "eq_filter_types": eq_filter_types_study(), "report_source_hashes": source_hashes_match()}
     pub, ours = dict(_flatten(result["eq_filter_types"]["published"])), dict(_flatten(result["eq_filter_types"]["oracle"]))
     for k, v in pub.items():
         if isinstance(v, str):
