@@ -36,14 +36,17 @@ struct DevicePool {
     std::mutex mu;
     std::multimap<size_t, void*> free_blocks;
     size_t cached_bytes = 0;
-    static constexpr size_t kMaxCached = size_t(96) << 30;
-    cudaError_t take(size_t bytes, void** out) {
+    size_t max_cached = size_t(96) << 30;  // AFSIM_POOL_MAX_GB at afsim_create; afsim_trim() gives everything back
+    // best fit: the smallest cached block that holds `bytes` and wastes at most a quarter of itself
+    cudaError_t take(size_t bytes, void** out, size_t* actual) {
+        *actual = bytes;
         {
             std::lock_guard<std::mutex> lock(mu);
-            auto it = free_blocks.find(bytes);
-            if (it != free_blocks.end()) {
+            auto it = free_blocks.lower_bound(bytes);
+            if (it != free_blocks.end() && it->first - bytes <= it->first / 4) {
                 *out = it->second;
-                cached_bytes -= bytes;
+                *actual = it->first;
+                cached_bytes -= it->first;
                 free_blocks.erase(it);
                 return cudaSuccess;
             }
@@ -58,7 +61,7 @@ struct DevicePool {
     }
     void give(size_t bytes, void* p) {
         std::lock_guard<std::mutex> lock(mu);
-        if (cached_bytes + bytes > kMaxCached) {
+        if (cached_bytes + bytes > max_cached) {
             cudaFree(p);
             return;
         }
@@ -73,6 +76,7 @@ struct DevicePool {
     }
 };
 
+struct AfsimSweep;
 struct AfsimHandle {
     int device = 0;
     DevicePool pool;
@@ -82,6 +86,8 @@ struct AfsimHandle {
     cudaStream_t stage_stream_map[kMaxStages] = {};  // low priority: map kernels that fill every SM
     cudaEvent_t ev_fork = nullptr;
     std::string error;
+    std::recursive_mutex call_mu;     // one call at a time per handle (include/afsim.h: threading contract)
+    std::set<AfsimSweep*> live;       // sweeps whose buffers come from `pool`: detached by afsim_destroy
 };
 
 namespace {
@@ -100,8 +106,8 @@ struct DeviceBuffers {  // returns what it allocated to the handle's pool
     template <typename T>
     cudaError_t alloc(T** out, size_t count) {
         void* p = nullptr;
-        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
-        const cudaError_t err = pool ? pool->take(bytes, &p) : cudaMalloc(&p, bytes);
+        size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
+        const cudaError_t err = pool ? pool->take(bytes, &p, &bytes) : cudaMalloc(&p, bytes);
         if (err != cudaSuccess) return err;
         blocks.emplace_back(bytes, p);
         *out = static_cast<T*>(p);
@@ -144,7 +150,16 @@ struct AfsimSweep {
     int kernels_per_launch = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool launched = false;
+    AfsimHandle* owner = nullptr;  // nullptr once the handle is gone (afsim_destroy detaches live sweeps)
+    int device = 0;
+    bool quiesced = false;         // afsim_sweep_release synchronised the streams this sweep ran on
     ~AfsimSweep() {
+        // error paths (a failed build / launch) get here with copies or kernels possibly still queued: nothing may
+        // hand these buffers to the next sweep before the device is idle
+        if (!quiesced) {
+            cudaSetDevice(device);
+            cudaDeviceSynchronize();
+        }
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_stop) cudaEventDestroy(ev_stop);
     }
@@ -166,6 +181,8 @@ int cuda_fail(AfsimHandle* h, cudaError_t err, const char* what) {
         const cudaError_t af_err__ = (expr);                     \
         if (af_err__ != cudaSuccess) return cuda_fail((h), af_err__, #expr); \
     } while (0)
+
+#define AF_LOCK(h) std::lock_guard<std::recursive_mutex> af_lock__((h)->call_mu)
 
 int env_int(const char* name, int fallback) {
     const char* v = std::getenv(name);
@@ -204,6 +221,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
                 const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs, int want_audio,
                 AfsimSweep** out_sweep, const SweepOptions& opt = SweepOptions()) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (!out_sweep) return set_error(h, AFSIM_INVALID_ARGUMENT, "out_sweep is null");
     *out_sweep = nullptr;
@@ -230,6 +248,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
 
     auto sweep = std::make_unique<AfsimSweep>();
     sweep->mem.pool = &h->pool;
+    sweep->device = h->device;
     sweep->n_pairs = n_pairs;
 
     // passages -> one device pool
@@ -767,6 +786,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
     AF_CUDA(h, cudaEventCreate(&sweep->ev_start));
     AF_CUDA(h, cudaEventCreate(&sweep->ev_stop));
     AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    sweep->owner = h;
+    h->live.insert(sweep.get());
     *out_sweep = sweep.release();
     return AFSIM_OK;
 }
@@ -898,16 +919,19 @@ int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle
         g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err);
         return AFSIM_CUDA_ERROR;
     }
-    auto h = std::make_unique<AfsimHandle>();
+    AfsimHandle* h = new AfsimHandle();
     h->device = device_ordinal;
+    h->pool.max_cached = static_cast<size_t>(env_int("AFSIM_POOL_MAX_GB", 96)) << 30;
+    auto fail = [&](const char* what, cudaError_t e) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        afsim_destroy(h);  // destroys whatever was created so far
+        return AFSIM_CUDA_ERROR;
+    };
     if (cuda_stream) {
         h->stream = static_cast<cudaStream_t>(cuda_stream);
     } else {
         err = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-        if (err != cudaSuccess) {
-            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(err);
-            return AFSIM_CUDA_ERROR;
-        }
+        if (err != cudaSuccess) return fail("cudaStreamCreate", err);
         h->own_stream = true;
     }
     int prio_least = 0, prio_greatest = 0;
@@ -915,32 +939,46 @@ int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle
     for (int i = 0; i < kMaxStages; ++i) {
         err = cudaStreamCreateWithPriority(&h->stage_stream[i], cudaStreamNonBlocking, prio_greatest);
         if (err == cudaSuccess) err = cudaStreamCreateWithPriority(&h->stage_stream_map[i], cudaStreamNonBlocking, prio_least);
-        if (err != cudaSuccess) {
-            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(err);
-            return AFSIM_CUDA_ERROR;
-        }
+        if (err != cudaSuccess) return fail("cudaStreamCreate", err);
     }
     err = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    if (err != cudaSuccess) {
-        g_create_error = std::string("cudaEventCreate: ") + cudaGetErrorString(err);
-        return AFSIM_CUDA_ERROR;
-    }
-    *out_handle = h.release();
+    if (err != cudaSuccess) return fail("cudaEventCreate", err);
+    *out_handle = h;
     return AFSIM_OK;
 }
 
 void afsim_destroy(AfsimHandle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (!h->live.empty()) {
+        // sweeps the caller still holds outlive the handle: they keep their device memory (freed with cudaFree by
+        // afsim_sweep_release(NULL, sweep)) but no longer point into this handle's pool
+        cudaDeviceSynchronize();
+        for (AfsimSweep* sw : h->live) {
+            sw->mem.pool = nullptr;
+            sw->owner = nullptr;
+            sw->quiesced = true;
+        }
+        h->live.clear();
+    }
     for (int i = 0; i < kMaxStages; ++i) {
         if (h->stage_stream[i]) cudaStreamDestroy(h->stage_stream[i]);
         if (h->stage_stream_map[i]) cudaStreamDestroy(h->stage_stream_map[i]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     h->pool.trim();
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int afsim_trim(AfsimHandle* h) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
+    std::lock_guard<std::recursive_mutex> lock(h->call_mu);
+    cudaSetDevice(h->device);
+    h->pool.trim();
+    return AFSIM_OK;
 }
 
 const char* afsim_last_error(const AfsimHandle* h) { return h ? h->error.c_str() : "null handle"; }
@@ -959,6 +997,7 @@ int afsim_sweep_prepare(AfsimHandle* h, const float* const* passages, const size
                         const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs, int want_audio,
                         AfsimSweep** out_sweep) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     if ((n_passages && (!passages || !passage_len)) || (n_candidates && !candidates))
         return set_error(h, AFSIM_INVALID_ARGUMENT, "null passages / candidates");
     PassageSource src;
@@ -971,6 +1010,7 @@ int afsim_sweep_prepare_synthetic(AfsimHandle* h, int kind, size_t n_passages, s
                                   const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
                                   const uint32_t* pair_candidate, size_t n_pairs, int want_audio, AfsimSweep** out_sweep) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     if (n_candidates && !candidates) return set_error(h, AFSIM_INVALID_ARGUMENT, "null candidates");
     if (kind != 0 && kind != 1) return set_error(h, AFSIM_INVALID_ARGUMENT, "synthetic kind must be 0 or 1");
     std::vector<size_t> lens(n_passages, passage_len);
@@ -983,6 +1023,7 @@ int afsim_sweep_prepare_synthetic(AfsimHandle* h, int kind, size_t n_passages, s
 
 int afsim_sweep_launch(AfsimHandle* h, AfsimSweep* sweep) {
     if (!h || !sweep) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     AF_CUDA(h, cudaSetDevice(h->device));
     AF_CUDA(h, cudaEventRecord(sweep->ev_start, h->stream));
@@ -997,6 +1038,7 @@ int afsim_sweep_launch(AfsimHandle* h, AfsimSweep* sweep) {
 
 int afsim_sweep_collect(AfsimHandle* h, AfsimSweep* sweep, AfChainMetrics* out_metrics) {
     if (!h || !sweep || (!out_metrics && sweep->n_pairs)) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     AF_CUDA(h, cudaSetDevice(h->device));
     if (sweep->n_pairs)
@@ -1011,6 +1053,7 @@ int afsim_sweep_collect(AfsimHandle* h, AfsimSweep* sweep, AfChainMetrics* out_m
 
 int afsim_sweep_collect_audio(AfsimHandle* h, AfsimSweep* sweep, size_t pair, float* out_audio, size_t n) {
     if (!h || !sweep) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (!sweep->d_audio) return set_error(h, AFSIM_INVALID_ARGUMENT, "sweep was prepared without want_audio");
     if (pair >= sweep->n_pairs || n > sweep->pair_len[pair] || (!out_audio && n))
@@ -1029,6 +1072,7 @@ int afsim_sweep_kernel_count(const AfsimSweep* sweep) { return sweep ? sweep->ke
 
 int afsim_sweep_last_render_ms(AfsimHandle* h, AfsimSweep* sweep, float* out_ms) {
     if (!h || !sweep || !out_ms) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (!sweep->launched) return set_error(h, AFSIM_INVALID_ARGUMENT, "sweep has not been launched");
     AF_CUDA(h, cudaSetDevice(h->device));
@@ -1039,20 +1083,28 @@ int afsim_sweep_last_render_ms(AfsimHandle* h, AfsimSweep* sweep, float* out_ms)
 
 void afsim_sweep_release(AfsimHandle* h, AfsimSweep* sweep) {
     if (!sweep) return;
+    h = sweep->owner;  // the handle the sweep was prepared on, or nullptr once that handle was destroyed
     if (h) {
+        std::lock_guard<std::recursive_mutex> lock(h->call_mu);
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         for (int i = 0; i < kMaxStages; ++i) {
             cudaStreamSynchronize(h->stage_stream[i]);
             cudaStreamSynchronize(h->stage_stream_map[i]);
         }
+        sweep->quiesced = true;
+        h->live.erase(sweep);
+        delete sweep;
+        return;
     }
+    cudaSetDevice(sweep->device);
     delete sweep;
 }
 
 int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks, int capacity, int* out_kind,
                                float* out_ms, int* out_launches, int* out_n) {
     if (!h || !sweep || !out_kind || !out_ms || !out_launches || !out_n) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     *out_n = 0;
     if (sweep->batches.empty()) return AFSIM_OK;
@@ -1121,9 +1173,33 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
     return AFSIM_OK;
 }
 
+int afsim_sweep_batch_info(const AfsimSweep* sweep, int capacity, int out_info[6], int* out_stage_streams, int* out_n) {
+    if (!sweep || !out_info || !out_stage_streams || !out_n) return AFSIM_INVALID_ARGUMENT;
+    *out_n = 0;
+    for (int k = 0; k < 6; ++k) out_info[k] = 0;
+    out_info[0] = static_cast<int>(sweep->batches.size());
+    if (sweep->batches.empty()) return AFSIM_OK;
+    const Batch& b = *sweep->batches[0];
+    const int n_stages = static_cast<int>(b.stages.size());
+    if (capacity < n_stages) return AFSIM_INVALID_ARGUMENT;
+    out_info[1] = b.args.n_streams;
+    out_info[2] = b.chunk;
+    out_info[3] = b.slots;
+    out_info[4] = n_stages;
+    out_info[5] = b.args.n_samples;
+    for (int i = 0; i < n_stages; ++i) {
+        const StageKind k = b.stages[i].kind;
+        const bool shared = k == SK_INPUT_SHARED || k == SK_EQ_SHARED || k == SK_SPLIT_SHARED;
+        out_stage_streams[i] = shared ? b.shared_input.n_streams : b.args.n_streams;
+    }
+    *out_n = n_stages;
+    return AFSIM_OK;
+}
+
 int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_chunk, int n_chunks, int capacity, int* out_kind,
                                   float* out_busy_ms, float* out_period_ms, int* out_n) {
     if (!h || !sweep || !out_kind || !out_busy_ms || !out_period_ms || !out_n) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     *out_n = 0;
     if (sweep->batches.empty()) return AFSIM_OK;
@@ -1167,6 +1243,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
 
 int afsim_selftest_math(AfsimHandle* h, uint64_t n, uint64_t out_mismatches[6]) {
     if (!h || !out_mismatches) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     AF_CUDA(h, cudaSetDevice(h->device));
     DeviceBuffers mem;
@@ -1183,6 +1260,7 @@ int afsim_selftest_math(AfsimHandle* h, uint64_t n, uint64_t out_mismatches[6]) 
 
 int afsim_measure_issue_peak(AfsimHandle* h, int kind, double* out) {
     if (!h || !out || (kind != 0 && kind != 1)) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     AF_CUDA(h, cudaSetDevice(h->device));
     DeviceBuffers mem;
@@ -1217,6 +1295,7 @@ int afsim_chain_sweep(AfsimHandle* h, const float* const* passages, const size_t
                       double sample_rate, const AfCandidate* candidates, size_t n_candidates, const uint32_t* pair_passage,
                       const uint32_t* pair_candidate, size_t n_pairs, AfChainMetrics* out_metrics, float* const* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     bool want_audio = false;
     if (out_audio)
         for (size_t i = 0; i < n_pairs; ++i) want_audio = want_audio || out_audio[i] != nullptr;
@@ -1237,9 +1316,23 @@ int afsim_chain_sweep(AfsimHandle* h, const float* const* passages, const size_t
 
 // ---- single-stream entry points ----------------------------------------------------------------------------------
 
+namespace {
+struct SweepReleaser {  // every exit path of a call that owns a sweep goes through afsim_sweep_release (stream syncs first)
+    void operator()(AfsimSweep* s) const {
+        if (!s) return;
+        const std::string keep = s->owner ? s->owner->error : std::string();
+        AfsimHandle* owner = s->owner;
+        afsim_sweep_release(owner, s);
+        if (owner) owner->error = keep;
+    }
+};
+typedef std::unique_ptr<AfsimSweep, SweepReleaser> SweepGuard;
+}  // namespace
+
 int afsim_chain_render(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
                        const AfChainSettings* settings, AfChainMetrics* out_metrics, float* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     if (!bands || !settings || !out_metrics || (!audio && n)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
     const auto started = std::chrono::steady_clock::now();
     AfCandidate cand;
@@ -1259,6 +1352,7 @@ int afsim_chain_render(AfsimHandle* h, const float* audio, size_t n, double samp
 int afsim_eq_response(AfsimHandle* h, const double* frequencies_hz, size_t n_freqs, const AfBand* bands, size_t n_sets,
                       int typed, double sample_rate, double* out_db) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if ((!frequencies_hz && n_freqs) || (!bands && n_sets) || (!out_db && n_freqs && n_sets))
         return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
@@ -1391,6 +1485,7 @@ static int eq_render_scan(AfsimHandle* h, const float* audio, size_t n, double s
 int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_rate, const AfBand bands[AFSIM_NUM_BANDS],
                     AfEqRenderStats* out_stats, float* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (!bands || !out_stats || (!audio && n)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
     CandidatePlan plan;
@@ -1410,7 +1505,7 @@ int afsim_eq_render(AfsimHandle* h, const float* audio, size_t n, double sample_
     AfsimSweep* sweep = nullptr;
     rc = build_sweep(h, src, lens, 1, sample_rate, nullptr, 1, &plan, nullptr, nullptr, 1, out_audio ? 1 : 0, &sweep);
     if (rc != AFSIM_OK) return rc;
-    std::unique_ptr<AfsimSweep> guard(sweep);
+    SweepGuard guard(sweep);
     rc = afsim_sweep_launch(h, sweep);
     if (rc != AFSIM_OK) return rc;
     StreamAccum acc;
@@ -1462,6 +1557,7 @@ int afsim_auto_makeup_sweep(AfsimHandle* h, const float* const* audio, const siz
                             const double* const* vad, const double* noise_floor_db, const double* noise_reliability,
                             const AfAutoMakeupSettings* settings, float* const* out_traces, float* const* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (n_streams == 0) return AFSIM_OK;
     if (!audio || !len || !noise_floor_db || !noise_reliability || !settings || !out_traces)
@@ -1498,7 +1594,7 @@ int afsim_auto_makeup_sweep(AfsimHandle* h, const float* const* audio, const siz
     int rc = build_sweep(h, src, len, n_streams, sample_rate, nullptr, n_streams, plans.data(), idx.data(), idx.data(), n_streams,
                          want_audio ? 1 : 0, &sweep, opt);
     if (rc != AFSIM_OK) return rc;
-    std::unique_ptr<AfsimSweep> guard(sweep);
+    SweepGuard guard(sweep);
     rc = afsim_sweep_launch(h, sweep);
     if (rc != AFSIM_OK) return rc;
     std::vector<float> rows, mk_rows;
@@ -1538,6 +1634,7 @@ int afsim_auto_makeup_control(AfsimHandle* h, const float* audio, size_t n, doub
                               size_t n_vad, double noise_floor_db, double noise_reliability, const AfAutoMakeupSettings* settings,
                               float* out_traces, float* out_audio) {
     if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
     h->error.clear();
     if (!settings || (!audio && n) || (!vad_probabilities && n_vad) || (!out_traces && n))
         return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");

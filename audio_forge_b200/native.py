@@ -23,12 +23,12 @@ LIB_PATH = _PKG / "libafsim.so"
 _lib = None
 
 EXPORTS = (
-    "afsim_abi_version", "afsim_create", "afsim_destroy", "afsim_last_error", "afsim_create_error",
+    "afsim_abi_version", "afsim_create", "afsim_destroy", "afsim_trim", "afsim_last_error", "afsim_create_error",
     "afsim_chain_settings_default", "afsim_default_bands", "afsim_chain_render", "afsim_eq_render",
     "afsim_eq_response", "afsim_chain_sweep", "afsim_sweep_prepare", "afsim_sweep_prepare_synthetic",
     "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
     "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
-    "afsim_sweep_profile_stages", "afsim_sweep_profile_wavefront", "afsim_measure_issue_peak",
+    "afsim_sweep_profile_stages", "afsim_sweep_profile_wavefront", "afsim_sweep_batch_info", "afsim_measure_issue_peak",
     "afsim_selftest_math", "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
@@ -50,7 +50,7 @@ def build(force: bool = False) -> Path:
     csrc = _PKG / "csrc"
     if force:
         subprocess.run(["make", "-C", str(csrc), "clean"], check=True, capture_output=True)
-    proc = subprocess.run(["make", "-C", str(csrc)], capture_output=True, text=True)
+    proc = subprocess.run(["make", "-j4", "-C", str(csrc)], capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("building libafsim.so failed:\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
     return LIB_PATH
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.afsim_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
     L.afsim_destroy.argtypes = [vp]
     L.afsim_destroy.restype = None
+    L.afsim_trim.argtypes = [vp]
     L.afsim_last_error.argtypes = [vp]
     L.afsim_last_error.restype = C.c_char_p
     L.afsim_create_error.restype = C.c_char_p
@@ -101,6 +102,7 @@ def lib() -> C.CDLL:
     L.afsim_sweep_release.restype = None
     L.afsim_sweep_profile_stages.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, C.POINTER(C.c_int),
                                              C.POINTER(C.c_int)]
+    L.afsim_sweep_batch_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.afsim_measure_issue_peak.argtypes = [vp, C.c_int, f64p]
     L.afsim_sweep_profile_wavefront.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, f32p,
                                                 C.POINTER(C.c_int)]
@@ -165,6 +167,14 @@ class Sweep:
                                                              kinds, busy, period, C.byref(n)))
         return [(STAGE_NAMES[kinds[i]], float(busy[i]), float(period[i])) for i in range(n.value)]
 
+    def batch_info(self) -> dict:
+        """Shape of the first batch (what profile_stages / profile_wavefront time): streams per launch of every stage."""
+        cap = 32
+        info, streams, n = (C.c_int * 6)(), (C.c_int * cap)(), C.c_int(0)
+        self._sim._check(lib().afsim_sweep_batch_info(self._ptr, cap, info, streams, C.byref(n)))
+        return {"batches": info[0], "streams": info[1], "chunk": info[2], "slots": info[3], "stages": info[4],
+                "samples": info[5], "stage_streams": [int(streams[i]) for i in range(n.value)]}
+
     @property
     def kernel_count(self) -> int:
         return int(lib().afsim_sweep_kernel_count(self._ptr))
@@ -195,6 +205,7 @@ class Simulator:
         if rc != abi.AFSIM_OK:
             raise AfsimError(rc, L.afsim_create_error().decode())
         self._h = h
+        self.cuda_stream = cuda_stream  # None: the library's own stream
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -206,6 +217,10 @@ class Simulator:
             self.close()
         except Exception:
             pass
+
+    def trim(self) -> None:
+        """Give the handle's cached device buffers back to the driver."""
+        self._check(lib().afsim_trim(self._h))
 
     def _check(self, rc: int) -> None:
         if rc == abi.AFSIM_OK:

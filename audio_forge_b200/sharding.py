@@ -18,16 +18,16 @@ def shard_streams(costs: Sequence[float], world_size: int) -> list[np.ndarray]:
     """Greedy longest-processing-time split of streams over ranks, balanced by cost (e.g. EQ sections x
     samples: a 48 dB/oct candidate costs up to 4x in the EQ stage).  Deterministic; every rank computes
     the same assignment.  Returns the sorted stream indices of each rank."""
+    import heapq
+
     costs = np.asarray(costs, dtype=np.float64)
     order = np.argsort(-costs, kind="stable")
-    loads = np.zeros(world_size)
-    counts = np.zeros(world_size, dtype=np.int64)
+    heap = [(0.0, 0, r) for r in range(world_size)]  # (load, streams, rank): least loaded, then fewest streams
     owner = np.empty(costs.size, dtype=np.int64)
-    for i in order:
-        r = int(np.lexsort((counts, loads))[0])  # least loaded, then fewest streams
+    for i in order.tolist():
+        load, count, r = heapq.heappop(heap)
         owner[i] = r
-        loads[r] += costs[i]
-        counts[r] += 1
+        heapq.heappush(heap, (load + float(costs[i]), count + 1, r))
     return [np.sort(np.nonzero(owner == r)[0]) for r in range(world_size)]
 
 
@@ -92,18 +92,99 @@ def gather_metrics(local_metrics, local_indices: np.ndarray, n_total: int, group
     return bytes_to_metrics(out)
 
 
+class _DeviceBytes:
+    """Zero-copy view of device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "version": 2, "data": (int(ptr), False)}
+
+
+class DeviceGather:
+    """The all-gather of a sharded sweep's metric structs WITHOUT a host hop: the sweep's device table
+    (``afsim_sweep_metrics_device_ptr``) is the NCCL send buffer, the gathered table is permuted into caller order on
+    the device and leaves the GPU once.  Buffers are built once per (shard layout) and reused by every step."""
+
+    def __init__(self, shards: Sequence[np.ndarray], rank: int, group=None):
+        import torch
+
+        self.size = C.sizeof(abi.AfChainMetrics)
+        self.group, self.rank, self.world = group, rank, len(shards)
+        self.counts = [int(len(s)) for s in shards]
+        self.n_total = int(sum(self.counts))
+        self.max_n = max(self.counts) if self.counts else 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.payload = torch.zeros(max(self.max_n, 1) * self.size, dtype=torch.uint8, device=dev)
+        self.gathered = torch.zeros(self.world * max(self.max_n, 1) * self.size, dtype=torch.uint8, device=dev)
+        # row of the gathered [world * max_n] table that holds caller pair i
+        src = np.zeros(self.n_total, dtype=np.int64)
+        for r, idx in enumerate(shards):
+            src[np.asarray(idx, dtype=np.int64)] = r * self.max_n + np.arange(len(idx), dtype=np.int64)
+        self.src_rows = torch.from_numpy(src).to(dev)
+        self.ordered = torch.zeros(max(self.n_total, 1) * self.size, dtype=torch.uint8, device=dev)
+
+    def gather(self, metrics_device_ptr: int):
+        """Queue copy + all-gather + permutation on torch's current stream -> device tensor [n_total * 136] (caller order)."""
+        import torch
+        import torch.distributed as dist
+
+        n_local = self.counts[self.rank]
+        if n_local:
+            local = torch.as_tensor(_DeviceBytes(metrics_device_ptr, n_local * self.size), device=self.payload.device)
+            self.payload[: n_local * self.size].copy_(local, non_blocking=True)
+        dist.all_gather_into_tensor(self.gathered, self.payload, group=self.group)
+        if self.n_total:
+            rows = self.gathered.view(self.world * max(self.max_n, 1), self.size)
+            torch.index_select(rows, 0, self.src_rows, out=self.ordered.view(max(self.n_total, 1), self.size)[: self.n_total])
+        return self.ordered
+
+    def to_host(self):
+        """AfChainMetrics[n_total] on the host (one D2H copy; synchronises)."""
+        return bytes_to_metrics(self.ordered[: self.n_total * self.size].cpu().numpy())
+
+
+def plan_shards(candidates, pair_passage, pair_candidate, passage_lens, world: int) -> list[np.ndarray]:
+    """The partition every rank computes identically: streams balanced by (fixed chain cost + EQ sections) x samples."""
+    pair_passage = np.asarray(pair_passage, dtype=np.int64)
+    costs = stream_costs(candidates, pair_candidate, np.asarray(passage_lens, dtype=np.float64)[pair_passage])
+    return shard_streams(costs, world)
+
+
 def sharded_chain_sweep(render, passages, sample_rate: float, candidates, pair_passage, pair_candidate, group=None):
-    """The whole multi-GPU step of a sweep: balance the streams over the ranks of ``group``, render this rank's shard
-    with ``render(passages, sample_rate, candidates, pair_passage, pair_candidate) -> AfChainMetrics array``
-    (``Simulator.chain_sweep``'s first result on a GPU rank), all-gather the metric structs.  Every rank returns the
-    AfChainMetrics of ALL pairs in caller order, so the final first-safe-scale / argmin pick is local and identical
-    on every rank."""
+    """The whole multi-GPU step of a sweep: balance the streams over the ranks of ``group``, render this rank's shard,
+    all-gather the metric structs.  Every rank returns the AfChainMetrics of ALL pairs in caller order, so the final
+    first-safe-scale / argmin pick is local and identical on every rank.
+
+    ``render`` is a ``native.Simulator`` (GPU ranks, NCCL group: the shard's metrics are gathered straight from the
+    sweep's device table, no host hop) or any callable ``render(passages, sample_rate, candidates, pair_passage,
+    pair_candidate) -> AfChainMetrics array`` (the gloo tests on CPU)."""
     import torch.distributed as dist
 
     pair_passage = np.asarray(pair_passage, dtype=np.uint32)
     pair_candidate = np.asarray(pair_candidate, dtype=np.uint32)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    costs = stream_costs(candidates, pair_candidate, [len(passages[int(p)]) for p in pair_passage])
-    mine = shard_streams(costs, world)[rank]
-    local = render(passages, sample_rate, candidates, pair_passage[mine], pair_candidate[mine])
+    shards = plan_shards(candidates, pair_passage, pair_candidate, [len(p) for p in passages], world)
+    mine = shards[rank]
+    if hasattr(render, "prepare_sweep") and dist.get_backend(group) == "nccl":
+        import torch
+
+        sweep = render.prepare_sweep(passages, sample_rate, candidates, pair_passage[mine], pair_candidate[mine])
+        try:
+            gather = DeviceGather(shards, rank, group)
+            if render.cuda_stream:  # the library launches on the caller's stream: queue the collective behind it
+                with torch.cuda.stream(torch.cuda.ExternalStream(render.cuda_stream)):
+                    sweep.launch()
+                    gather.gather(sweep.metrics_device_ptr)
+                    out = gather.to_host()
+            else:  # the library's own stream: wait for the render, then gather on torch's current stream
+                sweep.launch()
+                sweep.render_ms()
+                gather.gather(sweep.metrics_device_ptr)
+                out = gather.to_host()
+        finally:
+            sweep.release()
+        return out
+    if hasattr(render, "chain_sweep"):
+        local = render.chain_sweep(passages, sample_rate, candidates, pair_passage[mine], pair_candidate[mine])[0]
+    else:
+        local = render(passages, sample_rate, candidates, pair_passage[mine], pair_candidate[mine])
     return gather_metrics(local, mine, pair_passage.size, group=group)

@@ -197,7 +197,16 @@ int afsim_abi_version(void);
  * launch on (so a caller's CUDA events see the work).  Fails (AFSIM_CUDA_ERROR)
  * when no usable sm_100 device is present: there is no CPU path. */
 int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle);
+/* Threading: calls on ONE handle are serialised by the library (a per-handle lock; the reference's pyfunctions hold
+ * the GIL for the whole render, python_api.rs:378); different handles are independent.
+ * Lifetime: afsim_destroy may be called while sweeps prepared on the handle are still alive -- it waits for the
+ * device, detaches them (they keep their device memory and stay valid for afsim_sweep_release only), and every
+ * other afsim_sweep_* call on a detached sweep is an error the caller must not make.  afsim_sweep_release ignores
+ * its handle argument for a detached sweep, so release-after-destroy is safe in either order. */
 void afsim_destroy(AfsimHandle* handle);
+/* Gives the handle's cache of freed device buffers (sweep rings are recycled between calls; at most
+ * AFSIM_POOL_MAX_GB, default 96) back to the driver. */
+int afsim_trim(AfsimHandle* handle);
 /* Message of the last failure on this handle ("" if none).  Valid until the next call. */
 const char* afsim_last_error(const AfsimHandle* handle);
 /* Message of the last afsim_create failure in this thread. */
@@ -316,6 +325,11 @@ typedef enum AfStageKind {
  * of its launch durations, out_launches[i] = launches timed.  *out_n = entries written (<= capacity). */
 int afsim_sweep_profile_stages(AfsimHandle* handle, AfsimSweep* sweep, int max_chunks, int capacity,
                                int* out_kind, float* out_ms, int* out_launches, int* out_n);
+/* Shape of what afsim_sweep_profile_stages / _wavefront time: out_info = {batches of the sweep, streams of the first
+ * batch, samples per chunk, ring slots, stages, samples per stream}; out_stage_streams[i] = streams ONE launch of stage
+ * i really processes (a shared-prefix stage runs on the distinct (passage, setting) pairs only; a cut compressor grid's
+ * first batch is one piece).  The roofline arithmetic of bench.py uses these, not the sweep's pair count. */
+int afsim_sweep_batch_info(const AfsimSweep* sweep, int capacity, int out_info[6], int* out_stage_streams, int* out_n);
 /* The same batch in the LIVE wavefront (every stage on its own stream, as afsim_sweep_launch runs it) with timing
  * events around the launches of chunks [first_chunk, first_chunk + n_chunks): per stage, out_busy_ms[i] = mean time
  * from "launch eligible" (its waits satisfied) to "kernel done" -- the stage's duration under contention -- and
