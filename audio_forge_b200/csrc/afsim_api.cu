@@ -22,6 +22,7 @@
 #include "afsim_kernels.h"
 #include "afsim_plan.h"
 #include "afsim_render.h"
+#include "afsim_tail.h"
 
 using namespace afsim;
 
@@ -115,7 +116,7 @@ struct DeviceBuffers {  // returns what it allocated to the handle's pool
     }
 };
 
-enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT, SK_EQ_SHARED, SK_SPLIT_SHARED };
+enum StageKind { SK_INPUT, SK_INPUT_TP, SK_DEESSER, SK_EQ, SK_COMPRESSOR, SK_LIMITER, SK_OUTPUT, SK_SPLIT, SK_INPUT_SHARED, SK_INPUT_FANOUT, SK_EQ_SHARED, SK_SPLIT_SHARED, SK_TAIL };
 struct StageDesc {
     StageKind kind;
     int arg;  // SK_EQ: first section; SK_SPLIT: SplitOp
@@ -130,6 +131,8 @@ struct Batch {
     std::vector<uint32_t> members;  // caller's pair index of stream s
     size_t mk_ring_elems = 0;       // auto makeup: doubles in args.mk_ring
     int chunk = 0, slots = 0, eq_k = 0;
+    TailMap tail_map{};             // SK_TAIL: tensor map of the tail's input ring (buf_a)
+    int* tail_err = nullptr;        // SK_TAIL: the sweep's watchdog word
     std::vector<cudaEvent_t> events;  // [stage][slot]
     ~Batch() {
         for (cudaEvent_t e : events) cudaEventDestroy(e);
@@ -142,6 +145,7 @@ struct AfsimSweep {
     DeviceBuffers mem;
     std::vector<std::unique_ptr<Batch>> batches;
     AfChainMetrics* d_metrics = nullptr;   // [n_pairs], caller's pair order
+    int* d_tail_err = nullptr;             // set by the fused tail kernel if its pipeline watchdog fired
     StreamAccum* d_accum_first = nullptr;  // accum table of batch 0 (afsim_eq_render reads stream 0)
     float* d_audio = nullptr;
     std::vector<uint64_t> audio_off;       // per pair
@@ -242,6 +246,9 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             std::string msg;
             const int rc = plan_candidate(candidates[c].bands, candidates[c].settings, fs, &plans[c], &msg);
             if (rc != AFSIM_OK) return set_error(h, rc, msg);
+            if (plans[c].deesser_unstable)
+                return set_error(h, AFSIM_UNSUPPORTED,
+                                 "de-esser band edges reach Nyquist at this sample rate: the reference's de-esser is unstable there");
         }
     }
     const RateConstants rate = rate_constants(fs);
@@ -290,6 +297,8 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
     AF_CUDA(h, cudaMemcpyAsync(d_cleanup, &rate.cleanup, sizeof rate.cleanup, cudaMemcpyHostToDevice, h->stream));
     AF_CUDA(h, cudaStreamSynchronize(h->stream));
 
+    AF_CUDA(h, sweep->mem.alloc(&sweep->d_tail_err, 1));
+    AF_CUDA(h, cudaMemsetAsync(sweep->d_tail_err, 0, sizeof(int), h->stream));
     AF_CUDA(h, sweep->mem.alloc(&sweep->d_metrics, n_pairs));
     AF_CUDA(h, cudaMemsetAsync(sweep->d_metrics, 0, std::max<size_t>(n_pairs, 1) * sizeof(AfChainMetrics), h->stream));
 
@@ -497,7 +506,17 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         const bool split = split_mode == 2 || (split_mode != 1 && S <= 16384);
         const size_t ring_elems = static_cast<size_t>(a.ring_rows) * sp;
         AF_CUDA(h, alloc_ring(&a.buf_a, ring_elems));
-        if (a.structure & ST_LIMITER) {
+        // AFSIM_TAIL: 0 = the limiter / true-peak tail as separate stage kernels, 1 (default) = the fused SM-local tail
+        // kernel (afsim_tail.cu) for the batches that take the split kernels, 2 = for every batch
+        const int tail_mode = env_int("AFSIM_TAIL", 1);
+        const bool use_tail = (a.structure & ST_LIMITER) && tail_supported(a.lookahead) &&
+                              (tail_mode == 2 || (tail_mode == 1 && split));
+        if (use_tail) {
+            AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
+            AF_CUDA(h, sweep->mem.alloc(&a.tail_hist, static_cast<size_t>(kTailHistRows) * sp));
+            AF_CUDA(h, tail_make_map(a.buf_a, a.ring_rows, S_pad, &batch->tail_map));
+            batch->tail_err = sweep->d_tail_err;
+        } else if (a.structure & ST_LIMITER) {
             AF_CUDA(h, alloc_ring(&a.buf_b, ring_elems));
             AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
             if (split) {
@@ -510,7 +529,7 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         a.stage_inputs = (split || auto_makeup) ? 1 : 0;  // the compressor's serial kernels only run staged
         {
             int n_w = 0;
-            if (split && (a.structure & ST_LIMITER)) n_w = 1;
+            if (split && (a.structure & ST_LIMITER) && !use_tail) n_w = 1;
             if ((split || auto_makeup) && (a.structure & ST_COMPRESSOR)) n_w = 4;
             if (a.structure & ST_DEESSER) n_w = 13;  // the de-esser is always R/M split (afsim_deesser.h)
             for (int k = 0; k < n_w; ++k) AF_CUDA(h, alloc_ring(&a.w[k], ring_elems));
@@ -771,12 +790,14 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
             }
         }
         if (a.structure & ST_LIMITER) {
-            if (split)
+            if (use_tail)
+                batch->stages.push_back({SK_TAIL, 0});
+            else if (split)
                 for (int op : {SP_LIM_M, SP_LIM_R, SP_TP_FIR_IN, SP_TP_R, SP_TP_FIR_OUT}) batch->stages.push_back({SK_SPLIT, op});
             else
                 batch->stages.push_back({SK_LIMITER, 0});
         }
-        if (!(split && (a.structure & ST_LIMITER))) batch->stages.push_back({SK_OUTPUT, 0});
+        if (!((split || use_tail) && (a.structure & ST_LIMITER))) batch->stages.push_back({SK_OUTPUT, 0});
         if (static_cast<int>(batch->stages.size()) > kMaxStages) return set_error(h, AFSIM_UNSUPPORTED, "too many stages");
         batch->events.resize(batch->stages.size() * static_cast<size_t>(slots));
         for (cudaEvent_t& e : batch->events) AF_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -804,6 +825,7 @@ cudaError_t launch_stage(const Batch& b, const StageDesc& st, const ChunkArgs& c
         case SK_COMPRESSOR: return launch_compressor(b.args, ck, stream);
         case SK_LIMITER: return launch_limiter(b.args, ck, stream);
         case SK_SPLIT: return launch_split(static_cast<SplitOp>(st.arg), b.args, ck, stream);
+        case SK_TAIL: return launch_tail(b.args, ck, b.tail_map, b.tail_err, stream);
         default: return launch_output(b.args, ck, (b.args.structure & ST_LIMITER) != 0, stream);
     }
 }
@@ -915,6 +937,7 @@ int afsim_create(int device_ordinal, void* cuda_stream, AfsimHandle** out_handle
         return AFSIM_CUDA_ERROR;
     }
     err = configure_kernels();
+    if (err == cudaSuccess) err = tail_configure();
     if (err != cudaSuccess) {
         g_create_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err);
         return AFSIM_CUDA_ERROR;
@@ -1044,7 +1067,10 @@ int afsim_sweep_collect(AfsimHandle* h, AfsimSweep* sweep, AfChainMetrics* out_m
     if (sweep->n_pairs)
         AF_CUDA(h, cudaMemcpyAsync(out_metrics, sweep->d_metrics, sweep->n_pairs * sizeof(AfChainMetrics),
                                    cudaMemcpyDeviceToHost, h->stream));
+    int tail_err = 0;
+    AF_CUDA(h, cudaMemcpyAsync(&tail_err, sweep->d_tail_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (tail_err) return set_error(h, AFSIM_CUDA_ERROR, "fused tail kernel: pipeline watchdog fired (results invalid)");
     float ms = 0.0f;
     if (sweep->launched && cudaEventElapsedTime(&ms, sweep->ev_start, sweep->ev_stop) == cudaSuccess && sweep->n_pairs)
         for (size_t i = 0; i < sweep->n_pairs; ++i) out_metrics[i].candidate_runtime_ms = static_cast<double>(ms) / sweep->n_pairs;
@@ -1150,7 +1176,7 @@ int afsim_sweep_profile_stages(AfsimHandle* h, AfsimSweep* sweep, int max_chunks
         return cuda_fail(h, err, "afsim_sweep_profile_stages");
     }
     static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0};
+                                   AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0, AF_STAGE_TAIL};
     for (int i = 0; i < n_stages; ++i) {
         double total = 0.0;
         for (int c = 0; c < timed_chunks; ++c) {
@@ -1219,7 +1245,7 @@ int afsim_sweep_profile_wavefront(AfsimHandle* h, AfsimSweep* sweep, int first_c
     if (rc == AFSIM_OK && err != cudaSuccess) rc = cuda_fail(h, err, "afsim_sweep_profile_wavefront");
     if (rc == AFSIM_OK) {
         static const int kind_map[] = {AF_STAGE_INPUT, AF_STAGE_INPUT_TRUE_PEAK, AF_STAGE_DEESSER, AF_STAGE_EQ,
-                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0};
+                                       AF_STAGE_COMPRESSOR, AF_STAGE_LIMITER, AF_STAGE_OUTPUT, 0, AF_STAGE_INPUT, AF_STAGE_INPUT_FANOUT, AF_STAGE_EQ, 0, AF_STAGE_TAIL};
         for (int i = 0; i < n_stages; ++i) {
             double busy = 0.0;
             for (int c = 0; c < tr.n; ++c) {

@@ -173,6 +173,7 @@ struct BatchArgs {
     double* st_comp;              // [kStateCompressor][S_pad]
     double* st_lim;               // [kStateLimiter][S_pad]
     double* st_tp;                // [kStateTruePeak][S_pad]
+    float* tail_hist;             // [64][S_pad] fused tail (afsim_tail.cu): last 32 rows of the limiter / true-peak limiter outputs
     float* rows;                  // [4][n_rows][S_pad]
     double* st_mk;                // [kStateMakeup][S_pad] auto makeup + loudness meter state
     double* mk_ring;              // [2][n_slots][S_pad] the meter's window: full partial sums, then tail partial sums

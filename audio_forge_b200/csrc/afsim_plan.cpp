@@ -163,7 +163,7 @@ bool loudness_meter_supports(double fs) {  // dsp/loudness.rs:37-42 with `sample
     return std::find(std::begin(ok), std::end(ok), rate) != std::end(ok);
 }
 
-void plan_deesser(const AfChainSettings& s, double fs, CandidateParams& p) {
+bool plan_deesser(const AfChainSettings& s, double fs, CandidateParams& p) {
     // constructor (dsp/deesser.rs:110-134): bounds 4000 / 11000 split into thirds (:242-255)
     auto bounds = [](double lo, double hi, double out[4]) {
         const double span = rmax(hi - lo, 600.0);
@@ -218,6 +218,7 @@ void plan_deesser(const AfChainSettings& s, double fs, CandidateParams& p) {
     p.de[DE_BASE_INACTIVE] = time_constant_to_coeff(20.82, fs);
     p.de[DE_MANUAL_CAP] = max_red * 0.75;
     if (s.deesser_auto_enabled) p.flags |= LF_DE_AUTO;
+    return e1[1] >= 0.5 * fs || e1[2] >= 0.5 * fs || e1[3] >= 0.5 * fs;  // a configured edge at / beyond Nyquist
 }
 
 void plan_compressor(const AfChainSettings& s, double fs, CandidateParams& p) {
@@ -447,7 +448,7 @@ int plan_candidate(const AfBand bands[AFSIM_NUM_BANDS], const AfChainSettings& s
     if (s.eq_before_deesser) out->structure |= ST_EQ_BEFORE_DEESSER;
     if (s.deesser_enabled) {
         out->structure |= ST_DEESSER;
-        plan_deesser(s, fs, p);
+        out->deesser_unstable = plan_deesser(s, fs, p) ? 1u : 0u;
     }
     if (s.compressor_enabled) {
         out->structure |= ST_COMPRESSOR;

@@ -28,6 +28,11 @@ struct CandidatePlan {
     uint32_t structure;   // StructureFlag
     uint32_t lookahead;   // limiter lookahead in samples (0 when the limiter is off)
     uint32_t input_stage; // AfInputStage
+    // the de-esser's configured band edges reach Nyquist (e.g. the 11 kHz default at 16 kHz): its detector / dynamic
+    // EQ biquads are designed with w0 >= pi and are unstable in the reference itself.  The library rejects such a
+    // render (AFSIM_UNSUPPORTED) instead of returning numbers that amplify 1-ulp libm differences without bound;
+    // tests/hostsim ignores the flag to pin the non-finite semantics against the oracle.
+    uint32_t deesser_unstable;
 };
 
 struct RateConstants {

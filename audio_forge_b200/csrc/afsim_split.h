@@ -668,10 +668,17 @@ struct LimiterSpan {
     const float* first;  // FAST: &x(-L)
     size_t stride;
     int ring_rows, row0, t0, n_first, valid, L;
+    mutable bool nan_seen = false;  // a NaN was loaded: the windows that hold it take nan_aware_window (afsim_stages.h)
     AF_HD float operator()(int m) const {
-        if (FAST) return fabsf(first[(size_t)(m + L) * stride]);
-        if (n_first + m < 0 || m >= valid) return 0.0f;
-        return fabsf(ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]);
+        float v;
+        if (FAST)
+            v = fabsf(first[(size_t)(m + L) * stride]);
+        else if (n_first + m < 0 || m >= valid)
+            v = 0.0f;
+        else
+            v = fabsf(ring[(size_t)ring_row(row0, t0 + m, ring_rows) * stride]);
+        nan_seen = nan_seen || v != v;
+        return v;
     }
 };
 
@@ -700,6 +707,12 @@ AF_HD void limiter_windows(const LimiterSpan<FAST>& x, int L, float (&win)[kLimG
             float w = 0.0f;
             for (int m = j - L; m <= j; ++m) w = fmaxf(w, x(m));
             win[j] = w;
+        }
+    }
+    if (x.nan_seen) {  // rare: redo the group with the reference queue's NaN semantics
+        for (int j = 0; j < G; ++j) {
+            auto xj = [&](int m) { return x(j + m); };
+            win[j] = nan_aware_window(xj, L);
         }
     }
 }

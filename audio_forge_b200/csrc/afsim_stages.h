@@ -639,20 +639,40 @@ struct CompressorStage {
 // current block up to n.  Suffix maxima of a finished block are written to a [W][streams] scratch by
 // a backward walk at the block's last sample; prefix maxima are a running register.  Exact (max is
 // associative and commutative), O(1) amortised per sample for any L.
+// NaN: the reference's queue pops every entry a NaN is compared with (`tail_peak > NaN` is false) and the NaN entry is
+// itself popped by the next sample, so a NaN at index k removes the samples up to k from the windows of k+1 .. k+L;
+// `front.max(|x[n]|)` ignores a NaN operand (dsp/limiter.rs:216-237,253).  fmaxf drops NaN operands but keeps the
+// samples before them, so a window that holds a NaN is recomputed by nan_aware_window below (a de-esser / EQ that went
+// unstable mid-chain is what feeds NaN to the limiter: the chain's input itself is sanitised).
+// x(m): |sample n + m| for m in [-L, 0], 0 before the render's start.
+template <class X>
+AF_HD float nan_aware_window(const X& x, int L) {
+    float w = 0.0f;
+    for (int m = -L; m < 0; ++m) {
+        const float v = x(m);
+        w = v != v ? 0.0f : fmaxf(w, v);
+    }
+    const float v = x(0);
+    return v != v ? w : fmaxf(w, v);
+}
+
 struct LimiterStage {
     double g, min_g;
     float prefix;
+    uint32_t since_nan;  // samples since the last NaN input (saturating): <= L means the window holds one
 
     AF_HD void init() {
         g = 1.0;
         min_g = 1.0;
         prefix = 0.0f;
+        since_nan = 0x3fffffffu;
     }
     template <class IO>
     AF_HD void sync(IO& io) {
         io.f64(g);
         io.f64(min_g);
         io.f32(prefix);
+        io.u32(since_nan);
     }
 
     // in_ring / out_ring: this stream's column of the whole ring (row r at base[r * stride]);
@@ -677,6 +697,16 @@ struct LimiterStage {
                 // pos == L: the window is exactly the current block (covers n == L, the only n >= L in
                 // block 0); otherwise n >= W and the scratch holds the previous block's suffix maxima.
                 if (pos != L) window = fmaxf(window, sfx[(size_t)(pos + 1) * stride]);
+            }
+            since_nan = in != in ? 0u : (since_nan < 0x3fffffffu ? since_nan + 1u : since_nan);
+            if (since_nan <= (uint32_t)L) {  // rare: the exact queue semantics around a NaN
+                auto x = [&](int m) {
+                    if (n + m < 0) return 0.0f;
+                    int r = row0 + t + m;
+                    if (r < 0) r += ring_rows;
+                    return fabsf(in_ring[(size_t)r * stride]);
+                };
+                window = nan_aware_window(x, L);
             }
             const double peak = (double)window;
             const double target = peak > ceil_lin ? ceil_lin / peak : 1.0;

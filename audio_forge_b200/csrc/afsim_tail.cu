@@ -1,0 +1,531 @@
+// afsim_tail.cu -- the chain's tail as ONE SM-local kernel: sample limiter (dsp/limiter.rs:246-284) -> 4x true-peak
+// limiter (dsp/true_peak.rs:337-378) -> true-peak detector (dsp/true_peak.rs:208-218) + output statistics
+// (audio/processor/python_api.rs:529-575).
+//
+// The R/M split set runs this as five kernels (k_lim_m, k_lim_r, k_tp_fir_in, k_tp_r, k_tp_fir_out) that hand
+// every intermediate through HBM rings: ~60 B of DRAM traffic per stream-sample for 4 B of input, and two
+// one-warp-per-SM serial kernels whose launch time sets the pipeline period.  Here one CTA owns 32 streams (one lane
+// column of the stream-minor rings) for a whole chunk and keeps everything between the input and the statistics in
+// shared memory:
+//
+//   producer warp   TMA (cp.async.bulk.tensor.2d, tile = 32 time rows x 32 streams of the f32 input ring, mbarrier
+//                   complete_tx) into a time-circular x ring that also holds the L-sample lookback of the limiter
+//   map warps (4)   per 32-row sub-tile, 8 rows each:  LIM-M  sliding-window maximum + f64 target gain
+//                                                      FIR-IN 4x polyphase FIR over the limiter output -> input true
+//                                                             peaks -> f32 target gains of the true-peak limiter
+//                                                      FIR-OUT detector FIR over the true-peak limiter's output
+//   serial warps    LIM-R (lane = stream: g <- t < g ? t : r g + (1 - r) t, delayed sample x gain, clamp) and
+//                   TP-R (the same recurrence in f32, 20-sample delay, output statistics, per-block rows)
+//
+// Stages are linked by release / acquire counters in shared memory (in-order serial warps publish "sub-tiles done",
+// map tasks count arrivals per ring slot), the x ring by mbarriers.  Per sample every operation and its order are
+// those of the split kernels (afsim_split.h) -- the results are bit-identical to them and to the fused stages
+// (tests/test_gpu_tail.py) -- only the hand-off medium changes.  Nothing but the statistics (and the audio, when the
+// caller asked for it) leaves the SM: DRAM traffic is the 4 B read of the input per stream-sample.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "afsim_kernels.h"
+#include "afsim_render.h"
+#include "afsim_tail.h"
+
+namespace afsim {
+
+namespace {
+
+__constant__ float c_tail_fir[4][32] = {
+#include "true_peak_fir.inc"
+};
+
+constexpr int kSub = 32;  // time rows per sub-tile (= TMA box rows)
+constexpr int kMapW = kTailMapWarps;
+constexpr int kTG = 3;    // target-gain slots (f64, 8 KB each)
+constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is history for the FIR / the 20-sample delay)
+constexpr int kTT = 3;    // true-peak target slots
+constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
+constexpr int kMaxCX = 32;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+struct TailCtl {  // shared-memory control block
+    unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
+    int cnt_lim_m[kTG];
+    int cnt_fir_in[kTT];
+    int cnt_fir_out[kCY];
+    int done_lim_r;
+    int done_tp_r;
+    int error;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+    asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// Waits until *p >= v.  A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls the CTA's sticky
+// error flag is set, every wait returns at once, and the launcher's error word reports it.
+__device__ __forceinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
+    uint32_t spins = 0;
+    while (ld_acquire(p) < v) {
+        if (++spins > 64) __nanosleep(40);
+        if (spins > kSpinLimit || (spins & 1023u) == 1023u) {
+            if (spins > kSpinLimit) st_release(&ctl->error, 1);
+            if (ld_acquire(&ctl->error)) return;
+        }
+    }
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) st_release(&ctl->error, 1);
+        if ((spins & 255u) == 255u && ld_acquire(&ctl->error)) return;
+    }
+}
+// 2-D tile of the [ring_rows][S_pad] f32 ring: c0 = first stream (column), c1 = first ring row
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+struct TailSmem {
+    TailCtl* ctl;
+    float* xs;    // [cx * 32][32]   x ring (TMA destination)
+    double* tg;   // [kTG * 32][32]  limiter target gains
+    float* ol;    // [kCO * 32][32]  limiter output
+    float* tt;    // [kTT * 32][32]  true-peak limiter target gains
+    float* ys;    // [kCY * 32][32]  true-peak limiter output
+};
+
+__host__ __device__ inline size_t tail_smem_bytes(int cx) {
+    return 1024 + (size_t)cx * kSub * 32 * 4 + (size_t)kTG * kSub * 32 * 8 + (size_t)(kCO + kTT + kCY) * kSub * 32 * 4;
+}
+
+extern __shared__ __align__(1024) unsigned char tail_smem_raw[];
+
+__device__ __forceinline__ TailSmem carve(int cx) {
+    TailSmem sm;
+    unsigned char* p = tail_smem_raw;
+    sm.ctl = reinterpret_cast<TailCtl*>(p);
+    p += 1024;
+    sm.xs = reinterpret_cast<float*>(p);
+    p += (size_t)cx * kSub * 32 * 4;
+    sm.tg = reinterpret_cast<double*>(p);
+    p += (size_t)kTG * kSub * 32 * 8;
+    sm.ol = reinterpret_cast<float*>(p);
+    p += (size_t)kCO * kSub * 32 * 4;
+    sm.tt = reinterpret_cast<float*>(p);
+    p += (size_t)kTT * kSub * 32 * 4;
+    sm.ys = reinterpret_cast<float*>(p);
+    return sm;
+}
+
+// ---- map tasks (one warp = 8 rows of a sub-tile, lane = stream) ------------------------------------------------------
+
+// LIM-M: windows [r - L, r] of |x| for the 8 rows r = base .. base + 7 (dsp/limiter.rs:253-262; max is order
+// independent, so the shared part of the eight windows is scanned once), then the target gain in f64.
+__device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane, int base, int L, double ceil_lin,
+                                           double* tg_rows /* row 0 of this warp's 8 */) {
+    constexpr int G = 8;
+    bool nan_seen = false;
+    auto x = [&](int m) {
+        const float v = fabsf(xs[(size_t)((base + m) & xmask) * 32 + lane]);
+        nan_seen = nan_seen || v != v;
+        return v;
+    };
+    float win[G];
+    if (L >= G) {
+        float run = 0.0f;
+        for (int m = -1; m >= G - L; --m) run = fmaxf(run, x(m));
+        float left[G];
+#pragma unroll
+        for (int j = G - 1; j >= 0; --j) {
+            run = fmaxf(run, x(j - L));
+            left[j] = run;
+        }
+        float prefix = 0.0f;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            prefix = fmaxf(prefix, x(j));
+            win[j] = fmaxf(left[j], prefix);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            float w = 0.0f;
+            for (int m = j - L; m <= j; ++m) w = fmaxf(w, x(m));
+            win[j] = w;
+        }
+    }
+    if (nan_seen) {  // rare: the reference queue's NaN semantics (afsim_stages.h: nan_aware_window)
+        for (int j = 0; j < G; ++j) {
+            auto xj = [&](int m) { return x(j + m); };
+            win[j] = nan_aware_window(xj, L);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const double peak = (double)win[j];
+        tg_rows[(size_t)j * 32 + lane] = peak > ceil_lin ? ceil_lin / peak : 1.0;
+    }
+}
+
+// 4x polyphase FIR peaks of rows base .. base + 7 of a ring (taps in the reference's order, dsp/true_peak.rs:173-186)
+__device__ __forceinline__ void task_fir(const float* ring, int mask, int lane, int base, float (&pk)[kFirChunk]) {
+    float win[kFirWin];
+#pragma unroll
+    for (int i = 0; i < kFirWin; ++i) {
+        const float v = ring[(size_t)((base - 31 + i) & mask) * 32 + lane];
+        win[i] = af_finite(v) ? v : 0.0f;  // dsp/true_peak.rs:211,343 sanitise
+    }
+    fir8_peaks(win, c_tail_fir, pk);
+}
+
+}  // namespace
+
+// One CTA = 32 streams x one chunk.  Warp 0: TMA producer; warp 1: LIM-R; warp 2: TP-R; warps 3..6: maps.
+__global__ void __launch_bounds__(kTailThreads, 2)
+k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int cx, int* err_out) {
+    const TailSmem sm = carve(cx);
+    TailCtl* ctl = sm.ctl;
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    const int s_base = (int)blockIdx.x * 32, s = s_base + lane;
+    const size_t stride = (size_t)a.stride;
+    const int L = a.lookahead, Lt = (L + kSub - 1) / kSub;
+    const int n_sub = (ck.len + kSub - 1) / kSub;
+    const int xmask = cx * kSub - 1, omask = kCO * kSub - 1, ymask = kCY * kSub - 1;
+    // x ring: sample r of the chunk (r >= -Lt * 32: the lookback) lives at row (r + xoff) & xmask, i.e. sub-tile j in slot
+    // (j + Lt) mod cx -- its (j + Lt) / cx-th use, which is the parity its mbarrier is waited on with
+    const int xoff = Lt * kSub;
+    auto x_slot = [&](int j) { return (j + Lt) & (cx - 1); };
+    auto x_parity = [&](int j) { return (uint32_t)(((j + Lt) / cx) & 1); };
+    const bool first_chunk = ck.n0 == 0;
+
+    // ---- init: barriers, counters, histories -----------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < cx; ++i) mbar_init(&ctl->full[i], 1);
+        for (int i = 0; i < kTG; ++i) ctl->cnt_lim_m[i] = 0;
+        for (int i = 0; i < kTT; ++i) ctl->cnt_fir_in[i] = 0;
+        for (int i = 0; i < kCY; ++i) ctl->cnt_fir_out[i] = 0;
+        ctl->done_lim_r = 0;
+        ctl->done_tp_r = 0;
+        ctl->error = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // sub-tile -1 of the limiter-output / true-peak-output rings: the previous chunk's last 32 rows (parked), or silence
+    for (int i = (int)threadIdx.x; i < kSub * 32; i += kTailThreads) {
+        const int r = i >> 5, c = i & 31;
+        float ho = 0.0f, hy = 0.0f;
+        if (!first_chunk) {
+            ho = a.tail_hist[(size_t)r * stride + s_base + c];
+            hy = a.tail_hist[(size_t)(kSub + r) * stride + s_base + c];
+        }
+        sm.ol[(size_t)((r - kSub) & omask) * 32 + c] = ho;
+        sm.ys[(size_t)((r - kSub) & ymask) * 32 + c] = hy;
+    }
+    if (first_chunk)  // samples before the render's start are silence (dsp/limiter.rs:117-131: the delay line starts at zero)
+        for (int i = (int)threadIdx.x; i < xoff * 32; i += kTailThreads) sm.xs[i] = 0.0f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes above vs the TMA writes that reuse the slots
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---- producer: one thread feeds the x ring, Lt history sub-tiles first -----------------------------------------
+        if (lane == 0) {
+            for (int j = -Lt; j < n_sub; ++j) {
+                // slot (j mod cx) still holds sub-tile j - cx, whose rows LIM-M / LIM-R need up to sub-tile j - cx + Lt
+                const int need = j - cx + Lt + 1;
+                if (need > 0) wait_ge(&ctl->done_lim_r, need, ctl);
+                const int slot = x_slot(j);
+                if (j < 0 && first_chunk) {
+                    mbar_arrive(&ctl->full[slot]);  // zero-filled above; keeps the phase sequence uniform
+                } else {
+                    int row = ck.row0 + j * kSub;
+                    if (row < 0) row += a.ring_rows;
+                    mbar_expect_tx(&ctl->full[slot], kSub * 32 * 4);
+                    tma_load_2d(sm.xs + (size_t)slot * kSub * 32, &x_map, s_base, row, &ctl->full[slot]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- LIM-R: gain recurrence of the sample limiter, lane = stream ---------------------------------------------------
+        const CandidateParams& p = stream_params(a, s);
+        const double ceil_lin = p.l_ceil, rel = p.l_release, one_m_rel = 1.0 - rel;
+        LimiterR st;
+        if (first_chunk) {
+            st.init();
+        } else {
+            StateIO<false> io{a.st_lim + s, stride};
+            st.sync(io);
+        }
+        double g = st.g, min_g = st.min_g;
+        for (int j = 0; j < n_sub; ++j) {
+            const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
+            wait_ge(&ctl->cnt_lim_m[j % kTG], kMapW * (j / kTG + 1), ctl);
+            const int k = j - kCO + 1;  // the ring row block about to be overwritten was last read by FIR-IN(k) and TP-R(k)
+            if (k >= 0) {
+                wait_ge(&ctl->cnt_fir_in[k % kTT], kMapW * (k / kTT + 1), ctl);
+                wait_ge(&ctl->done_tp_r, k + 1, ctl);
+            }
+            mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);  // x rows: already landed (the maps waited for them)
+            const double* tg = sm.tg + (size_t)(j % kTG) * kSub * 32 + lane;
+#pragma unroll
+            for (int u0 = 0; u0 < kSub; u0 += 8) {
+                double tgt[8];
+                float delayed[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    tgt[u] = tg[(size_t)(u0 + u) * 32];
+                    delayed[u] = sm.xs[(size_t)((j * kSub + u0 + u - L + xoff) & xmask) * 32 + lane];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u0 + u < valid) {
+                        if (tgt[u] < g)
+                            g = tgt[u];
+                        else
+                            g = rel * g + one_m_rel * tgt[u];
+                        min_g = fmin(min_g, g);
+                        sm.ol[(size_t)((j * kSub + u0 + u) & omask) * 32 + lane] =
+                            (float)clampd((double)delayed[u] * g, -ceil_lin, ceil_lin);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) st_release(&ctl->done_lim_r, j + 1);
+        }
+        st.g = g;
+        st.min_g = min_g;
+        if (ck.n0 + ck.len >= a.n_samples) {
+            a.accum[s].limiter_gr_db = st.peak_reduction_db();
+        } else {
+            StateIO<true> io{a.st_lim + s, stride};
+            st.sync(io);
+        }
+    } else if (warp == 2) {
+        // ---- TP-R: gain recurrence of the true-peak limiter + output statistics, lane = stream -------------------------------
+        const CandidateParams& p = stream_params(a, s);
+        const float ceil_lin = p.tp_ceil, rel = p.tp_release, one_m_rel = 1.0f - rel;
+        TpR st;
+        if (first_chunk) {
+            st.init();
+        } else {
+            StateIO<false> io{a.st_tp + s, stride};
+            st.sync(io);
+        }
+        BlockClock clk;
+        clk.init(a.block_samples, a.n_samples, ck.n0);
+        float* rows_out = a.rows + (size_t)1 * a.n_rows * stride + s;
+        for (int j = 0; j < n_sub; ++j) {
+            const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
+            wait_ge(&ctl->cnt_fir_in[j % kTT], kMapW * (j / kTT + 1), ctl);
+            const int k = j - kCY + 1;  // last reader of the output ring rows about to be overwritten: FIR-OUT(k)
+            if (k >= 0) wait_ge(&ctl->cnt_fir_out[k % kCY], kMapW * (k / kCY + 1), ctl);
+            const float* tt = sm.tt + (size_t)(j % kTT) * kSub * 32 + lane;
+#pragma unroll
+            for (int u0 = 0; u0 < kSub; u0 += 8) {
+                float pk[8], delayed[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    pk[u] = tt[(size_t)(u0 + u) * 32];
+                    const float v = sm.ol[(size_t)((j * kSub + u0 + u - kTpDelay) & omask) * 32 + lane];
+                    delayed[u] = af_finite(v) ? v : 0.0f;
+                }
+                const int n_first = ck.n0 + j * kSub + u0;
+                auto walk = [&](auto may_end) {
+                    constexpr bool CHECK = decltype(may_end)::value;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (u0 + u < valid) {
+                            const float target = pk[u];
+                            if (target < st.g) {
+                                st.g = target;
+                                st.limited = true;
+                            } else {
+                                st.g = rel * st.g + one_m_rel * target;
+                            }
+                            st.min_g = fminf(st.min_g, st.g);
+                            float o = clampf(delayed[u] * st.g, -ceil_lin, ceil_lin);
+                            if (!af_finite(o)) o = 0.0f;
+                            sm.ys[(size_t)((j * kSub + u0 + u) & ymask) * 32 + lane] = o;
+                            st.peak_out = fmaxf(st.peak_out, fabsf(o));
+                            const double sq = (double)o * (double)o;
+                            st.sum_out += sq;
+                            st.blk_out += sq;
+                            if (CHECK && clk.at_end(n_first + u)) {
+                                st.events += st.limited ? 1u : 0u;
+                                st.limited = false;
+                                const float rms = (float)sqrt(st.blk_out / (double)clk.block_len(n_first + u));
+                                rows_out[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                                st.blk_out = 0.0;
+                                clk.advance();
+                            }
+                        }
+                    }
+                };
+                if (clk.ends_after(n_first, 8))  // no analysis block (nor the signal) ends inside these 8 samples
+                    walk(TileRagged());
+                else
+                    walk(TileFull());
+            }
+            __syncwarp();
+            if (lane == 0) st_release(&ctl->done_tp_r, j + 1);
+        }
+        if (ck.n0 + ck.len >= a.n_samples) {
+            StreamAccum& acc = a.accum[s];
+            acc.sum_out = st.sum_out;
+            acc.peak_out = st.peak_out;
+            acc.non_finite = st.non_finite ? 1u : 0u;
+            acc.tp_gr_db = st.peak_reduction_db();
+            acc.events = st.events;
+        } else {
+            StateIO<true> io{a.st_tp + s, stride};
+            st.sync(io);
+        }
+    } else {
+        // ---- maps: warp m owns rows [8m, 8m + 8) of every sub-tile; step t = LIM-M(t), FIR-IN(t - 1), FIR-OUT(t - 2) --------
+        const int m = warp - 3;
+        const double l_ceil = a.map_tab[(size_t)MT_L_CEIL * stride + s];
+        const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
+        float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
+        float max_in = 0.0f, max_out = 0.0f;
+        for (int t = 0; t < n_sub + 2; ++t) {
+            if (t < n_sub) {
+                const int j = t;
+                if (j == 0)
+                    for (int h = -Lt; h < 0; ++h) mbar_wait(&ctl->full[x_slot(h)], x_parity(h), ctl);
+                mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);
+                if (j - kTG >= 0) wait_ge(&ctl->done_lim_r, j - kTG + 1, ctl);
+                task_lim_m(sm.xs, xmask, lane, j * kSub + 8 * m + xoff, L, l_ceil, sm.tg + (size_t)((j % kTG) * kSub + 8 * m) * 32);
+                __syncwarp();
+                if (lane == 0) red_release_add(&ctl->cnt_lim_m[j % kTG], 1);
+            }
+            if (t >= 1 && t - 1 < n_sub) {
+                const int j = t - 1;
+                const int valid = ck.len - j * kSub - 8 * m;  // rows of this warp's 8 that exist
+                wait_ge(&ctl->done_lim_r, j + 1, ctl);
+                if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);
+                float pk[kFirChunk];
+                task_fir(sm.ol, omask, lane, j * kSub + 8 * m, pk);
+                float* tt = sm.tt + (size_t)((j % kTT) * kSub + 8 * m) * 32 + lane;
+#pragma unroll
+                for (int i = 0; i < kFirChunk; ++i) {
+                    // feed-forward part of dsp/true_peak.rs:349-354
+                    tt[(size_t)i * 32] = pk[i] > tp_ceil ? clampf((tp_ceil * 0.999f) / pk[i], 0.0f, 1.0f) : 1.0f;
+                    if (i < valid) max_in = fmaxf(max_in, pk[i]);
+                }
+                __syncwarp();
+                if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], 1);
+            }
+            if (t >= 2) {
+                const int j = t - 2;
+                const int valid = ck.len - j * kSub - 8 * m;
+                wait_ge(&ctl->done_tp_r, j + 1, ctl);
+                float pk[kFirChunk];
+                task_fir(sm.ys, ymask, lane, j * kSub + 8 * m, pk);
+#pragma unroll
+                for (int i = 0; i < kFirChunk; ++i)
+                    if (i < valid) max_out = fmaxf(max_out, pk[i]);
+                if (audio) {
+#pragma unroll
+                    for (int i = 0; i < kFirChunk; ++i)
+                        if (i < valid) audio[j * kSub + 8 * m + i] = sm.ys[(size_t)((j * kSub + 8 * m + i) & ymask) * 32 + lane];
+                }
+                __syncwarp();
+                if (lane == 0) red_release_add(&ctl->cnt_fir_out[j % kCY], 1);
+            }
+        }
+        // running maxima of the two oversamplers: order independent (python_api.rs:552-560) -> atomics
+        atomic_max_nonneg(&a.accum[s].peak_pre_tp, max_in);
+        atomic_max_nonneg(&a.accum[s].peak_out_tp, max_out);
+    }
+    __syncthreads();
+    // park the last 32 rows of both rings for the next chunk's FIR history and 20-sample delay
+    if (ck.n0 + ck.len < a.n_samples)
+        for (int i = (int)threadIdx.x; i < kSub * 32; i += kTailThreads) {
+            const int r = i >> 5, c = i & 31;
+            const int row = ck.len - kSub + r;
+            a.tail_hist[(size_t)r * stride + s_base + c] = sm.ol[(size_t)(row & omask) * 32 + c];
+            a.tail_hist[(size_t)(kSub + r) * stride + s_base + c] = sm.ys[(size_t)(row & ymask) * 32 + c];
+        }
+    if (threadIdx.x == 0 && ctl->error && err_out) atomicExch(err_out, 1);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+
+int tail_ring_subtiles(int lookahead) {
+    const int lt = (lookahead + kSub - 1) / kSub;
+    int cx = 8;
+    while (cx < lt + 4) cx <<= 1;
+    return cx;
+}
+
+bool tail_supported(int lookahead) { return lookahead >= 1 && tail_ring_subtiles(lookahead) <= kMaxCX; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cudaError_t tail_make_map(const float* ring, int ring_rows, int stride, TailMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        const cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (err != cudaSuccess) return err;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    static_assert(sizeof(TailMap) == sizeof(CUtensorMap), "TailMap must hold a CUtensorMap");
+    const cuuint64_t dims[2] = {(cuuint64_t)stride, (cuuint64_t)ring_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)kSub};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult rc = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ring),
+                               dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return rc == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+cudaError_t tail_configure() {
+    return cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes(kMaxCX));
+}
+
+cudaError_t launch_tail(const BatchArgs& a, const ChunkArgs& ck, const TailMap& map, int* err_flag, cudaStream_t st) {
+    const int cx = tail_ring_subtiles(a.lookahead);
+    CUtensorMap m;
+    memcpy(&m, &map, sizeof m);
+    k_tail<<<dim3((unsigned)(a.stride / 32)), kTailThreads, tail_smem_bytes(cx), st>>>(a, ck, m, cx, err_flag);
+    return cudaGetLastError();
+}
+
+}  // namespace afsim

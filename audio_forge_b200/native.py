@@ -33,7 +33,7 @@ EXPORTS = (
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
                "comp_r1", "comp_m2", "comp_r3", "comp_m4", "comp_r5", "comp_m6", "lim_m", "lim_r", "tp_fir_in", "tp_r",
-               "tp_fir_out", "de_ra", "de_mb", "de_rc", "comp_r7", "de_mc2", "de_rc3", "de_rc1a", "de_mc1b", "de_rc1c") + ("?",) * 12 + ("input_fanout",)
+               "tp_fir_out", "de_ra", "de_mb", "de_rc", "comp_r7", "de_mc2", "de_rc3", "de_rc1a", "de_mc1b", "de_rc1c") + ("?",) * 12 + ("input_fanout", "tail")
 
 
 class AfsimError(RuntimeError):

@@ -316,7 +316,8 @@ typedef enum AfStageKind {
      * compressor R1 M2 R3 M4 R5 M6, limiter M R, true-peak FIR-in R FIR-out */
     AF_STAGE_SPLIT_BASE = 8,
     /* ... AF_STAGE_SPLIT_BASE + 14 = auto makeup R7 */
-    AF_STAGE_INPUT_FANOUT = 40 /* copy of the shared input stage (one render per distinct passage) to every stream */
+    AF_STAGE_INPUT_FANOUT = 40, /* copy of the shared input stage (one render per distinct passage) to every stream */
+    AF_STAGE_TAIL = 41 /* limiter -> true-peak limiter -> detector + output statistics fused in one SM-local, TMA-fed kernel */
 } AfStageKind;
 
 /* Runs the first batch of the sweep once with the stage kernels SERIALISED on the handle's stream

@@ -29,11 +29,13 @@ def sim():
 X = golden_chain_input(blocks=100)  # 48 000 samples = 47 chunks of 1024
 
 
-@pytest.mark.parametrize("path", ["fused", "split"])
+@pytest.mark.parametrize("path", ["fused", "split", "tail"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_chain_render_matches_oracle(sim, name, path, monkeypatch):
-    """Both kernel paths: one-thread-per-stream fused stages (large sweeps) and the R/M split (few streams)."""
+    """All kernel paths: one-thread-per-stream fused stages (large sweeps), the R/M split (few streams) with the
+    limiter / true-peak tail as five stage kernels, and with the fused SM-local tail kernel (the default)."""
     monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
+    monkeypatch.setenv("AFSIM_TAIL", "1" if path == "tail" else "0")
     bands, overrides = CASES[name]
     settings = abi.make_settings(**overrides)
     m0, a0, _ = pyoracle.chain_render(X, FS, bands, settings, return_audio=True)

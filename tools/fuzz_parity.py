@@ -14,7 +14,7 @@ from tests.signals import speech_like  # noqa: E402
 
 
 def random_case(rng):
-    fs = float(rng.choice([16000.0, 32000.0, 44100.0, 48000.0, 96000.0]))
+    fs = float(rng.choice([8000.0, 11025.0, 16000.0, 22050.0, 32000.0, 44100.0, 48000.0, 96000.0]))
     n = int(rng.choice([rng.integers(1, 200), rng.integers(200, 4000), rng.integers(4000, 40000)]))
     nyq = fs / 2.0 - 1.0
     typed = bool(rng.random() < 0.5)
@@ -30,9 +30,9 @@ def random_case(rng):
     auto_makeup = bool(rng.random() < 0.25) and stage in ("none", "dc_hp80")
     overrides = dict(
         use_typed_bands=typed, input_stage=stage, eq_before_deesser=bool(rng.random() < 0.5),
-        deesser_enabled=bool(rng.random() < 0.5) and fs >= 32000.0, deesser_auto_enabled=bool(rng.random() < 0.6),
+        deesser_enabled=bool(rng.random() < 0.5), deesser_auto_enabled=bool(rng.random() < 0.6),
         deesser_auto_amount=float(rng.uniform(0, 1)), deesser_low_cut_hz=float(rng.uniform(3000, 6000)),
-        deesser_high_cut_hz=float(rng.uniform(7000, min(12000.0, nyq))), deesser_threshold_db=float(rng.uniform(-50, -10)),
+        deesser_high_cut_hz=float(rng.uniform(min(7000.0, 0.8 * nyq), min(12000.0, 1.1 * nyq))), deesser_threshold_db=float(rng.uniform(-50, -10)),
         deesser_ratio=float(rng.uniform(1.5, 10)), deesser_attack_ms=float(rng.uniform(0.5, 10)),
         deesser_release_ms=float(rng.uniform(20, 200)), deesser_max_reduction_db=float(rng.uniform(2, 18)),
         compressor_enabled=bool(rng.random() < 0.8), compressor_threshold_db=float(rng.uniform(-50, -6)),
@@ -105,6 +105,8 @@ def main():
         except (ValueError, native.AfsimError) as e:
             if m0 is None:
                 continue  # both reject
+            if isinstance(e, native.AfsimError) and e.status == abi.AFSIM_UNSUPPORTED and "Nyquist" in e.message:
+                continue  # de-esser band edges at / beyond Nyquist: unstable in the reference itself, rejected loudly here
             failures.append({"case": i, "error": str(e), "overrides": overrides, "fs": fs, "n": int(x.size)})
             continue
         if m0 is None:
