@@ -47,7 +47,7 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 24;
+constexpr uint32_t kSpinLimit = 1u << 22;
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
@@ -216,6 +216,7 @@ __device__ __forceinline__ void task_fir(const float* ring, int mask, int lane, 
 // One CTA = 32 streams x one chunk.  Warp 0: TMA producer; warp 1: LIM-R; warp 2: TP-R; warps 3..6: maps.
 __global__ void __launch_bounds__(kTailThreads, 2)
 k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int cx, int* err_out) {
+    if (err_out && *reinterpret_cast<volatile int*>(err_out)) return;  // an earlier launch's watchdog fired: do not pile up waits
     const TailSmem sm = carve(cx);
     TailCtl* ctl = sm.ctl;
     const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
