@@ -130,6 +130,35 @@ def select_winner(evaluated: Mapping[tuple, tuple[float, Mapping, Mapping[str, f
     return (expanded if expanded_selected else threshold_only), expanded, threshold_only, expanded_selected
 
 
+TIE_MARGIN = 1.0e-5          # score distance below which the argmin / the expanded-vs-threshold-only rule is "near"
+HARD_REJECT_MARGIN_DB = 0.01  # the parity tolerance of the rendered metrics
+
+
+def search_decision_margins(evaluated: Mapping[tuple, tuple[float, Mapping, Mapping[str, float]]], incumbent: Mapping[str, float],
+                            peak_cap_db: float) -> dict[str, Any]:
+    """How close the search's decisions came to flipping (no CPU re-render; counts only, so that "bit-exact
+    selection" is auditable): hard-reject tests within HARD_REJECT_MARGIN_DB of their limit (voice_setup.py:862-867),
+    the gap between the two best scores, and the distance of the expanded-vs-threshold-only rule (voice_setup.py:
+    984-995) from its required improvement."""
+    near_reject = 0
+    for _, sim, _ in evaluated.values():
+        ceiling = float(sim.get("limiter_effective_ceiling_db", -1.5))
+        d_peak = abs(float(sim.get("output_true_peak_db", 120.0)) - (ceiling + 0.10))
+        d_cap = abs(float(sim.get("compressor_gain_reduction_db", 0.0)) - (peak_cap_db + 1.0e-6))
+        if min(d_peak, d_cap) < HARD_REJECT_MARGIN_DB:
+            near_reject += 1
+    feasible = sorted(item[0] for item in evaluated.values() if np.isfinite(item[0]))
+    best_gap = feasible[1] - feasible[0] if len(feasible) > 1 else float("inf")
+    _, expanded, threshold_only, _ = select_winner(evaluated, incumbent) if feasible else (None, None, None, False)
+    rule_distance = float("inf")
+    if threshold_only is not None and expanded is not None:
+        required = max(0.001, 0.01 * threshold_only[0])
+        rule_distance = abs((threshold_only[0] - expanded[0]) - required)
+    return {"candidates": len(evaluated), "near_hard_reject": near_reject, "hard_reject_margin_db": HARD_REJECT_MARGIN_DB,
+            "best_score_gap": best_gap, "tie_rule_distance": rule_distance, "tie_margin": TIE_MARGIN,
+            "near_tie": bool(best_gap < TIE_MARGIN or rule_distance < TIE_MARGIN)}
+
+
 def calibrate_compressor_batch(*, speech_audio, sample_rate: float, eq_settings: Mapping[str, Any],
                                deesser_settings: Mapping[str, Any], compressor_settings: Mapping[str, Any],
                                target_p95_db: float, target_median_db: float, peak_cap_db: float,
@@ -254,5 +283,7 @@ def calibrate_compressor_batch(*, speech_audio, sample_rate: float, eq_settings:
         "search_runtime_ms": (time.perf_counter() - started) * 1000.0,
         "threshold_db": calibrated["threshold_db"], "ratio": calibrated["ratio"],
         "attack_ms": calibrated["attack_ms"], "release_ms": calibrated["release_ms"],
+        # not part of the reference's diagnostics: how close the decisions came to flipping
+        "decision_margins": search_decision_margins(evaluated, incumbent, peak_cap_db),
     })
     return calibrated, diagnostics

@@ -91,6 +91,36 @@ def is_headroom_safe(simulation: Mapping[str, Any]) -> bool:
             and true_peak_gr <= TRUE_PEAK_GAIN_REDUCTION_WARN_DB)
 
 
+DECISION_MARGIN_DB = 0.01  # the parity tolerance of the rendered metrics (north_star): closer than this = auditable
+
+
+def headroom_margins_db(simulation: Mapping[str, Any]) -> dict[str, float]:
+    """Signed distance of each of the three metrics from its threshold (>= 0: on the safe side).  A render is "near a
+    threshold" when any |margin| < DECISION_MARGIN_DB: there a <= 2-ulp device-libm difference could in principle
+    flip is_headroom_safe against a CPU render, so callers can audit exactly those (no CPU re-render happens here)."""
+    pre = _as_float(simulation.get("pre_limiter_true_peak_headroom_db"), simulation.get("true_peak_headroom_db", 120.0))
+    limiter_gr = _as_float(simulation.get("limiter_gain_reduction_db"), 0.0)
+    true_peak_gr = _as_float(simulation.get("true_peak_limiter_gain_reduction_db"), 0.0)
+    return {"pre_limiter_true_peak_headroom_db": pre - HEADROOM_TARGET_DB,
+            "limiter_gain_reduction_db": LIMITER_GAIN_REDUCTION_WARN_DB - limiter_gr,
+            "true_peak_limiter_gain_reduction_db": TRUE_PEAK_GAIN_REDUCTION_WARN_DB - true_peak_gr}
+
+
+def decision_margin_report(simulations: Sequence[Mapping[str, Any]], examined: int) -> dict[str, Any]:
+    """Margins of the renders the sequential walk really examined (scales 0 .. `examined`): how many sit within
+    DECISION_MARGIN_DB of a threshold, and the smallest |margin| seen."""
+    near, smallest, which = 0, float("inf"), None
+    for index in range(examined + 1):
+        margins = headroom_margins_db(simulations[index])
+        closest = min(margins, key=lambda k: abs(margins[k]))
+        if abs(margins[closest]) < DECISION_MARGIN_DB:
+            near += 1
+        if abs(margins[closest]) < smallest:
+            smallest, which = abs(margins[closest]), (index, closest)
+    return {"renders_examined": examined + 1, "near_threshold": near, "margin_db": DECISION_MARGIN_DB,
+            "smallest_abs_margin_db": smallest, "smallest_at": {"scale_index": which[0], "metric": which[1]} if which else None}
+
+
 def select_scale(simulations: Sequence[Mapping[str, Any]]) -> int:
     """Index into HEADROOM_SCALES the sequential walk of headroom.py:306-320 ends on."""
     for index, simulation in enumerate(simulations):
@@ -130,6 +160,8 @@ def finish_validation(eq_settings: Mapping[str, Any], simulations: Sequence[Mapp
         "safe": safe, "authoritative": authoritative, "advisory": not authoritative,
         "meets_advisory_thresholds": meets, "gain_scale": scale, "before": dict(before), "after": dict(selected),
         "status": "safe" if safe else "risk" if authoritative else "advisory",
+        # not part of the reference's dict: how close the examined renders came to a decision threshold
+        "decision_margins": decision_margin_report(simulations, index),
     }
     result["headroom_safe"] = safe
     result["headroom_advisory"] = not authoritative

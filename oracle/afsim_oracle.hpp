@@ -711,6 +711,7 @@ class LoudnessMeter {
         current_lufs_ = static_cast<float>(lufs);
     }
     float loudness_momentary() const { return current_lufs_; }
+    void reset() { *this = LoudnessMeter(fs_); }  // loudness.rs:146-154: a fresh meter, -100 LUFS
 
   private:
     uint32_t fs_;
@@ -827,6 +828,17 @@ class Compressor {
         const double blended = 0.6 * db_to_linear(peak_db) + 0.4 * db_to_linear(rms_db);
         return linear_to_db(blended, 1e-10);
     }
+    void set_limiter_feedback_gain_reduction_db(double db) { limiter_feedback_gr_db_ = rclamp(db, 0.0, 24.0); }  // :385-387
+    // the reference's unit tests call these private methods directly (compressor.rs:1074-1095,1169-1245)
+    void test_update_auto_makeup_gain(double activity, double reliability, size_t elapsed) {
+        update_auto_makeup_gain(activity, reliability, elapsed);
+    }
+    void test_estimate_activity(double rms_db, const AutoMakeupActivityInput* ev, double* activity, double* reliability) const {
+        const Activity a = estimate_activity(rms_db, ev);
+        *activity = a.activity;
+        *reliability = a.reliability;
+    }
+    static double test_speech_activity_from_rms_db(double rms_db) { return speech_activity_from_rms_db(rms_db); }
     float process_sample(float input) { return process_sample_impl(input, true); }
     void process_block_inplace(float* buf, size_t n) { process_block_with_activity(buf, n, nullptr); }
     void process_block_with_activity(float* buf, size_t n, const AutoMakeupActivityInput* evidence) {  // :700-722

@@ -524,6 +524,27 @@ void orc_comp_process_block_with_activity(void* c, float* buf, size_t n, int has
     const AutoMakeupActivityInput ev{vad_probability, vad_reliability, noise_floor_db, live_noise_reliability};
     static_cast<Compressor*>(c)->process_block_with_activity(buf, n, has_evidence ? &ev : nullptr);
 }
+// dsp/loudness.rs: LoudnessMeter::new fails for a rate outside the list (:35-40) -> nullptr
+void* orc_meter_new(uint32_t fs) { return LoudnessMeter::supported_rate(fs) ? new LoudnessMeter(fs) : nullptr; }
+void orc_meter_free(void* m) { delete static_cast<LoudnessMeter*>(m); }
+void orc_meter_process(void* m, const float* x, size_t n) { static_cast<LoudnessMeter*>(m)->process(x, n); }
+float orc_meter_momentary(void* m) { return static_cast<LoudnessMeter*>(m)->loudness_momentary(); }
+void orc_meter_reset(void* m) { static_cast<LoudnessMeter*>(m)->reset(); }
+void orc_comp_update_auto_makeup_gain(void* c, double activity, double reliability, size_t elapsed) {
+    static_cast<Compressor*>(c)->test_update_auto_makeup_gain(activity, reliability, elapsed);
+}
+void orc_comp_estimate_activity(void* c, double rms_db, int has_evidence, double vad_probability, double vad_reliability,
+                                double noise_floor_db, double live_noise_reliability, double* out2) {
+    const AutoMakeupActivityInput ev{vad_probability, vad_reliability, noise_floor_db, live_noise_reliability};
+    static_cast<Compressor*>(c)->test_estimate_activity(rms_db, has_evidence ? &ev : nullptr, &out2[0], &out2[1]);
+}
+double orc_comp_speech_activity_from_rms_db(double rms_db) { return Compressor::test_speech_activity_from_rms_db(rms_db); }
+double orc_comp_auto_makeup_activity(void* c) { return static_cast<Compressor*>(c)->auto_makeup_activity(); }
+double orc_comp_auto_makeup_activity_reliability(void* c) { return static_cast<Compressor*>(c)->auto_makeup_activity_reliability(); }
+void orc_comp_set_limiter_feedback_gain_reduction_db(void* c, double db) {
+    static_cast<Compressor*>(c)->set_limiter_feedback_gain_reduction_db(db);
+}
+void orc_comp_set_makeup_gain(void* c, double db) { static_cast<Compressor*>(c)->set_makeup_gain(db); }
 double orc_comp_gain_reduction(void* c) { return static_cast<Compressor*>(c)->current_gain_reduction(); }
 double orc_comp_makeup_gain(void* c) { return static_cast<Compressor*>(c)->current_makeup_gain(); }
 double orc_comp_plosive_ratio(void* c) { return static_cast<Compressor*>(c)->plosive_ratio(); }
@@ -564,6 +585,33 @@ void orc_input_stage_process(int mode, double fs, float* buf, size_t n, float* i
         info4[2] = st.cleanup().rumble_detected() ? 1.0f : 0.0f;
         info4[3] = st.cleanup().selected_high_pass_hz();
     }
+}
+// processor/tests.rs:500-549 `process_adaptive_input_cleanup`: per chunk analyse the raw block, DC block (+ the fixed
+// high-pass when the mode is Off), process; info5: [ever_hum, ever_rumble, max selected_high_pass_hz (starting from
+// INPUT_PREFILTER_HZ), final hum_line_hz, final selected_high_pass_hz].  mode: 0 off, 2 gentle, 3 strong.
+void orc_cleanup_harness(int mode, float fs, float* buf, size_t n, size_t chunk, float* info5) {
+    InputPreFilterState dc;
+    Biquad hp(BiquadType::HighPass, 80.0, 0.0, 0.707, static_cast<double>(fs));
+    AdaptiveInputCleanup cleanup(fs);
+    if (mode == 2) cleanup.set_mode(CleanupMode::Gentle);
+    if (mode == 3) cleanup.set_mode(CleanupMode::Strong);
+    bool ever_hum = false, ever_rumble = false;
+    float max_hp = 80.0f;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t len = std::min(chunk, n - off);
+        float* blk = buf + off;
+        if (cleanup.enabled()) cleanup.analyze_input(blk, len);
+        apply_input_pre_filter(blk, len, dc, hp, !cleanup.enabled());
+        if (cleanup.enabled()) cleanup.process_block(blk, len);
+        ever_hum = ever_hum || cleanup.hum_detected();
+        ever_rumble = ever_rumble || cleanup.rumble_detected();
+        max_hp = rmaxf(max_hp, cleanup.selected_high_pass_hz());
+    }
+    info5[0] = ever_hum ? 1.0f : 0.0f;
+    info5[1] = ever_rumble ? 1.0f : 0.0f;
+    info5[2] = max_hp;
+    info5[3] = cleanup.hum_line_hz();
+    info5[4] = cleanup.selected_high_pass_hz();
 }
 // routing.rs:616-641 harness: analyze only; info3: [hum_line_hz, phase_valid, hum_hold_samples]
 void orc_cleanup_analyze(int mode, float fs, const float* buf, size_t n, float* info3) {

@@ -93,6 +93,22 @@ def lib() -> C.CDLL:
         L.orc_comp_set_noise_reference_reliability.argtypes = [C.c_void_p, C.c_double]
         L.orc_comp_process_block_with_activity.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_int, C.c_double, C.c_double,
                                                            C.c_double, C.c_double]
+        L.orc_meter_new.restype = C.c_void_p
+        L.orc_meter_new.argtypes = [C.c_uint32]
+        L.orc_meter_free.argtypes = [C.c_void_p]
+        L.orc_meter_process.argtypes = [C.c_void_p, f32p, C.c_size_t]
+        L.orc_meter_momentary.restype = C.c_float
+        L.orc_meter_momentary.argtypes = [C.c_void_p]
+        L.orc_meter_reset.argtypes = [C.c_void_p]
+        L.orc_comp_update_auto_makeup_gain.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_size_t]
+        L.orc_comp_estimate_activity.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, f64p]
+        L.orc_comp_speech_activity_from_rms_db.restype = C.c_double
+        L.orc_comp_speech_activity_from_rms_db.argtypes = [C.c_double]
+        L.orc_comp_set_limiter_feedback_gain_reduction_db.argtypes = [C.c_void_p, C.c_double]
+        L.orc_comp_set_makeup_gain.argtypes = [C.c_void_p, C.c_double]
+        for name in ("auto_makeup_activity", "auto_makeup_activity_reliability"):
+            getattr(L, f"orc_comp_{name}").restype = C.c_double
+            getattr(L, f"orc_comp_{name}").argtypes = [C.c_void_p]
         for name in ("gain_reduction", "makeup_gain", "plosive_ratio"):
             getattr(L, f"orc_comp_{name}").restype = C.c_double
             getattr(L, f"orc_comp_{name}").argtypes = [C.c_void_p]
@@ -115,6 +131,7 @@ def lib() -> C.CDLL:
         L.orc_tpl_set_ceiling_linear.argtypes = [C.c_void_p, C.c_float]
         L.orc_tpl_process.argtypes = [C.c_void_p, f32p, C.c_size_t, f32p]
         L.orc_input_stage_process.argtypes = [C.c_int, C.c_double, f32p, C.c_size_t, f32p]
+        L.orc_cleanup_harness.argtypes = [C.c_int, C.c_float, f32p, C.c_size_t, C.c_size_t, f32p]
         L.orc_cleanup_analyze.argtypes = [C.c_int, C.c_float, f32p, C.c_size_t, f32p]
         L.orc_percentile_f32.restype = C.c_float
         L.orc_percentile_f32.argtypes = [f32p, C.c_size_t, C.c_float]

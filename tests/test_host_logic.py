@@ -95,6 +95,21 @@ def test_batched_headroom_validation_equals_the_sequential_walk():
     assert np.allclose(r["band_gains"], np.asarray(hot["band_gains"]) * headroom.HEADROOM_SCALES[index])
     assert results[1]["headroom_gain_scale"] == 1.0 and results[1]["headroom_safe"]
     assert results[2] == broken  # headroom.py:303-304: malformed settings pass through untouched
+    # decision margins: the walk examined scales 0 .. index; none of these renders sits within 0.01 dB of a threshold
+    margins = r["headroom_validation"]["decision_margins"]
+    assert margins["renders_examined"] == index + 1 and margins["near_threshold"] == 0
+    worst = min(abs(v) for k in range(index + 1) for v in headroom.headroom_margins_db(sims[k]).values())
+    assert margins["smallest_abs_margin_db"] == worst >= headroom.DECISION_MARGIN_DB
+
+
+def test_decision_margins_flag_renders_next_to_a_threshold():
+    safe = {"pre_limiter_true_peak_headroom_db": 1.004, "limiter_gain_reduction_db": 0.2, "true_peak_limiter_gain_reduction_db": 0.1}
+    unsafe = {"pre_limiter_true_peak_headroom_db": 3.0, "limiter_gain_reduction_db": 1.5, "true_peak_limiter_gain_reduction_db": 0.1}
+    m = headroom.headroom_margins_db(safe)
+    assert abs(m["pre_limiter_true_peak_headroom_db"] - 0.004) < 1e-12 and m["limiter_gain_reduction_db"] == 0.8
+    report = headroom.decision_margin_report([unsafe, safe, unsafe], examined=1)
+    assert report["renders_examined"] == 2 and report["near_threshold"] == 1
+    assert report["smallest_at"] == {"scale_index": 1, "metric": "pre_limiter_true_peak_headroom_db"}
 
 
 def test_abstain_when_no_scale_is_safe():
