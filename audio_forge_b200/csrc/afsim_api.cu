@@ -1092,6 +1092,18 @@ int afsim_sweep_collect_audio(AfsimHandle* h, AfsimSweep* sweep, size_t pair, fl
     return AFSIM_OK;
 }
 
+int afsim_sweep_status(AfsimHandle* h, AfsimSweep* sweep) {
+    if (!h || !sweep) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
+    h->error.clear();
+    AF_CUDA(h, cudaSetDevice(h->device));
+    int tail_err = 0;
+    AF_CUDA(h, cudaMemcpyAsync(&tail_err, sweep->d_tail_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (tail_err) return set_error(h, AFSIM_CUDA_ERROR, "fused tail kernel: pipeline watchdog fired (results invalid)");
+    return AFSIM_OK;
+}
+
 void* afsim_sweep_metrics_device_ptr(AfsimSweep* sweep) { return sweep ? sweep->d_metrics : nullptr; }
 
 int afsim_sweep_kernel_count(const AfsimSweep* sweep) { return sweep ? sweep->kernels_per_launch : 0; }

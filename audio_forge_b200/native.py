@@ -26,9 +26,11 @@ EXPORTS = (
     "afsim_abi_version", "afsim_create", "afsim_destroy", "afsim_trim", "afsim_last_error", "afsim_create_error",
     "afsim_chain_settings_default", "afsim_default_bands", "afsim_chain_render", "afsim_eq_render",
     "afsim_eq_response", "afsim_chain_sweep", "afsim_sweep_prepare", "afsim_sweep_prepare_synthetic",
-    "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
+    "afsim_sweep_launch", "afsim_sweep_collect", "afsim_sweep_status", "afsim_sweep_collect_audio", "afsim_sweep_metrics_device_ptr",
     "afsim_sweep_kernel_count", "afsim_sweep_last_render_ms", "afsim_sweep_release",
     "afsim_sweep_profile_stages", "afsim_sweep_profile_wavefront", "afsim_sweep_batch_info", "afsim_measure_issue_peak",
+    "afsim_multi_create", "afsim_multi_destroy", "afsim_multi_device_count", "afsim_multi_last_error",
+    "afsim_multi_create_error", "afsim_multi_chain_sweep", "afsim_multi_partition",
     "afsim_selftest_math", "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
@@ -92,6 +94,17 @@ def lib() -> C.CDLL:
                                                 u32p, u32p, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.afsim_sweep_launch.argtypes = [vp, vp]
     L.afsim_sweep_collect.argtypes = [vp, vp, metrics_p]
+    L.afsim_sweep_status.argtypes = [vp, vp]
+    L.afsim_multi_create.argtypes = [C.c_uint32, C.POINTER(vp)]
+    L.afsim_multi_destroy.argtypes = [vp]
+    L.afsim_multi_destroy.restype = None
+    L.afsim_multi_device_count.argtypes = [vp]
+    L.afsim_multi_last_error.argtypes = [vp]
+    L.afsim_multi_last_error.restype = C.c_char_p
+    L.afsim_multi_create_error.restype = C.c_char_p
+    L.afsim_multi_chain_sweep.argtypes = [vp, C.POINTER(f32p), szp, C.c_size_t, C.c_double, cand_p, C.c_size_t, u32p, u32p,
+                                          C.c_size_t, metrics_p, f32p]
+    L.afsim_multi_partition.argtypes = [cand_p, C.c_size_t, szp, C.c_size_t, u32p, u32p, C.c_size_t, C.c_int, u32p]
     L.afsim_sweep_collect_audio.argtypes = [vp, vp, C.c_size_t, f32p, C.c_size_t]
     L.afsim_sweep_metrics_device_ptr.argtypes = [vp]
     L.afsim_sweep_metrics_device_ptr.restype = vp
@@ -357,6 +370,63 @@ class Simulator:
                                                         candidates, len(candidates), _u32p(pp), _u32p(pc), n_pairs,
                                                         1 if want_audio else 0, C.byref(ptr)))
         return Sweep(self, ptr.value, n_pairs, [passage_len] * n_pairs)
+
+
+class MultiSimulator:
+    """One handle for several GPUs of the box (afsim_multi_* in include/afsim.h): what the Rust host would bind.  The
+    partition, the per-GPU renders and the NCCL gather of the metric structs all happen inside the library."""
+
+    def __init__(self, device_mask: int):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.afsim_multi_create(int(device_mask), C.byref(h))
+        if rc != abi.AFSIM_OK:
+            raise AfsimError(rc, L.afsim_multi_create_error().decode())
+        self._h = h
+        self.n_devices = int(L.afsim_multi_device_count(h))
+        self.last_device_ms = 0.0
+
+    def chain_sweep(self, passages, sample_rate, candidates, pair_passage=None, pair_candidate=None):
+        passages = [np.ascontiguousarray(p, dtype=np.float32) for p in passages]
+        f32p = C.POINTER(C.c_float)
+        ptrs = (f32p * max(len(passages), 1))(*[_f32p(p) for p in passages])
+        lens = (C.c_size_t * max(len(passages), 1))(*[p.size for p in passages])
+        pp, pc, n_pairs = Simulator._pairs(len(passages), len(candidates), pair_passage, pair_candidate)
+        out = (abi.AfChainMetrics * max(n_pairs, 1))()
+        ms = C.c_float(0.0)
+        rc = lib().afsim_multi_chain_sweep(self._h, ptrs, lens, len(passages), float(sample_rate), candidates, len(candidates),
+                                           _u32p(pp), _u32p(pc), n_pairs, out, C.byref(ms))
+        if rc != abi.AFSIM_OK:
+            msg = lib().afsim_multi_last_error(self._h).decode()
+            if rc == abi.AFSIM_INVALID_ARGUMENT:
+                raise ValueError(msg)
+            raise AfsimError(rc, msg)
+        self.last_device_ms = float(ms.value)
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib().afsim_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def partition(candidates, passage_lens, pair_passage, pair_candidate, n_parts: int) -> np.ndarray:
+    """afsim_multi_partition: owner of every pair (the C-side partitioner; no GPU needed)."""
+    lens = (C.c_size_t * max(len(passage_lens), 1))(*[int(v) for v in passage_lens])
+    pp = np.ascontiguousarray(pair_passage, dtype=np.uint32)
+    pc = np.ascontiguousarray(pair_candidate, dtype=np.uint32)
+    owner = np.zeros(pp.size, dtype=np.uint32)
+    rc = lib().afsim_multi_partition(candidates, len(candidates), lens, len(passage_lens), _u32p(pp), _u32p(pc), pp.size,
+                                     int(n_parts), _u32p(owner))
+    if rc != abi.AFSIM_OK:
+        raise ValueError("afsim_multi_partition: invalid arguments")
+    return owner
 
 
 def exported_symbols_present() -> list[str]:

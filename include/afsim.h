@@ -291,6 +291,9 @@ int afsim_sweep_collect(AfsimHandle* handle, AfsimSweep* sweep, AfChainMetrics* 
 /* Copies one stream's rendered audio (want_audio sweeps) to the host. */
 int afsim_sweep_collect_audio(AfsimHandle* handle, AfsimSweep* sweep, size_t pair, float* out_audio,
                               size_t n);
+/* Waits for the stream and reports an asynchronous failure of the last launch (AFSIM_OK otherwise) without copying
+ * anything: for callers that read the metrics through afsim_sweep_metrics_device_ptr instead of afsim_sweep_collect. */
+int afsim_sweep_status(AfsimHandle* handle, AfsimSweep* sweep);
 /* Device pointer of the n_pairs AfChainMetrics (for an NCCL gather without a host hop). */
 void* afsim_sweep_metrics_device_ptr(AfsimSweep* sweep);
 /* Kernels launched by one afsim_sweep_launch. */
@@ -299,6 +302,31 @@ int afsim_sweep_kernel_count(const AfsimSweep* sweep);
  * events on the handle's stream); waits for completion. */
 int afsim_sweep_last_render_ms(AfsimHandle* handle, AfsimSweep* sweep, float* out_ms);
 void afsim_sweep_release(AfsimHandle* handle, AfsimSweep* sweep);
+
+/* ---- one handle for all GPUs of the box --------------------- */
+
+/* The Rust host binds ONE handle per process (the shape of its runtime-loaded plugin, dsp/deepfilter_ffi.rs:335-386).
+ * afsim_multi_create opens one simulator per GPU named in `device_mask` (bit d = CUDA device d) and, for more than one
+ * GPU, one NCCL communicator over them (libnccl.so.2 is resolved at run time; AFSIM_UNSUPPORTED when it is missing).
+ * afsim_multi_chain_sweep is afsim_chain_sweep over all of them: the candidate x passage streams are partitioned by
+ * cost (afsim_multi_partition), every GPU renders its shard (passages are replicated), and the per-stream metric
+ * structs are all-gathered device to device with ncclAllGather -- the only exchange on the path; out_metrics is in the
+ * caller's pair order.  out_device_ms (nullable): device time of the slowest GPU, render + gather (CUDA events). */
+typedef struct AfsimMulti AfsimMulti;
+int afsim_multi_create(uint32_t device_mask, AfsimMulti** out_handle);
+void afsim_multi_destroy(AfsimMulti* handle);
+int afsim_multi_device_count(const AfsimMulti* handle);
+const char* afsim_multi_last_error(const AfsimMulti* handle);
+const char* afsim_multi_create_error(void);
+int afsim_multi_chain_sweep(AfsimMulti* handle, const float* const* passages, const size_t* passage_len,
+                            size_t n_passages, double sample_rate, const AfCandidate* candidates, size_t n_candidates,
+                            const uint32_t* pair_passage, const uint32_t* pair_candidate, size_t n_pairs,
+                            AfChainMetrics* out_metrics, float* out_device_ms);
+/* The partition afsim_multi_chain_sweep uses (deterministic; also what audio_forge_b200/sharding.py computes for the
+ * one-process-per-GPU launch): out_owner[i] = part of pair i, parts balanced by (40 + EQ sections) x samples. */
+int afsim_multi_partition(const AfCandidate* candidates, size_t n_candidates, const size_t* passage_len,
+                          size_t n_passages, const uint32_t* pair_passage, const uint32_t* pair_candidate,
+                          size_t n_pairs, int n_parts, uint32_t* out_owner);
 
 /* ---- measurement helpers (bench.py; no reference counterpart) ------------------ */
 

@@ -151,6 +151,22 @@ def test_large_compressor_grids_are_cut_along_passages():
     assert np.bincount(piece).max() <= 1000 and np.bincount(piece).sum() == passage.size
 
 
+def test_c_abi_partitioner_equals_the_python_one():
+    """afsim_multi_partition (what afsim_multi_chain_sweep shards with, one process for all GPUs) and
+    sharding.plan_shards (one process per GPU under torchrun) are the same deterministic rule."""
+    from audio_forge_b200 import native, workloads
+    cands = workloads.full_chain_candidates(96, seed=2)
+    lens = [30000, 48000, 12345]
+    rng = np.random.default_rng(0)
+    pp = rng.integers(0, 3, size=500).astype(np.uint32)
+    pc = rng.integers(0, 96, size=500).astype(np.uint32)
+    for world in (1, 2, 3, 8):
+        owner = native.partition(cands, lens, pp, pc, world)
+        shards = sharding.plan_shards(cands, pp, pc, lens, world)
+        for r in range(world):
+            assert np.array_equal(np.nonzero(owner == r)[0], shards[r])
+
+
 def test_shard_streams_is_balanced_and_complete():
     rng = np.random.default_rng(0)
     costs = rng.choice([50.0, 56.0, 80.0], size=1000) * 480000
