@@ -506,11 +506,16 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         const bool split = split_mode == 2 || (split_mode != 1 && S <= 16384);
         const size_t ring_elems = static_cast<size_t>(a.ring_rows) * sp;
         AF_CUDA(h, alloc_ring(&a.buf_a, ring_elems));
-        // AFSIM_TAIL: 0 = the limiter / true-peak tail as separate stage kernels, 1 (default) = the fused SM-local tail
-        // kernel (afsim_tail.cu) for the batches that take the split kernels, 2 = for every batch
-        const int tail_mode = env_int("AFSIM_TAIL", 1);
-        const bool use_tail = (a.structure & ST_LIMITER) && tail_supported(a.lookahead) &&
-                              (tail_mode == 2 || (tail_mode == 1 && split));
+        // The limiter / true-peak tail as ONE SM-local, TMA-fed kernel (afsim_tail.cu) instead of five stage kernels.
+        // AFSIM_TAIL: 1 = never, 2 = always; default: the few-stream (split) batches whose chain IS the tail -- no
+        // compressor, no de-esser (batch true-peak detection + limiting, BASELINE config 4).  Behind a compressor /
+        // de-esser wavefront the five thin stage kernels overlap with the other stages' kernels across chunks, and one
+        // CTA-per-32-streams kernel that holds 100 KB of shared memory per CTA displaces the serial kernels' staging
+        // areas (measured: C2 -32 %, C5 at 8192 streams per GPU -13 %).
+        const int tail_mode = env_int("AFSIM_TAIL", 0);
+        const bool tail_dominated = !(a.structure & (ST_COMPRESSOR | ST_DEESSER));
+        const bool use_tail = (a.structure & ST_LIMITER) && tail_supported(a.lookahead) && tail_mode != 1 &&
+                              (tail_mode == 2 || (split && tail_dominated));
         if (use_tail) {
             AF_CUDA(h, sweep->mem.alloc(&a.st_lim, kStateLimiter * sp));
             AF_CUDA(h, sweep->mem.alloc(&a.tail_hist, static_cast<size_t>(kTailHistRows) * sp));

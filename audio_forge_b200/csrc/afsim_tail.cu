@@ -41,7 +41,6 @@ __constant__ float c_tail_fir[4][32] = {
 };
 
 constexpr int kSub = 32;  // time rows per sub-tile (= TMA box rows)
-constexpr int kMapW = kTailMapWarps;
 constexpr int kTG = 3;    // target-gain slots (f64, 8 KB each)
 constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is history for the FIR / the 20-sample delay)
 constexpr int kTT = 3;    // true-peak target slots
@@ -51,8 +50,8 @@ constexpr uint32_t kSpinLimit = 1u << 22;
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
-    int cnt_lim_m[kTG];
-    int cnt_fir_in[kTT];
+    int done_lim_m;   // serial / single-warp stages: sub-tiles finished, in order
+    int cnt_fir_in[kTT];  // map tasks: FIR units arrived, per ring slot (4 per use)
     int cnt_fir_out[kCY];
     int done_lim_r;
     int done_tp_r;
@@ -150,70 +149,76 @@ __device__ __forceinline__ TailSmem carve(int cx) {
     return sm;
 }
 
-// ---- map tasks (one warp = 8 rows of a sub-tile, lane = stream) ------------------------------------------------------
+// ---- map tasks (lane = stream) ------------------------------------------------------------------------------------------
 
-// LIM-M: windows [r - L, r] of |x| for the 8 rows r = base .. base + 7 (dsp/limiter.rs:253-262; max is order
-// independent, so the shared part of the eight windows is scanned once), then the target gain in f64.
+// LIM-M, one warp per sub-tile: windows [r - L, r] of |x| for the 32 rows r = base .. base + 31 (dsp/limiter.rs:253-262;
+// max is order independent, so the part the 32 windows share is scanned once: L + 32 loads for 32 outputs), then the
+// target gain in f64.  The scan runs on NaN-PROPAGATING maxima (max.NaN.f32): without a NaN in the span they equal
+// fmaxf bit for bit, and a NaN result sends the sub-tile to the reference queue's NaN semantics (nan_aware_window).
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane, int base, int L, double ceil_lin,
-                                           double* tg_rows /* row 0 of this warp's 8 */) {
-    constexpr int G = 8;
-    bool nan_seen = false;
-    auto x = [&](int m) {
-        const float v = fabsf(xs[(size_t)((base + m) & xmask) * 32 + lane]);
-        nan_seen = nan_seen || v != v;
-        return v;
+                                           double* tg /* row 0 of the sub-tile's slot */) {
+    constexpr int G = kSub;
+    auto x = [&](int m) { return fabsf(xs[(size_t)((base + m) & xmask) * 32 + lane]); };
+    auto store_target = [&](int j, float w) {
+        const double peak = (double)w;
+        tg[(size_t)j * 32 + lane] = peak > ceil_lin ? ceil_lin / peak : 1.0;
     };
-    float win[G];
+    bool nan_seen = false;
     if (L >= G) {
+        float win[G];
         float run = 0.0f;
-        for (int m = -1; m >= G - L; --m) run = fmaxf(run, x(m));
-        float left[G];
+        for (int m = -1; m >= G - L; --m) run = max_nan(run, x(m));
 #pragma unroll
-        for (int j = G - 1; j >= 0; --j) {
-            run = fmaxf(run, x(j - L));
-            left[j] = run;
+        for (int j = G - 1; j >= 0; --j) {  // suffix part of window j: the samples before the sub-tile, from j - L on
+            run = max_nan(run, x(j - L));
+            win[j] = run;
         }
         float prefix = 0.0f;
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            prefix = fmaxf(prefix, x(j));
-            win[j] = fmaxf(left[j], prefix);
+        for (int j = 0; j < G; ++j) {       // prefix part: the sub-tile's own samples up to j; the target leaves at once
+            prefix = max_nan(prefix, x(j));
+            const float w = max_nan(win[j], prefix);
+            nan_seen = nan_seen || w != w;
+            store_target(j, w);
         }
     } else {
-#pragma unroll
+#pragma unroll 4
         for (int j = 0; j < G; ++j) {
             float w = 0.0f;
-            for (int m = j - L; m <= j; ++m) w = fmaxf(w, x(m));
-            win[j] = w;
+            for (int m = j - L; m <= j; ++m) w = max_nan(w, x(m));
+            nan_seen = nan_seen || w != w;
+            store_target(j, w);
         }
     }
-    if (nan_seen) {  // rare: the reference queue's NaN semantics (afsim_stages.h: nan_aware_window)
+    if (nan_seen) {  // rare: a NaN inside a lookback -- every row again with the reference queue's semantics
+#pragma unroll 1
         for (int j = 0; j < G; ++j) {
             auto xj = [&](int m) { return x(j + m); };
-            win[j] = nan_aware_window(xj, L);
+            store_target(j, nan_aware_window(xj, L));
         }
-    }
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-        const double peak = (double)win[j];
-        tg_rows[(size_t)j * 32 + lane] = peak > ceil_lin ? ceil_lin / peak : 1.0;
     }
 }
 
-// 4x polyphase FIR peaks of rows base .. base + 7 of a ring (taps in the reference's order, dsp/true_peak.rs:173-186)
+// 4x polyphase FIR peaks of rows base .. base + 7 of a ring (taps in the reference's order, dsp/true_peak.rs:173-186).
+// The rings hold SANITISED samples (non-finite -> 0 at the write, dsp/true_peak.rs:211,343), so the window loads are plain.
 __device__ __forceinline__ void task_fir(const float* ring, int mask, int lane, int base, float (&pk)[kFirChunk]) {
     float win[kFirWin];
 #pragma unroll
-    for (int i = 0; i < kFirWin; ++i) {
-        const float v = ring[(size_t)((base - 31 + i) & mask) * 32 + lane];
-        win[i] = af_finite(v) ? v : 0.0f;  // dsp/true_peak.rs:211,343 sanitise
-    }
+    for (int i = 0; i < kFirWin; ++i) win[i] = ring[(size_t)((base - 31 + i) & mask) * 32 + lane];
     fir8_peaks(win, c_tail_fir, pk);
 }
 
 }  // namespace
 
-// One CTA = 32 streams x one chunk.  Warp 0: TMA producer; warp 1: LIM-R; warp 2: TP-R; warps 3..6: maps.
+// One CTA = 32 streams x one chunk, 7 warps:
+//   warp 0  LIM-R + TMA producer      warp 1  TP-R + output statistics      warp 2  LIM-M (a whole sub-tile per step)
+//   warps 3..6  FIR units of 8 rows (4 of FIR-IN and 4 of FIR-OUT per step), spread 3 / 2 / 2 / 1 so that the warp
+//   schedulers that also host a serial warp get less map work (warp w issues on scheduler w mod 4)
 __global__ void __launch_bounds__(kTailThreads, 2)
 k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int cx, int* err_out) {
     if (err_out && *reinterpret_cast<volatile int*>(err_out)) return;  // an earlier launch's watchdog fired: do not pile up waits
@@ -235,9 +240,9 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
     // ---- init: barriers, counters, histories -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int i = 0; i < cx; ++i) mbar_init(&ctl->full[i], 1);
-        for (int i = 0; i < kTG; ++i) ctl->cnt_lim_m[i] = 0;
         for (int i = 0; i < kTT; ++i) ctl->cnt_fir_in[i] = 0;
         for (int i = 0; i < kCY; ++i) ctl->cnt_fir_out[i] = 0;
+        ctl->done_lim_m = 0;
         ctl->done_lim_r = 0;
         ctl->done_tp_r = 0;
         ctl->error = 0;
@@ -260,25 +265,21 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
     __syncthreads();
 
     if (warp == 0) {
-        // ---- producer: one thread feeds the x ring, Lt history sub-tiles first -----------------------------------------
-        if (lane == 0) {
-            for (int j = -Lt; j < n_sub; ++j) {
-                // slot (j mod cx) still holds sub-tile j - cx, whose rows LIM-M / LIM-R need up to sub-tile j - cx + Lt
-                const int need = j - cx + Lt + 1;
-                if (need > 0) wait_ge(&ctl->done_lim_r, need, ctl);
-                const int slot = x_slot(j);
-                if (j < 0 && first_chunk) {
-                    mbar_arrive(&ctl->full[slot]);  // zero-filled above; keeps the phase sequence uniform
-                } else {
-                    int row = ck.row0 + j * kSub;
-                    if (row < 0) row += a.ring_rows;
-                    mbar_expect_tx(&ctl->full[slot], kSub * 32 * 4);
-                    tma_load_2d(sm.xs + (size_t)slot * kSub * 32, &x_map, s_base, row, &ctl->full[slot]);
-                }
+        // ---- LIM-R: gain recurrence of the sample limiter, lane = stream; lane 0 also feeds the x ring -----------------------
+        auto load_subtile = [&](int j) {  // one thread: sub-tile j -> its slot (the slot's previous tenant is no longer needed)
+            const int slot = x_slot(j);
+            if (j < 0 && first_chunk) {
+                mbar_arrive(&ctl->full[slot]);  // zero-filled above; keeps the phase sequence uniform
+            } else {
+                int row = ck.row0 + j * kSub;
+                if (row < 0) row += a.ring_rows;
+                mbar_expect_tx(&ctl->full[slot], kSub * 32 * 4);
+                tma_load_2d(sm.xs + (size_t)slot * kSub * 32, &x_map, s_base, row, &ctl->full[slot]);
             }
-        }
-    } else if (warp == 1) {
-        // ---- LIM-R: gain recurrence of the sample limiter, lane = stream ---------------------------------------------------
+        };
+        // slot (j mod cx) is free once LIM-R finished sub-tile j - cx + Lt: the first cx sub-tiles need no wait
+        if (lane == 0)
+            for (int j = -Lt; j < n_sub && j < cx - Lt; ++j) load_subtile(j);
         const CandidateParams& p = stream_params(a, s);
         const double ceil_lin = p.l_ceil, rel = p.l_release, one_m_rel = 1.0 - rel;
         LimiterR st;
@@ -291,13 +292,12 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         double g = st.g, min_g = st.min_g;
         for (int j = 0; j < n_sub; ++j) {
             const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
-            wait_ge(&ctl->cnt_lim_m[j % kTG], kMapW * (j / kTG + 1), ctl);
-            const int k = j - kCO + 1;  // the ring row block about to be overwritten was last read by FIR-IN(k) and TP-R(k)
+            wait_ge(&ctl->done_lim_m, j + 1, ctl);
+            const int k = j - kCO + 1;  // the ring rows about to be overwritten were last read by FIR-IN(k) and TP-R(k)
             if (k >= 0) {
-                wait_ge(&ctl->cnt_fir_in[k % kTT], kMapW * (k / kTT + 1), ctl);
+                wait_ge(&ctl->cnt_fir_in[k % kTT], 4 * (k / kTT + 1), ctl);
                 wait_ge(&ctl->done_tp_r, k + 1, ctl);
             }
-            mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);  // x rows: already landed (the maps waited for them)
             const double* tg = sm.tg + (size_t)(j % kTG) * kSub * 32 + lane;
 #pragma unroll
             for (int u0 = 0; u0 < kSub; u0 += 8) {
@@ -316,13 +316,18 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                         else
                             g = rel * g + one_m_rel * tgt[u];
                         min_g = fmin(min_g, g);
-                        sm.ol[(size_t)((j * kSub + u0 + u) & omask) * 32 + lane] =
-                            (float)clampd((double)delayed[u] * g, -ceil_lin, ceil_lin);
+                        const float y = (float)clampd((double)delayed[u] * g, -ceil_lin, ceil_lin);
+                        // both readers sanitise what they read (dsp/true_peak.rs:211,343): done once, here
+                        sm.ol[(size_t)((j * kSub + u0 + u) & omask) * 32 + lane] = af_finite(y) ? y : 0.0f;
                     }
                 }
             }
             __syncwarp();
-            if (lane == 0) st_release(&ctl->done_lim_r, j + 1);
+            if (lane == 0) {
+                st_release(&ctl->done_lim_r, j + 1);
+                const int jn = j + cx - Lt;  // its slot held sub-tile j - Lt: nobody needs that any more
+                if (jn < n_sub) load_subtile(jn);
+            }
         }
         st.g = g;
         st.min_g = min_g;
@@ -332,7 +337,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             StateIO<true> io{a.st_lim + s, stride};
             st.sync(io);
         }
-    } else if (warp == 2) {
+    } else if (warp == 1) {
         // ---- TP-R: gain recurrence of the true-peak limiter + output statistics, lane = stream -------------------------------
         const CandidateParams& p = stream_params(a, s);
         const float ceil_lin = p.tp_ceil, rel = p.tp_release, one_m_rel = 1.0f - rel;
@@ -348,9 +353,9 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         float* rows_out = a.rows + (size_t)1 * a.n_rows * stride + s;
         for (int j = 0; j < n_sub; ++j) {
             const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
-            wait_ge(&ctl->cnt_fir_in[j % kTT], kMapW * (j / kTT + 1), ctl);
+            wait_ge(&ctl->cnt_fir_in[j % kTT], 4 * (j / kTT + 1), ctl);
             const int k = j - kCY + 1;  // last reader of the output ring rows about to be overwritten: FIR-OUT(k)
-            if (k >= 0) wait_ge(&ctl->cnt_fir_out[k % kCY], kMapW * (k / kCY + 1), ctl);
+            if (k >= 0) wait_ge(&ctl->cnt_fir_out[k % kCY], 4 * (k / kCY + 1), ctl);
             const float* tt = sm.tt + (size_t)(j % kTT) * kSub * 32 + lane;
 #pragma unroll
             for (int u0 = 0; u0 < kSub; u0 += 8) {
@@ -358,8 +363,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     pk[u] = tt[(size_t)(u0 + u) * 32];
-                    const float v = sm.ol[(size_t)((j * kSub + u0 + u - kTpDelay) & omask) * 32 + lane];
-                    delayed[u] = af_finite(v) ? v : 0.0f;
+                    delayed[u] = sm.ol[(size_t)((j * kSub + u0 + u - kTpDelay) & omask) * 32 + lane];  // sanitised at the write
                 }
                 const int n_first = ck.n0 + j * kSub + u0;
                 auto walk = [&](auto may_end) {
@@ -412,61 +416,69 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             StateIO<true> io{a.st_tp + s, stride};
             st.sync(io);
         }
-    } else {
-        // ---- maps: warp m owns rows [8m, 8m + 8) of every sub-tile; step t = LIM-M(t), FIR-IN(t - 1), FIR-OUT(t - 2) --------
-        const int m = warp - 3;
+    } else if (warp == 2) {
+        // ---- LIM-M: one sub-tile per step ---------------------------------------------------------------------------------------
         const double l_ceil = a.map_tab[(size_t)MT_L_CEIL * stride + s];
+        for (int j = 0; j < n_sub; ++j) {
+            if (j == 0)
+                for (int h = -Lt; h < 0; ++h) mbar_wait(&ctl->full[x_slot(h)], x_parity(h), ctl);
+            mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);
+            if (j - kTG >= 0) wait_ge(&ctl->done_lim_r, j - kTG + 1, ctl);  // the slot's previous targets were consumed
+            task_lim_m(sm.xs, xmask, lane, j * kSub + xoff, L, l_ceil, sm.tg + (size_t)(j % kTG) * kSub * 32);
+            __syncwarp();
+            if (lane == 0) st_release(&ctl->done_lim_m, j + 1);
+        }
+    } else {
+        // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: FIR-OUT units of sub-tile t - 2 (their input is
+        // ready first), then FIR-IN units of sub-tile t - 1.  warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1; warp 5: IN 3 + OUT 2;
+        // warp 6: OUT 3.
+        const int m = warp - 3;
+        const int in_first = m == 0 ? 0 : (m == 3 ? 4 : m + 1), in_count = m == 0 ? 2 : (m == 3 ? 0 : 1);
+        const int out_unit = m;
         const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
         float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
         float max_in = 0.0f, max_out = 0.0f;
-        for (int t = 0; t < n_sub + 2; ++t) {
-            if (t < n_sub) {
-                const int j = t;
-                if (j == 0)
-                    for (int h = -Lt; h < 0; ++h) mbar_wait(&ctl->full[x_slot(h)], x_parity(h), ctl);
-                mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);
-                if (j - kTG >= 0) wait_ge(&ctl->done_lim_r, j - kTG + 1, ctl);
-                task_lim_m(sm.xs, xmask, lane, j * kSub + 8 * m + xoff, L, l_ceil, sm.tg + (size_t)((j % kTG) * kSub + 8 * m) * 32);
-                __syncwarp();
-                if (lane == 0) red_release_add(&ctl->cnt_lim_m[j % kTG], 1);
-            }
-            if (t >= 1 && t - 1 < n_sub) {
-                const int j = t - 1;
-                const int valid = ck.len - j * kSub - 8 * m;  // rows of this warp's 8 that exist
-                wait_ge(&ctl->done_lim_r, j + 1, ctl);
-                if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);
-                float pk[kFirChunk];
-                task_fir(sm.ol, omask, lane, j * kSub + 8 * m, pk);
-                float* tt = sm.tt + (size_t)((j % kTT) * kSub + 8 * m) * 32 + lane;
-#pragma unroll
-                for (int i = 0; i < kFirChunk; ++i) {
-                    // feed-forward part of dsp/true_peak.rs:349-354
-                    tt[(size_t)i * 32] = pk[i] > tp_ceil ? clampf((tp_ceil * 0.999f) / pk[i], 0.0f, 1.0f) : 1.0f;
-                    if (i < valid) max_in = fmaxf(max_in, pk[i]);
-                }
-                __syncwarp();
-                if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], 1);
-            }
+        for (int t = 1; t < n_sub + 2; ++t) {
             if (t >= 2) {
-                const int j = t - 2;
-                const int valid = ck.len - j * kSub - 8 * m;
+                const int j = t - 2, base = j * kSub + 8 * out_unit;
+                const int valid = ck.len - base;
                 wait_ge(&ctl->done_tp_r, j + 1, ctl);
                 float pk[kFirChunk];
-                task_fir(sm.ys, ymask, lane, j * kSub + 8 * m, pk);
+                task_fir(sm.ys, ymask, lane, base, pk);
 #pragma unroll
                 for (int i = 0; i < kFirChunk; ++i)
                     if (i < valid) max_out = fmaxf(max_out, pk[i]);
                 if (audio) {
 #pragma unroll
                     for (int i = 0; i < kFirChunk; ++i)
-                        if (i < valid) audio[j * kSub + 8 * m + i] = sm.ys[(size_t)((j * kSub + 8 * m + i) & ymask) * 32 + lane];
+                        if (i < valid) audio[base + i] = sm.ys[(size_t)((base + i) & ymask) * 32 + lane];
                 }
                 __syncwarp();
                 if (lane == 0) red_release_add(&ctl->cnt_fir_out[j % kCY], 1);
             }
+            if (t - 1 < n_sub && in_count > 0) {
+                const int j = t - 1;
+                wait_ge(&ctl->done_lim_r, j + 1, ctl);
+                if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);  // the slot's previous targets were consumed
+                for (int q = in_first; q < in_first + in_count; ++q) {
+                    const int base = j * kSub + 8 * q;
+                    const int valid = ck.len - base;
+                    float pk[kFirChunk];
+                    task_fir(sm.ol, omask, lane, base, pk);
+                    float* tt = sm.tt + (size_t)((j % kTT) * kSub + 8 * q) * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < kFirChunk; ++i) {
+                        // feed-forward part of dsp/true_peak.rs:349-354
+                        tt[(size_t)i * 32] = pk[i] > tp_ceil ? clampf((tp_ceil * 0.999f) / pk[i], 0.0f, 1.0f) : 1.0f;
+                        if (i < valid) max_in = fmaxf(max_in, pk[i]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], in_count);
+            }
         }
         // running maxima of the two oversamplers: order independent (python_api.rs:552-560) -> atomics
-        atomic_max_nonneg(&a.accum[s].peak_pre_tp, max_in);
+        if (in_count > 0) atomic_max_nonneg(&a.accum[s].peak_pre_tp, max_in);
         atomic_max_nonneg(&a.accum[s].peak_out_tp, max_out);
     }
     __syncthreads();

@@ -35,7 +35,7 @@ def test_chain_render_matches_oracle(sim, name, path, monkeypatch):
     """All kernel paths: one-thread-per-stream fused stages (large sweeps), the R/M split (few streams) with the
     limiter / true-peak tail as five stage kernels, and with the fused SM-local tail kernel (the default)."""
     monkeypatch.setenv("AFSIM_SPLIT", "1" if path == "fused" else "2")
-    monkeypatch.setenv("AFSIM_TAIL", "1" if path == "tail" else "0")
+    monkeypatch.setenv("AFSIM_TAIL", "2" if path == "tail" else "1")
     bands, overrides = CASES[name]
     settings = abi.make_settings(**overrides)
     m0, a0, _ = pyoracle.chain_render(X, FS, bands, settings, return_audio=True)

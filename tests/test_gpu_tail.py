@@ -1,6 +1,6 @@
 """The fused tail kernel (csrc/afsim_tail.cu: limiter -> true-peak limiter -> detector + output statistics in one
 SM-local, TMA-fed kernel) against the five split stage kernels it replaces: per sample the operations and their order
-are the same, so metrics AND rendered audio must be bit-identical (AFSIM_TAIL=0 keeps the split kernels), for every
+are the same, so metrics AND rendered audio must be bit-identical (AFSIM_TAIL=1 keeps the split kernels, 2 forces the tail), for every
 lookahead the shared-memory x ring supports, ragged lengths, partial sub-tiles and odd chunk sizes."""
 import numpy as np
 import pytest
@@ -37,9 +37,9 @@ def test_tail_is_bit_identical_to_the_split_kernels(sim, n, chunk, monkeypatch):
     monkeypatch.setenv("AFSIM_SPLIT", "2")
     passages = [1.4 * speech_like(n, seed=21 + k) for k in range(3)]
     cands = _cands()
-    monkeypatch.setenv("AFSIM_TAIL", "0")
-    want, want_audio = sim.chain_sweep(passages, FS, cands, return_audio=True)
     monkeypatch.setenv("AFSIM_TAIL", "1")
+    want, want_audio = sim.chain_sweep(passages, FS, cands, return_audio=True)
+    monkeypatch.setenv("AFSIM_TAIL", "2")
     got, got_audio = sim.chain_sweep(passages, FS, cands, return_audio=True)
     for i in range(len(cands) * 3):
         assert metric_mismatches(want[i], got[i]) == {}, i
@@ -47,7 +47,7 @@ def test_tail_is_bit_identical_to_the_split_kernels(sim, n, chunk, monkeypatch):
 
 
 def test_tail_matches_oracle_with_audio(sim, monkeypatch):
-    monkeypatch.setenv("AFSIM_TAIL", "1")
+    monkeypatch.setenv("AFSIM_TAIL", "2")
     x = 1.4 * speech_like(48000, seed=5)
     cands = _cands()
     for i in (2, 5, 9, 10):
@@ -63,11 +63,11 @@ def test_tail_on_a_large_fused_batch(sim, monkeypatch):
     n, n_streams = 12000, 20480
     cands = workloads.true_peak_candidates(1)
     out = {}
-    for mode in ("0", "2"):
+    for mode in ("1", "2"):
         monkeypatch.setenv("AFSIM_TAIL", mode)
         sweep = sim.prepare_synthetic_sweep(1, n_streams, n, FS, cands)
         sweep.launch()
         out[mode] = sweep.collect()
         sweep.release()
     for i in range(0, n_streams, 97):
-        assert metric_mismatches(out["0"][i], out["2"][i]) == {}, i
+        assert metric_mismatches(out["1"][i], out["2"][i]) == {}, i
