@@ -72,10 +72,10 @@ __device__ __forceinline__ void red_release_add(int* p, int v) {
 }
 // Waits until *p >= v.  A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls the CTA's sticky
 // error flag is set, every wait returns at once, and the launcher's error word reports it.
-__device__ __forceinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
+__device__ __noinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
     uint32_t spins = 0;
     while (ld_acquire(p) < v) {
-        if (++spins > 64) __nanosleep(40);
+        if (++spins > 8) __nanosleep(64);  // a few fast polls, then sleep: polling warps take issue slots from the working ones
         if (spins > kSpinLimit || (spins & 1023u) == 1023u) {
             if (spins > kSpinLimit) st_release(&ctl->error, 1);
             if (ld_acquire(&ctl->error)) return;
@@ -102,7 +102,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
+__device__ __noinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > kSpinLimit) st_release(&ctl->error, 1);
@@ -115,6 +115,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// per-block output level row (python_api.rs:54-56,570-575): one out-of-line instance of the sqrt / log10 code
+__device__ __noinline__ void store_output_row(float* dst, double block_sum, int block_len) {
+    const float rms = (float)sqrt(block_sum / (double)block_len);
+    *dst = lin_to_db_f32(rms);
 }
 
 struct TailSmem {
@@ -168,26 +174,30 @@ __device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane,
         const double peak = (double)w;
         tg[(size_t)j * 32 + lane] = peak > ceil_lin ? ceil_lin / peak : 1.0;
     };
+    // The suffix parts of the 32 windows are parked as floats in the slot itself (each thread its own column; the double
+    // written later covers the float): small rolled loops instead of a 32-register array -- the kernel's seven warps
+    // run four different code paths at once, and code size is what the instruction cache feels.
+    float* scratch = reinterpret_cast<float*>(tg);
     bool nan_seen = false;
     if (L >= G) {
-        float win[G];
         float run = 0.0f;
+#pragma unroll 4
         for (int m = -1; m >= G - L; --m) run = max_nan(run, x(m));
-#pragma unroll
+#pragma unroll 4
         for (int j = G - 1; j >= 0; --j) {  // suffix part of window j: the samples before the sub-tile, from j - L on
             run = max_nan(run, x(j - L));
-            win[j] = run;
+            scratch[(size_t)j * 64 + 2 * lane] = run;
         }
         float prefix = 0.0f;
-#pragma unroll
+#pragma unroll 2
         for (int j = 0; j < G; ++j) {       // prefix part: the sub-tile's own samples up to j; the target leaves at once
             prefix = max_nan(prefix, x(j));
-            const float w = max_nan(win[j], prefix);
+            const float w = max_nan(scratch[(size_t)j * 64 + 2 * lane], prefix);
             nan_seen = nan_seen || w != w;
             store_target(j, w);
         }
     } else {
-#pragma unroll 4
+#pragma unroll 1
         for (int j = 0; j < G; ++j) {
             float w = 0.0f;
             for (int m = j - L; m <= j; ++m) w = max_nan(w, x(m));
@@ -299,7 +309,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                 wait_ge(&ctl->done_tp_r, k + 1, ctl);
             }
             const double* tg = sm.tg + (size_t)(j % kTG) * kSub * 32 + lane;
-#pragma unroll
+#pragma unroll 1
             for (int u0 = 0; u0 < kSub; u0 += 8) {
                 double tgt[8];
                 float delayed[8];
@@ -357,7 +367,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             const int k = j - kCY + 1;  // last reader of the output ring rows about to be overwritten: FIR-OUT(k)
             if (k >= 0) wait_ge(&ctl->cnt_fir_out[k % kCY], 4 * (k / kCY + 1), ctl);
             const float* tt = sm.tt + (size_t)(j % kTT) * kSub * 32 + lane;
-#pragma unroll
+#pragma unroll 1
             for (int u0 = 0; u0 < kSub; u0 += 8) {
                 float pk[8], delayed[8];
 #pragma unroll
@@ -389,8 +399,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                             if (CHECK && clk.at_end(n_first + u)) {
                                 st.events += st.limited ? 1u : 0u;
                                 st.limited = false;
-                                const float rms = (float)sqrt(st.blk_out / (double)clk.block_len(n_first + u));
-                                rows_out[(size_t)clk.blk * stride] = lin_to_db_f32(rms);
+                                store_output_row(rows_out + (size_t)clk.blk * stride, st.blk_out, clk.block_len(n_first + u));
                                 st.blk_out = 0.0;
                                 clk.advance();
                             }
@@ -429,42 +438,43 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             if (lane == 0) st_release(&ctl->done_lim_m, j + 1);
         }
     } else {
-        // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: FIR-OUT units of sub-tile t - 2 (their input is
-        // ready first), then FIR-IN units of sub-tile t - 1.  warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1; warp 5: IN 3 + OUT 2;
-        // warp 6: OUT 3.
+        // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: the FIR-OUT unit of sub-tile t - 2 (its input
+        // is ready first), then the FIR-IN units of sub-tile t - 1.  warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1;
+        // warp 5: IN 3 + OUT 2; warp 6: OUT 3.  ONE instance of the unrolled FIR serves both kinds (code size).
         const int m = warp - 3;
         const int in_first = m == 0 ? 0 : (m == 3 ? 4 : m + 1), in_count = m == 0 ? 2 : (m == 3 ? 0 : 1);
-        const int out_unit = m;
         const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
         float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
         float max_in = 0.0f, max_out = 0.0f;
         for (int t = 1; t < n_sub + 2; ++t) {
-            if (t >= 2) {
-                const int j = t - 2, base = j * kSub + 8 * out_unit;
+#pragma unroll 1
+            for (int task = 0; task <= in_count; ++task) {  // task 0: the OUT unit; tasks 1..: the IN units
+                const bool is_out = task == 0;
+                const int j = is_out ? t - 2 : t - 1;
+                if (j < 0 || j >= n_sub) continue;
+                const int q = is_out ? m : in_first + task - 1;
+                const int base = j * kSub + 8 * q;
                 const int valid = ck.len - base;
-                wait_ge(&ctl->done_tp_r, j + 1, ctl);
+                if (is_out) {
+                    wait_ge(&ctl->done_tp_r, j + 1, ctl);
+                } else if (task == 1) {
+                    wait_ge(&ctl->done_lim_r, j + 1, ctl);
+                    if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);  // the slot's previous targets were consumed
+                }
                 float pk[kFirChunk];
-                task_fir(sm.ys, ymask, lane, base, pk);
-#pragma unroll
-                for (int i = 0; i < kFirChunk; ++i)
-                    if (i < valid) max_out = fmaxf(max_out, pk[i]);
-                if (audio) {
+                task_fir(is_out ? sm.ys : sm.ol, is_out ? ymask : omask, lane, base, pk);
+                if (is_out) {
 #pragma unroll
                     for (int i = 0; i < kFirChunk; ++i)
-                        if (i < valid) audio[base + i] = sm.ys[(size_t)((base + i) & ymask) * 32 + lane];
-                }
-                __syncwarp();
-                if (lane == 0) red_release_add(&ctl->cnt_fir_out[j % kCY], 1);
-            }
-            if (t - 1 < n_sub && in_count > 0) {
-                const int j = t - 1;
-                wait_ge(&ctl->done_lim_r, j + 1, ctl);
-                if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);  // the slot's previous targets were consumed
-                for (int q = in_first; q < in_first + in_count; ++q) {
-                    const int base = j * kSub + 8 * q;
-                    const int valid = ck.len - base;
-                    float pk[kFirChunk];
-                    task_fir(sm.ol, omask, lane, base, pk);
+                        if (i < valid) max_out = fmaxf(max_out, pk[i]);
+                    if (audio) {
+#pragma unroll
+                        for (int i = 0; i < kFirChunk; ++i)
+                            if (i < valid) audio[base + i] = sm.ys[(size_t)((base + i) & ymask) * 32 + lane];
+                    }
+                    __syncwarp();
+                    if (lane == 0) red_release_add(&ctl->cnt_fir_out[j % kCY], 1);
+                } else {
                     float* tt = sm.tt + (size_t)((j % kTT) * kSub + 8 * q) * 32 + lane;
 #pragma unroll
                     for (int i = 0; i < kFirChunk; ++i) {
@@ -472,9 +482,9 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                         tt[(size_t)i * 32] = pk[i] > tp_ceil ? clampf((tp_ceil * 0.999f) / pk[i], 0.0f, 1.0f) : 1.0f;
                         if (i < valid) max_in = fmaxf(max_in, pk[i]);
                     }
+                    __syncwarp();
+                    if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], 1);
                 }
-                __syncwarp();
-                if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], in_count);
             }
         }
         // running maxima of the two oversamplers: order independent (python_api.rs:552-560) -> atomics
