@@ -433,6 +433,12 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         a.eq_default = d_eq_default;
         a.cleanup = d_cleanup;
         a.metrics = sweep->d_metrics;
+        {  // tuning knobs are read HERE, once per sweep (never cached across sweeps: tests flip them between calls)
+            const char* v = std::getenv("AFSIM_MAP_BLOCKS_PER_SM");
+            a.map_blocks_per_sm = v && *v ? std::atoi(v) : 0;
+            v = std::getenv("AFSIM_FIR_BLOCKS_PER_SM");
+            a.fir_blocks_per_sm = v && *v ? std::atoi(v) : -1;
+        }
 
         // chunking: a multiple of 8 (true-peak FIR groups) and of the compressor micro-tile, long
         // enough to hold the biquad crossfade and the limiter lookback

@@ -438,14 +438,6 @@ cudaError_t launch_input_true_peak(const BatchArgs& a, const ChunkArgs& ck, cuda
     return cudaGetLastError();
 }
 
-static int env_blocks_per_sm() {
-    const char* v = getenv("AFSIM_MAP_BLOCKS_PER_SM");
-    return v && *v ? atoi(v) : 0;
-}
-static int env_fir_blocks_per_sm() {
-    const char* v = getenv("AFSIM_FIR_BLOCKS_PER_SM");
-    return v && *v ? atoi(v) : -1;
-}
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -473,14 +465,14 @@ cudaError_t launch_split(SplitOp op, const BatchArgs& a, const ChunkArgs& ck, cu
     // Map kernels are FP64 / FP32 issue bound and need only a few warps per SM to saturate the pipe; capping
     // the grid (blocks loop over sample groups) leaves issue slots for the co-resident serial kernels of the
     // other wavefront stages.  AFSIM_MAP_BLOCKS_PER_SM = 0 removes the cap.
-    static const int blocks_per_sm = env_blocks_per_sm();
+    const int blocks_per_sm = a.map_blocks_per_sm;  // read with the other knobs when the sweep is built (afsim_api.cu)
     const unsigned gx = (unsigned)((a.n_streams + 31) / 32);
     unsigned gy = (unsigned)((n_groups + kMapWarps - 1) / kMapWarps);
     // The FP32 FIR maps and the limiter window map have so much instruction-level parallelism per warp that a few
     // resident warps saturate the FMA issue; every further resident warp only takes issue slots from the serial
     // kernels' warps on the same scheduler (round-robin among ready warps).  Their grids are capped (blocks loop
     // over sample groups).  AFSIM_FIR_BLOCKS_PER_SM overrides the cap (0 = none).
-    static const int fir_blocks_env = env_fir_blocks_per_sm();
+    const int fir_blocks_env = a.fir_blocks_per_sm;
     const bool fir_like = op == SP_TP_FIR_IN || op == SP_TP_FIR_OUT || op == SP_LIM_M;
     int cap_per_sm = blocks_per_sm;
     if (fir_like) cap_per_sm = fir_blocks_env >= 0 ? fir_blocks_env : kFirBlocksPerSm;

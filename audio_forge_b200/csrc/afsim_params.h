@@ -216,6 +216,8 @@ struct BatchArgs {
     int input_stage;              // AfInputStage
     int stage_inputs;             // 1: serial kernels stage their inputs through shared memory (few-stream batches)
     uint32_t structure;           // StructureFlag
+    int map_blocks_per_sm;        // AFSIM_MAP_BLOCKS_PER_SM: grid cap of the map kernels (0 = none)
+    int fir_blocks_per_sm;        // AFSIM_FIR_BLOCKS_PER_SM: grid cap of the FIR / limiter-window maps (-1 = the default cap)
 };
 
 }  // namespace afsim

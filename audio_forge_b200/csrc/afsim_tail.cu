@@ -46,7 +46,7 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 22;
+constexpr uint32_t kSpinLimit = 1u << 19;  // x <= 1.6 us: about a second
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
@@ -70,13 +70,17 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 __device__ __forceinline__ void red_release_add(int* p, int v) {
     asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-// Waits until *p >= v.  A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls the CTA's sticky
-// error flag is set, every wait returns at once, and the launcher's error word reports it.
+// Waits until *p >= v.  A pipeline step takes microseconds, so a waiting warp backs off fast (100 ns doubling to 1.6 us):
+// with 64 ns naps the polls of the waiting warps were 45 % of all instructions the kernel issued (ncu, r02 pass D).
+// A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls the CTA's sticky error flag is set, every
+// wait returns at once, and the launcher's error word reports it.
 __device__ __noinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
-    uint32_t spins = 0;
+    if (ld_acquire(p) >= v) return;
+    uint32_t spins = 0, nap = 100;
     while (ld_acquire(p) < v) {
-        if (++spins > 8) __nanosleep(64);  // a few fast polls, then sleep: polling warps take issue slots from the working ones
-        if (spins > kSpinLimit || (spins & 1023u) == 1023u) {
+        __nanosleep(nap);
+        if (nap < 1600) nap <<= 1;
+        if (++spins > kSpinLimit || (spins & 63u) == 63u) {
             if (spins > kSpinLimit) st_release(&ctl->error, 1);
             if (ld_acquire(&ctl->error)) return;
         }
@@ -104,9 +108,9 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 }
 __device__ __noinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity)) {  // try_wait itself suspends the warp in hardware for a while
         if (++spins > kSpinLimit) st_release(&ctl->error, 1);
-        if ((spins & 255u) == 255u && ld_acquire(&ctl->error)) return;
+        if ((spins & 63u) == 63u && ld_acquire(&ctl->error)) return;
     }
 }
 // 2-D tile of the [ring_rows][S_pad] f32 ring: c0 = first stream (column), c1 = first ring row
