@@ -46,7 +46,7 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 19;  // x <= 1.6 us: about a second
+constexpr uint32_t kSpinLimit = 1u << 21;  // x 256 ns: about half a second
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
@@ -70,17 +70,15 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 __device__ __forceinline__ void red_release_add(int* p, int v) {
     asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-// Waits until *p >= v.  A pipeline step takes microseconds, so a waiting warp backs off fast (100 ns doubling to 1.6 us):
-// with 64 ns naps the polls of the waiting warps were 45 % of all instructions the kernel issued (ncu, r02 pass D).
-// A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls the CTA's sticky error flag is set, every
-// wait returns at once, and the launcher's error word reports it.
+// Waits until *p >= v: a few polls, then short naps (a napping warp costs no issue slots, but every nanosecond of a nap
+// is latency on a hand-off: 64 ns naps alone made the polls 45 % of all instructions issued, 1.6 us naps made the
+// kernel 30 % slower -- ncu, r02 passes D / E).  A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls
+// the CTA's sticky error flag is set, every wait returns at once, and the launcher's error word reports it.
 __device__ __noinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
-    if (ld_acquire(p) >= v) return;
-    uint32_t spins = 0, nap = 100;
+    uint32_t spins = 0;
     while (ld_acquire(p) < v) {
-        __nanosleep(nap);
-        if (nap < 1600) nap <<= 1;
-        if (++spins > kSpinLimit || (spins & 63u) == 63u) {
+        if (++spins > 2) __nanosleep(spins < 32 ? 128 : 256);
+        if (spins > kSpinLimit || (spins & 63u) == 63u) {
             if (spins > kSpinLimit) st_release(&ctl->error, 1);
             if (ld_acquire(&ctl->error)) return;
         }
@@ -442,26 +440,28 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             if (lane == 0) st_release(&ctl->done_lim_m, j + 1);
         }
     } else {
-        // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: the FIR-OUT unit of sub-tile t - 2 (its input
-        // is ready first), then the FIR-IN units of sub-tile t - 1.  warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1;
-        // warp 5: IN 3 + OUT 2; warp 6: OUT 3.  ONE instance of the unrolled FIR serves both kinds (code size).
+        // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: the FIR-IN units of sub-tile t - 1 (they feed
+        // the serial TP-R warp: first), then the FIR-OUT unit of sub-tile t - 3 -- TWO steps behind the FIR-IN of the same
+        // sub-tile, so that TP-R has a whole step to turn its targets into output rows and no FIR warp ever waits for it.
+        // warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1; warp 5: IN 3 + OUT 2; warp 6: OUT 3.  ONE instance of the unrolled
+        // FIR serves both kinds (code size).
         const int m = warp - 3;
         const int in_first = m == 0 ? 0 : (m == 3 ? 4 : m + 1), in_count = m == 0 ? 2 : (m == 3 ? 0 : 1);
         const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
         float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
         float max_in = 0.0f, max_out = 0.0f;
-        for (int t = 1; t < n_sub + 2; ++t) {
+        for (int t = 1; t < n_sub + 3; ++t) {
 #pragma unroll 1
-            for (int task = 0; task <= in_count; ++task) {  // task 0: the OUT unit; tasks 1..: the IN units
-                const bool is_out = task == 0;
-                const int j = is_out ? t - 2 : t - 1;
+            for (int task = 0; task <= in_count; ++task) {  // tasks 0 .. in_count - 1: the IN units; the last one: the OUT unit
+                const bool is_out = task == in_count;
+                const int j = is_out ? t - 3 : t - 1;
                 if (j < 0 || j >= n_sub) continue;
-                const int q = is_out ? m : in_first + task - 1;
+                const int q = is_out ? m : in_first + task;
                 const int base = j * kSub + 8 * q;
                 const int valid = ck.len - base;
                 if (is_out) {
                     wait_ge(&ctl->done_tp_r, j + 1, ctl);
-                } else if (task == 1) {
+                } else if (task == 0) {
                     wait_ge(&ctl->done_lim_r, j + 1, ctl);
                     if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);  // the slot's previous targets were consumed
                 }
