@@ -17,8 +17,8 @@
 //   serial warps    LIM-R (lane = stream: g <- t < g ? t : r g + (1 - r) t, delayed sample x gain, clamp) and
 //                   TP-R (the same recurrence in f32, 20-sample delay, output statistics, per-block rows)
 //
-// Stages are linked by release / acquire counters in shared memory (in-order serial warps publish "sub-tiles done",
-// map tasks count arrivals per ring slot), the x ring by mbarriers.  Per sample every operation and its order are
+// Stages are linked by mbarriers in shared memory (one phase per finished sub-tile; waiting warps are suspended by the
+// hardware), the x ring by the TMA's complete_tx mbarriers.  Per sample every operation and its order are
 // those of the split kernels (afsim_split.h) -- the results are bit-identical to them and to the fused stages
 // (tests/test_gpu_tail.py) -- only the hand-off medium changes.  Nothing but the statistics (and the audio, when the
 // caller asked for it) leaves the SM: DRAM traffic is the 4 B read of the input per stream-sample.
@@ -46,15 +46,19 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 21;  // x 256 ns: about half a second
+constexpr uint32_t kSpinLimit = 1u << 16;  // failed try_waits (each a hardware time slice) before the watchdog fires
 
 struct TailCtl {  // shared-memory control block
-    unsigned long long full[kMaxCX];  // mbarriers: x sub-tile landed
-    int done_lim_m;   // serial / single-warp stages: sub-tiles finished, in order
-    int cnt_fir_in[kTT];  // map tasks: FIR units arrived, per ring slot (4 per use)
-    int cnt_fir_out[kCY];
-    int done_lim_r;
-    int done_tp_r;
+    unsigned long long full[kMaxCX];  // x sub-tile landed (TMA complete_tx)
+    // stage hand-offs: barrier [j & 3] completes its (j >> 2)-th phase when the stage has finished sub-tile j.  Waiting is
+    // mbarrier.try_wait -- the warp is suspended by the hardware, not polling: with flag polling the polls of the waiting
+    // warps were 45 % of all instructions this kernel issued (ncu, r02 passes D - F).  Depth 4 is enough: no stage can
+    // finish sub-tile j + 4 before every waiter for its sub-tile j has passed (each is gated by a ring of <= 4 sub-tiles).
+    unsigned long long lim_m[4];    // 1 arrival  (LIM-M warp)      -> LIM-R
+    unsigned long long lim_r[4];    // 1 arrival  (LIM-R warp)      -> FIR-IN warps, LIM-M (target slot free)
+    unsigned long long fir_in[4];   // 3 arrivals (warps 3, 4, 5)   -> TP-R, LIM-R (limiter-output rows free)
+    unsigned long long tp_r[4];     // 1 arrival  (TP-R warp)       -> FIR-OUT warps, FIR-IN (target slot free), LIM-R
+    unsigned long long fir_out[4];  // 4 arrivals (warps 3 .. 6)    -> TP-R (output rows free)
     int error;
 };
 
@@ -66,23 +70,6 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-    asm volatile("red.release.cta.shared.add.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-// Waits until *p >= v: a few polls, then short naps (a napping warp costs no issue slots, but every nanosecond of a nap
-// is latency on a hand-off: 64 ns naps alone made the polls 45 % of all instructions issued, 1.6 us naps made the
-// kernel 30 % slower -- ncu, r02 passes D / E).  A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit polls
-// the CTA's sticky error flag is set, every wait returns at once, and the launcher's error word reports it.
-__device__ __noinline__ void wait_ge(const int* p, int v, TailCtl* ctl) {
-    uint32_t spins = 0;
-    while (ld_acquire(p) < v) {
-        if (++spins > 2) __nanosleep(spins < 32 ? 128 : 256);
-        if (spins > kSpinLimit || (spins & 63u) == 63u) {
-            if (spins > kSpinLimit) st_release(&ctl->error, 1);
-            if (ld_acquire(&ctl->error)) return;
-        }
-    }
 }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -104,13 +91,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
         : "memory");
     return ok != 0;
 }
+// A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit failed try_waits (each suspends the warp for a
+// hardware time slice) the CTA's sticky error flag is set, every wait returns at once, and the launcher's error word reports it.
 __device__ __noinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {  // try_wait itself suspends the warp in hardware for a while
+    while (!mbar_try_wait(bar, parity)) {
         if (++spins > kSpinLimit) st_release(&ctl->error, 1);
-        if ((spins & 63u) == 63u && ld_acquire(&ctl->error)) return;
+        if ((spins & 15u) == 15u && ld_acquire(&ctl->error)) return;
     }
 }
+// "stage finished sub-tile j": wait for / signal phase j >> 2 of barrier j & 3
+__device__ __forceinline__ void wait_done(unsigned long long* bars, int j, TailCtl* ctl) {
+    mbar_wait(&bars[j & 3], (uint32_t)((j >> 2) & 1), ctl);
+}
+__device__ __forceinline__ void signal_done(unsigned long long* bars, int j) { mbar_arrive(&bars[j & 3]); }
 // 2-D tile of the [ring_rows][S_pad] f32 ring: c0 = first stream (column), c1 = first ring row
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
     asm volatile(
@@ -252,11 +246,13 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
     // ---- init: barriers, counters, histories -----------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int i = 0; i < cx; ++i) mbar_init(&ctl->full[i], 1);
-        for (int i = 0; i < kTT; ++i) ctl->cnt_fir_in[i] = 0;
-        for (int i = 0; i < kCY; ++i) ctl->cnt_fir_out[i] = 0;
-        ctl->done_lim_m = 0;
-        ctl->done_lim_r = 0;
-        ctl->done_tp_r = 0;
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&ctl->lim_m[i], 1);
+            mbar_init(&ctl->lim_r[i], 1);
+            mbar_init(&ctl->fir_in[i], 3);
+            mbar_init(&ctl->tp_r[i], 1);
+            mbar_init(&ctl->fir_out[i], 4);
+        }
         ctl->error = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -304,11 +300,11 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         double g = st.g, min_g = st.min_g;
         for (int j = 0; j < n_sub; ++j) {
             const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
-            wait_ge(&ctl->done_lim_m, j + 1, ctl);
+            wait_done(ctl->lim_m, j, ctl);
             const int k = j - kCO + 1;  // the ring rows about to be overwritten were last read by FIR-IN(k) and TP-R(k)
             if (k >= 0) {
-                wait_ge(&ctl->cnt_fir_in[k % kTT], 4 * (k / kTT + 1), ctl);
-                wait_ge(&ctl->done_tp_r, k + 1, ctl);
+                wait_done(ctl->fir_in, k, ctl);
+                wait_done(ctl->tp_r, k, ctl);
             }
             const double* tg = sm.tg + (size_t)(j % kTG) * kSub * 32 + lane;
 #pragma unroll 1
@@ -336,7 +332,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             }
             __syncwarp();
             if (lane == 0) {
-                st_release(&ctl->done_lim_r, j + 1);
+                signal_done(ctl->lim_r, j);
                 const int jn = j + cx - Lt;  // its slot held sub-tile j - Lt: nobody needs that any more
                 if (jn < n_sub) load_subtile(jn);
             }
@@ -365,9 +361,9 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         float* rows_out = a.rows + (size_t)1 * a.n_rows * stride + s;
         for (int j = 0; j < n_sub; ++j) {
             const int valid = ck.len - j * kSub < kSub ? ck.len - j * kSub : kSub;
-            wait_ge(&ctl->cnt_fir_in[j % kTT], 4 * (j / kTT + 1), ctl);
+            wait_done(ctl->fir_in, j, ctl);
             const int k = j - kCY + 1;  // last reader of the output ring rows about to be overwritten: FIR-OUT(k)
-            if (k >= 0) wait_ge(&ctl->cnt_fir_out[k % kCY], 4 * (k / kCY + 1), ctl);
+            if (k >= 0) wait_done(ctl->fir_out, k, ctl);
             const float* tt = sm.tt + (size_t)(j % kTT) * kSub * 32 + lane;
 #pragma unroll 1
             for (int u0 = 0; u0 < kSub; u0 += 8) {
@@ -414,7 +410,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                     walk(TileFull());
             }
             __syncwarp();
-            if (lane == 0) st_release(&ctl->done_tp_r, j + 1);
+            if (lane == 0) signal_done(ctl->tp_r, j);
         }
         if (ck.n0 + ck.len >= a.n_samples) {
             StreamAccum& acc = a.accum[s];
@@ -434,10 +430,10 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             if (j == 0)
                 for (int h = -Lt; h < 0; ++h) mbar_wait(&ctl->full[x_slot(h)], x_parity(h), ctl);
             mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);
-            if (j - kTG >= 0) wait_ge(&ctl->done_lim_r, j - kTG + 1, ctl);  // the slot's previous targets were consumed
+            if (j - kTG >= 0) wait_done(ctl->lim_r, j - kTG, ctl);  // the slot's previous targets were consumed
             task_lim_m(sm.xs, xmask, lane, j * kSub + xoff, L, l_ceil, sm.tg + (size_t)(j % kTG) * kSub * 32);
             __syncwarp();
-            if (lane == 0) st_release(&ctl->done_lim_m, j + 1);
+            if (lane == 0) signal_done(ctl->lim_m, j);
         }
     } else {
         // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: the FIR-IN units of sub-tile t - 1 (they feed
@@ -460,10 +456,10 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                 const int base = j * kSub + 8 * q;
                 const int valid = ck.len - base;
                 if (is_out) {
-                    wait_ge(&ctl->done_tp_r, j + 1, ctl);
+                    wait_done(ctl->tp_r, j, ctl);
                 } else if (task == 0) {
-                    wait_ge(&ctl->done_lim_r, j + 1, ctl);
-                    if (j - kTT >= 0) wait_ge(&ctl->done_tp_r, j - kTT + 1, ctl);  // the slot's previous targets were consumed
+                    wait_done(ctl->lim_r, j, ctl);
+                    if (j - kTT >= 0) wait_done(ctl->tp_r, j - kTT, ctl);  // the slot's previous targets were consumed
                 }
                 float pk[kFirChunk];
                 task_fir(is_out ? sm.ys : sm.ol, is_out ? ymask : omask, lane, base, pk);
@@ -477,7 +473,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                             if (i < valid) audio[base + i] = sm.ys[(size_t)((base + i) & ymask) * 32 + lane];
                     }
                     __syncwarp();
-                    if (lane == 0) red_release_add(&ctl->cnt_fir_out[j % kCY], 1);
+                    if (lane == 0) signal_done(ctl->fir_out, j);
                 } else {
                     float* tt = sm.tt + (size_t)((j % kTT) * kSub + 8 * q) * 32 + lane;
 #pragma unroll
@@ -487,7 +483,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
                         if (i < valid) max_in = fmaxf(max_in, pk[i]);
                     }
                     __syncwarp();
-                    if (lane == 0) red_release_add(&ctl->cnt_fir_in[j % kTT], 1);
+                    if (lane == 0 && task == in_count - 1) signal_done(ctl->fir_in, j);  // one arrival per warp, after its last IN unit
                 }
             }
         }
