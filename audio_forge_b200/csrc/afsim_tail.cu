@@ -46,7 +46,7 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 16;  // failed try_waits (each a hardware time slice) before the watchdog fires
+constexpr uint32_t kSpinLimit = 1u << 17;  // failed try_waits (each up to a 4 us hardware nap) before the watchdog fires
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // x sub-tile landed (TMA complete_tx)
@@ -84,10 +84,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // %3: suspend-time hint (ns): the hardware parks the
+        "selp.u32 %0, 1, 0, p;\n\t}"                                      // warp until the phase completes or the time is up
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
         : "memory");
     return ok != 0;
 }
