@@ -46,7 +46,7 @@ constexpr int kCO = 4;    // limiter-output ring, sub-tiles (one of them is hist
 constexpr int kTT = 3;    // true-peak target slots
 constexpr int kCY = 4;    // true-peak limiter output ring, sub-tiles
 constexpr int kMaxCX = 32;
-constexpr uint32_t kSpinLimit = 1u << 17;  // failed try_waits (each up to a 4 us hardware nap) before the watchdog fires
+constexpr uint32_t kSpinLimit = 1u << 21;  // failed try_waits (~90 ns each: a fifth of a second) before the watchdog fires
 
 struct TailCtl {  // shared-memory control block
     unsigned long long full[kMaxCX];  // x sub-tile landed (TMA complete_tx)
@@ -56,18 +56,13 @@ struct TailCtl {  // shared-memory control block
     // finish sub-tile j + 4 before every waiter for its sub-tile j has passed (each is gated by a ring of <= 4 sub-tiles).
     unsigned long long lim_m[4];    // 1 arrival  (LIM-M warp)      -> LIM-R
     unsigned long long lim_r[4];    // 1 arrival  (LIM-R warp)      -> FIR-IN warps, LIM-M (target slot free)
-    unsigned long long fir_in[4];   // 3 arrivals (warps 3, 4, 5)   -> TP-R, LIM-R (limiter-output rows free)
+    unsigned long long fir_in[4];   // 4 arrivals (warps 3 .. 6)    -> TP-R, LIM-R (limiter-output rows free)
     unsigned long long tp_r[4];     // 1 arrival  (TP-R warp)       -> FIR-OUT warps, FIR-IN (target slot free), LIM-R
     unsigned long long fir_out[4];  // 4 arrivals (warps 3 .. 6)    -> TP-R (output rows free)
     int error;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
@@ -80,25 +75,27 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"  // %3: suspend-time hint (ns): the hardware parks the
-        "selp.u32 %0, 1, 0, p;\n\t}"                                      // warp until the phase completes or the time is up
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
-        : "memory");
-    return ok != 0;
-}
-// A stuck pipeline (a bug) must never hang the GPU: after kSpinLimit failed try_waits (each suspends the warp for a
-// hardware time slice) the CTA's sticky error flag is set, every wait returns at once, and the launcher's error word reports it.
+// Waits for the phase with the given parity.  The loop is a handful of instructions per failed try (the hardware parks
+// the warp for a short time slice per try_wait, ~90 ns measured, whatever the hint says -- so tries are frequent, and a
+// 18-instruction C++ loop around them was 41 % of all instructions issued).  A stuck pipeline (a bug) must never hang the
+// GPU: after kSpinLimit failed tries the CTA's sticky error flag is set and every later wait gives up at once.
 __device__ __noinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, TailCtl* ctl) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) st_release(&ctl->error, 1);
-        if ((spins & 15u) == 15u && ld_acquire(&ctl->error)) return;
-    }
+    uint32_t tries;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n"
+        "TAIL_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra TAIL_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, %4;\n\t"
+        "@p bra TAIL_WAIT_LOOP;\n"
+        "TAIL_WAIT_DONE:\n\t"
+        "mov.u32 %0, n;\n\t}"
+        : "=r"(tries)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u), "r"(ctl->error ? 1u : kSpinLimit)
+        : "memory");
+    if (tries >= kSpinLimit) st_release(&ctl->error, 1);
 }
 // "stage finished sub-tile j": wait for / signal phase j >> 2 of barrier j & 3
 __device__ __forceinline__ void wait_done(unsigned long long* bars, int j, TailCtl* ctl) {
@@ -185,12 +182,12 @@ __device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane,
             scratch[(size_t)j * 64 + 2 * lane] = run;
         }
         float prefix = 0.0f;
-#pragma unroll 2
-        for (int j = 0; j < G; ++j) {       // prefix part: the sub-tile's own samples up to j; the target leaves at once
+#pragma unroll 4
+        for (int j = 0; j < G; ++j) {       // prefix part: the sub-tile's own samples up to j
             prefix = max_nan(prefix, x(j));
             const float w = max_nan(scratch[(size_t)j * 64 + 2 * lane], prefix);
             nan_seen = nan_seen || w != w;
-            store_target(j, w);
+            scratch[(size_t)j * 64 + 2 * lane] = w;
         }
     } else {
 #pragma unroll 1
@@ -198,8 +195,18 @@ __device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane,
             float w = 0.0f;
             for (int m = j - L; m <= j; ++m) w = max_nan(w, x(m));
             nan_seen = nan_seen || w != w;
-            store_target(j, w);
+            scratch[(size_t)j * 64 + 2 * lane] = w;
         }
+    }
+    // the f64 divisions, eight independent ones in flight: one division is a ~15-deep dependent FP64 chain, and this warp
+    // is alone on its role -- rolled two at a time it was the slowest stage of the whole pipeline (84 % busy, ncu pass H)
+#pragma unroll 1
+    for (int j0 = 0; j0 < G; j0 += 8) {
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = scratch[(size_t)(j0 + i) * 64 + 2 * lane];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) store_target(j0 + i, w[i]);
     }
     if (nan_seen) {  // rare: a NaN inside a lookback -- every row again with the reference queue's semantics
 #pragma unroll 1
@@ -223,8 +230,7 @@ __device__ __forceinline__ void task_fir(const float* ring, int mask, int lane, 
 
 // One CTA = 32 streams x one chunk, 7 warps:
 //   warp 0  LIM-R + TMA producer      warp 1  TP-R + output statistics      warp 2  LIM-M (a whole sub-tile per step)
-//   warps 3..6  FIR units of 8 rows (4 of FIR-IN and 4 of FIR-OUT per step), spread 3 / 2 / 2 / 1 so that the warp
-//   schedulers that also host a serial warp get less map work (warp w issues on scheduler w mod 4)
+//   warps 3..6  FIR units of 8 rows: one FIR-IN and one FIR-OUT unit per warp and step
 __global__ void __launch_bounds__(kTailThreads, 2)
 k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int cx, int* err_out) {
     if (err_out && *reinterpret_cast<volatile int*>(err_out)) return;  // an earlier launch's watchdog fired: do not pile up waits
@@ -249,7 +255,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         for (int i = 0; i < 4; ++i) {
             mbar_init(&ctl->lim_m[i], 1);
             mbar_init(&ctl->lim_r[i], 1);
-            mbar_init(&ctl->fir_in[i], 3);
+            mbar_init(&ctl->fir_in[i], 4);
             mbar_init(&ctl->tp_r[i], 1);
             mbar_init(&ctl->fir_out[i], 4);
         }
@@ -439,10 +445,10 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         // ---- FIR units: unit q = rows [8q, 8q + 8) of a sub-tile.  Per step t: the FIR-IN units of sub-tile t - 1 (they feed
         // the serial TP-R warp: first), then the FIR-OUT unit of sub-tile t - 3 -- TWO steps behind the FIR-IN of the same
         // sub-tile, so that TP-R has a whole step to turn its targets into output rows and no FIR warp ever waits for it.
-        // warp 3: IN 0,1 + OUT 0; warp 4: IN 2 + OUT 1; warp 5: IN 3 + OUT 2; warp 6: OUT 3.  ONE instance of the unrolled
-        // FIR serves both kinds (code size).
+        // Warp 3 + m owns unit m of both kinds (the serial warps issue so little that the schedulers hosting them need no
+        // relief: a 3 / 2 / 2 / 1 split only made warp 3 the straggler).  ONE instance of the unrolled FIR serves both kinds.
         const int m = warp - 3;
-        const int in_first = m == 0 ? 0 : (m == 3 ? 4 : m + 1), in_count = m == 0 ? 2 : (m == 3 ? 0 : 1);
+        const int in_first = m, in_count = 1;  // one FIR-IN and one FIR-OUT unit per warp and step
         const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
         float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;
         float max_in = 0.0f, max_out = 0.0f;
