@@ -54,7 +54,7 @@ struct TailCtl {  // shared-memory control block
     // mbarrier.try_wait -- the warp is suspended by the hardware, not polling: with flag polling the polls of the waiting
     // warps were 45 % of all instructions this kernel issued (ncu, r02 passes D - F).  Depth 4 is enough: no stage can
     // finish sub-tile j + 4 before every waiter for its sub-tile j has passed (each is gated by a ring of <= 4 sub-tiles).
-    unsigned long long lim_m[4];    // 1 arrival  (LIM-M warp)      -> LIM-R
+    unsigned long long lim_m[4];    // 2 arrivals (LIM-M warps 2, 7) -> LIM-R
     unsigned long long lim_r[4];    // 1 arrival  (LIM-R warp)      -> FIR-IN warps, LIM-M (target slot free)
     unsigned long long fir_in[4];   // 4 arrivals (warps 3 .. 6)    -> TP-R, LIM-R (limiter-output rows free)
     unsigned long long tp_r[4];     // 1 arrival  (TP-R warp)       -> FIR-OUT warps, FIR-IN (target slot free), LIM-R
@@ -150,18 +150,18 @@ __device__ __forceinline__ TailSmem carve(int cx) {
 
 // ---- map tasks (lane = stream) ------------------------------------------------------------------------------------------
 
-// LIM-M, one warp per sub-tile: windows [r - L, r] of |x| for the 32 rows r = base .. base + 31 (dsp/limiter.rs:253-262;
-// max is order independent, so the part the 32 windows share is scanned once: L + 32 loads for 32 outputs), then the
-// target gain in f64.  The scan runs on NaN-PROPAGATING maxima (max.NaN.f32): without a NaN in the span they equal
+// LIM-M, G rows per task: windows [r - L, r] of |x| for the rows r = base .. base + G - 1 (dsp/limiter.rs:253-262; max is
+// order independent, so the part the G windows share is scanned once: L + G loads for G outputs), then the target gain
+// in f64.  The scan runs on NaN-PROPAGATING maxima (max.NaN.f32): without a NaN in the span they equal
 // fmaxf bit for bit, and a NaN result sends the sub-tile to the reference queue's NaN semantics (nan_aware_window).
 __device__ __forceinline__ float max_nan(float a, float b) {
     float r;
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+template <int G>
 __device__ __forceinline__ void task_lim_m(const float* xs, int xmask, int lane, int base, int L, double ceil_lin,
-                                           double* tg /* row 0 of the sub-tile's slot */) {
-    constexpr int G = kSub;
+                                           double* tg /* the slot row of the task's first row */) {
     auto x = [&](int m) { return fabsf(xs[(size_t)((base + m) & xmask) * 32 + lane]); };
     auto store_target = [&](int j, float w) {
         const double peak = (double)w;
@@ -228,8 +228,8 @@ __device__ __forceinline__ void task_fir(const float* ring, int mask, int lane, 
 
 }  // namespace
 
-// One CTA = 32 streams x one chunk, 7 warps:
-//   warp 0  LIM-R + TMA producer      warp 1  TP-R + output statistics      warp 2  LIM-M (a whole sub-tile per step)
+// One CTA = 32 streams x one chunk, 8 warps:
+//   warp 0  LIM-R + TMA producer      warp 1  TP-R + output statistics      warps 2, 7  LIM-M (16 rows of a sub-tile each)
 //   warps 3..6  FIR units of 8 rows: one FIR-IN and one FIR-OUT unit per warp and step
 __global__ void __launch_bounds__(kTailThreads, 2)
 k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int cx, int* err_out) {
@@ -253,7 +253,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
     if (threadIdx.x == 0) {
         for (int i = 0; i < cx; ++i) mbar_init(&ctl->full[i], 1);
         for (int i = 0; i < 4; ++i) {
-            mbar_init(&ctl->lim_m[i], 1);
+            mbar_init(&ctl->lim_m[i], 2);
             mbar_init(&ctl->lim_r[i], 1);
             mbar_init(&ctl->fir_in[i], 4);
             mbar_init(&ctl->tp_r[i], 1);
@@ -429,15 +429,17 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
             StateIO<true> io{a.st_tp + s, stride};
             st.sync(io);
         }
-    } else if (warp == 2) {
-        // ---- LIM-M: one sub-tile per step ---------------------------------------------------------------------------------------
+    } else if (warp == 2 || warp == 7) {
+        // ---- LIM-M: two warps, 16 rows of every sub-tile each (alone this role was the slowest stage: 80 % busy) -----------
+        const int half = warp == 2 ? 0 : 1;
         const double l_ceil = a.map_tab[(size_t)MT_L_CEIL * stride + s];
         for (int j = 0; j < n_sub; ++j) {
             if (j == 0)
                 for (int h = -Lt; h < 0; ++h) mbar_wait(&ctl->full[x_slot(h)], x_parity(h), ctl);
             mbar_wait(&ctl->full[x_slot(j)], x_parity(j), ctl);
             if (j - kTG >= 0) wait_done(ctl->lim_r, j - kTG, ctl);  // the slot's previous targets were consumed
-            task_lim_m(sm.xs, xmask, lane, j * kSub + xoff, L, l_ceil, sm.tg + (size_t)(j % kTG) * kSub * 32);
+            task_lim_m<kSub / 2>(sm.xs, xmask, lane, j * kSub + 16 * half + xoff, L, l_ceil,
+                                 sm.tg + (size_t)((j % kTG) * kSub + 16 * half) * 32);
             __syncwarp();
             if (lane == 0) signal_done(ctl->lim_m, j);
         }
@@ -447,7 +449,7 @@ k_tail(BatchArgs a, ChunkArgs ck, const __grid_constant__ CUtensorMap x_map, int
         // sub-tile, so that TP-R has a whole step to turn its targets into output rows and no FIR warp ever waits for it.
         // Warp 3 + m owns unit m of both kinds (the serial warps issue so little that the schedulers hosting them need no
         // relief: a 3 / 2 / 2 / 1 split only made warp 3 the straggler).  ONE instance of the unrolled FIR serves both kinds.
-        const int m = warp - 3;
+        const int m = warp - 3;  // warps 3 .. 6
         const int in_first = m, in_count = 1;  // one FIR-IN and one FIR-OUT unit per warp and step
         const float tp_ceil = (float)a.map_tab[(size_t)MT_TP_CEIL * stride + s];
         float* audio = (a.audio && s < a.n_streams) ? a.audio + a.audio_off[s] + ck.n0 : nullptr;

@@ -10,7 +10,7 @@ namespace afsim {
 struct ChunkArgs;
 
 constexpr int kTailMapWarps = 4;
-constexpr int kTailThreads = 32 * (3 + kTailMapWarps);  // producer, LIM-R, TP-R, map warps
+constexpr int kTailThreads = 32 * (4 + kTailMapWarps);  // LIM-R (+ TMA producer), TP-R, two LIM-M warps, four FIR warps
 constexpr int kTailHistRows = 64;                      // parked between chunks: 32 rows of each of the two output rings
 
 struct alignas(64) TailMap {  // a CUtensorMap (kept opaque so that callers need not include <cuda.h>)
