@@ -290,3 +290,26 @@ def ctypes_sizeof_metrics() -> int:
 
 def ctypes_sizeof_candidate_params() -> int:
     return CANDIDATE_PARAMS_BYTES
+
+
+# ---- product resampler simulator (include/afsim.h; rust-core/src/audio/processor/resampling.rs:158-272) ----
+RESAMPLER_WINDOWS = ("blackman_harris", "blackman_harris_squared", "blackman", "blackman_squared", "hann", "hann_squared")
+
+
+class AfResamplerSpec(C.Structure):
+    _fields_ = [
+        ("input_rate", C.c_uint32),
+        ("output_rate", C.c_uint32),
+        ("chunk_size", C.c_uint32),
+        ("sinc_len", C.c_uint32),
+        ("window", C.c_int32),
+    ]
+
+
+class AfResamplerShape(C.Structure):
+    _fields_ = [
+        ("frames", C.c_uint64),
+        ("expected_frames", C.c_uint64),
+        ("delay", C.c_uint32),
+        ("blocks", C.c_uint32),
+    ]

@@ -22,6 +22,7 @@
 #include "afsim_kernels.h"
 #include "afsim_plan.h"
 #include "afsim_render.h"
+#include "afsim_resample.h"
 #include "afsim_tail.h"
 
 using namespace afsim;
@@ -78,6 +79,23 @@ struct DevicePool {
 };
 
 struct AfsimSweep;
+
+// The last resampler plan of a handle stays on the device: the tool's cases repeat one (configuration, length) pair
+// for many signals, and a 60 s plan is 2.9 M frames (46 MB) walked sequentially on the host.
+struct ResampleCache {
+    ResamplePlan plan;
+    ResampleFrame* d_frames = nullptr;
+    double* d_table = nullptr;
+    bool matches(const AfResamplerSpec& sp, size_t n_in) const {
+        return d_frames && plan.n_in == n_in && std::memcmp(&plan.spec, &sp, sizeof sp) == 0;
+    }
+    void drop() {
+        if (d_frames) cudaFree(d_frames);
+        if (d_table) cudaFree(d_table);
+        d_frames = nullptr;
+        d_table = nullptr;
+    }
+};
 struct AfsimHandle {
     int device = 0;
     DevicePool pool;
@@ -89,6 +107,7 @@ struct AfsimHandle {
     std::string error;
     std::recursive_mutex call_mu;     // one call at a time per handle (include/afsim.h: threading contract)
     std::set<AfsimSweep*> live;       // sweeps whose buffers come from `pool`: detached by afsim_destroy
+    ResampleCache resample;
 };
 
 namespace {
@@ -1001,6 +1020,7 @@ void afsim_destroy(AfsimHandle* h) {
         if (h->stage_stream_map[i]) cudaStreamDestroy(h->stage_stream_map[i]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    h->resample.drop();
     h->pool.trim();
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1709,3 +1729,149 @@ int afsim_auto_makeup_control(AfsimHandle* h, const float* audio, size_t n, doub
 }
 
 }  // extern "C"
+
+// ---- product resampler simulator (afsim_resample.cu) --------------------------------------------------------------
+
+void afsim_resampler_spec_default(AfResamplerSpec* out) {
+    if (!out) return;
+    std::memset(out, 0, sizeof *out);
+    out->chunk_size = 1024;
+    out->sinc_len = 128;
+    out->window = AF_WINDOW_BLACKMAN;
+}
+
+int afsim_product_resampler_shape(const AfResamplerSpec* spec, size_t n_in, AfResamplerShape* out_shape, char* err, size_t err_capacity) {
+    std::string msg;
+    int rc = AFSIM_INVALID_ARGUMENT;
+    if (!spec || !out_shape) {
+        msg = "null argument";
+    } else {
+        ResamplePlan plan;
+        rc = plan_resampler(*spec, n_in, false, false, &plan, &msg);
+        if (rc == AFSIM_OK) *out_shape = plan.shape;
+    }
+    if (err && err_capacity) {
+        std::strncpy(err, msg.c_str(), err_capacity - 1);
+        err[err_capacity - 1] = 0;
+    }
+    return rc;
+}
+
+int afsim_product_resampler_plan(const AfResamplerSpec* spec, size_t n_in, double* out_table, int64_t* out_base, int32_t* out_phase,
+                                 double* out_frac) {
+    if (!spec) return AFSIM_INVALID_ARGUMENT;
+    ResamplePlan plan;
+    std::string msg;
+    const int rc = plan_resampler(*spec, n_in, true, out_table != nullptr, &plan, &msg);
+    if (rc != AFSIM_OK) return rc;
+    if (out_table) std::memcpy(out_table, plan.table.data(), plan.table.size() * sizeof(double));
+    for (size_t i = 0; i < plan.frames.size(); ++i) {
+        if (out_base) out_base[i] = plan.frames[i].base;
+        if (out_phase) out_phase[i] = plan.frames[i].sub;
+        if (out_frac) out_frac[i] = plan.frames[i].frac;
+    }
+    return AFSIM_OK;
+}
+
+namespace {
+int resampler_on_device(AfsimHandle* h, const AfResamplerSpec& spec, size_t n_in) {  // plan + table + frames resident
+    if (h->resample.matches(spec, n_in)) return AFSIM_OK;
+    std::string msg;
+    ResamplePlan plan;
+    const int rc = plan_resampler(spec, n_in, true, true, &plan, &msg);
+    if (rc != AFSIM_OK) return set_error(h, rc, msg);
+    h->resample.drop();
+    AF_CUDA(h, cudaMalloc(&h->resample.d_table, plan.table.size() * sizeof(double)));
+    AF_CUDA(h, cudaMalloc(&h->resample.d_frames, std::max<size_t>(plan.frames.size(), 1) * sizeof(ResampleFrame)));
+    AF_CUDA(h, cudaMemcpyAsync(h->resample.d_table, plan.table.data(), plan.table.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    AF_CUDA(h, cudaMemcpyAsync(h->resample.d_frames, plan.frames.data(), plan.frames.size() * sizeof(ResampleFrame), cudaMemcpyHostToDevice,
+                               h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors go away below
+    plan.frames.clear();
+    plan.frames.shrink_to_fit();
+    plan.table.clear();
+    plan.table.shrink_to_fit();
+    h->resample.plan = std::move(plan);
+    return AFSIM_OK;
+}
+}  // namespace
+
+int afsim_product_resampler_device(AfsimHandle* h, const AfResamplerSpec* spec, const double* d_in, size_t in_stride, size_t n_streams,
+                                   size_t n_in, double* d_out, size_t out_stride, float* out_ms) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
+    h->error.clear();
+    if (!spec || (!d_in && n_in && n_streams) || (!d_out && n_streams)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    if (n_streams > 0x7fffffffu) return set_error(h, AFSIM_INVALID_ARGUMENT, "too many streams");
+    AF_CUDA(h, cudaSetDevice(h->device));
+    const int rc = resampler_on_device(h, *spec, n_in);
+    if (rc != AFSIM_OK) return rc;
+    const ResamplePlan& plan = h->resample.plan;
+    if (in_stride < n_in || out_stride < plan.shape.frames) return set_error(h, AFSIM_INVALID_ARGUMENT, "stride shorter than the signal");
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (out_ms) {
+        AF_CUDA(h, cudaEventCreate(&e0));
+        AF_CUDA(h, cudaEventCreate(&e1));
+        AF_CUDA(h, cudaEventRecord(e0, h->stream));
+    }
+    AF_CUDA(h, launch_resample(d_in, in_stride, n_in, d_out, out_stride, plan.shape.frames, static_cast<int>(n_streams), h->resample.d_frames,
+                               h->resample.d_table, static_cast<int>(spec->sinc_len), plan.max_span, h->stream));
+    if (out_ms) AF_CUDA(h, cudaEventRecord(e1, h->stream));
+    AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (out_ms) {
+        AF_CUDA(h, cudaEventElapsedTime(out_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return AFSIM_OK;
+}
+
+int afsim_product_resampler(AfsimHandle* h, const AfResamplerSpec* spec, const double* const* samples, size_t n_streams, size_t n_in,
+                            double* const* out, AfResamplerShape* out_shape) {
+    if (!h) return AFSIM_INVALID_ARGUMENT;
+    AF_LOCK(h);
+    h->error.clear();
+    if (!spec || (!samples && n_streams) || (!out && n_streams)) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+    if (n_streams > 0x7fffffffu) return set_error(h, AFSIM_INVALID_ARGUMENT, "too many streams");
+    {   // validation in the reference's order (resampling.rs:187-221): rates, chunk, sinc_len, window, then the samples
+        std::string msg;
+        ResamplePlan probe;
+        const int rc = plan_resampler(*spec, n_in, false, false, &probe, &msg);
+        if (rc == AFSIM_INVALID_ARGUMENT && msg.rfind("resampler flush", 0) != 0) return set_error(h, rc, msg);
+        for (size_t s = 0; s < n_streams; ++s) {
+            if (!samples[s] && n_in) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+            for (size_t i = 0; i < n_in; ++i)
+                if (!std::isfinite(samples[s][i])) return set_error(h, AFSIM_INVALID_ARGUMENT, "samples must be finite");
+        }
+        if (rc != AFSIM_OK) return set_error(h, rc, msg);
+        if (out_shape) *out_shape = probe.shape;
+    }
+    if (n_streams == 0) return AFSIM_OK;
+    AF_CUDA(h, cudaSetDevice(h->device));
+    const int rc = resampler_on_device(h, *spec, n_in);
+    if (rc != AFSIM_OK) return rc;
+    const ResamplePlan& plan = h->resample.plan;
+    const size_t frames = plan.shape.frames;
+    const size_t in_stride = (n_in + 31) / 32 * 32 + 32, out_stride = (frames + 31) / 32 * 32;
+    DeviceBuffers mem;
+    mem.pool = &h->pool;
+    // streams go through the device in groups that fit a bounded staging area (a 60 s signal is 21 + 23 MB)
+    const size_t per_stream = (in_stride + out_stride) * sizeof(double);
+    const size_t group = std::max<size_t>(1, std::min(n_streams, (size_t(4) << 30) / std::max<size_t>(per_stream, 1)));
+    double *d_in = nullptr, *d_out = nullptr;
+    AF_CUDA(h, mem.alloc(&d_in, group * in_stride));
+    AF_CUDA(h, mem.alloc(&d_out, group * std::max<size_t>(out_stride, 1)));
+    for (size_t s0 = 0; s0 < n_streams; s0 += group) {
+        const size_t ns = std::min(group, n_streams - s0);
+        for (size_t s = 0; s < ns; ++s)
+            if (n_in) AF_CUDA(h, cudaMemcpyAsync(d_in + s * in_stride, samples[s0 + s], n_in * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        AF_CUDA(h, launch_resample(d_in, in_stride, n_in, d_out, out_stride, frames, static_cast<int>(ns), h->resample.d_frames,
+                                   h->resample.d_table, static_cast<int>(spec->sinc_len), plan.max_span, h->stream));
+        for (size_t s = 0; s < ns; ++s) {
+            if (!out[s0 + s]) return set_error(h, AFSIM_INVALID_ARGUMENT, "null argument");
+            if (frames) AF_CUDA(h, cudaMemcpyAsync(out[s0 + s], d_out + s * out_stride, frames * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        AF_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return AFSIM_OK;
+}

@@ -275,6 +275,55 @@ def eq_magnitude_response_v2(frequencies_hz, bands, sample_rate: float, *, devic
     return simulator(device).eq_response(list(frequencies_hz), band_arr, sample_rate, typed=True)[0].tolist()
 
 
+# ---- product resampler simulator (rust-core/src/audio/processor/resampling.rs:170-272) -------------------------
+def _resampler_spec(input_rate, output_rate, chunk_size, sinc_len, window) -> abi.AfResamplerSpec:
+    if window is not None and window not in abi.RESAMPLER_WINDOWS:
+        # the reference validates rates, chunk and sinc_len first (resampling.rs:187-202); let the library do that
+        # with a window id it rejects, then report the name as the reference does
+        spec = native.resampler_spec(int(input_rate), int(output_rate), int(chunk_size), sinc_len, None)
+        native.resampler_shape(spec, 0)
+        raise ValueError(f"unsupported resampler window {str(window)!r}".replace("'", '"'))
+    return native.resampler_spec(int(input_rate), int(output_rate), int(chunk_size), sinc_len, window)
+
+
+def simulate_product_resampler_batch(signals, input_rate: int, output_rate: int, chunk_size: int = 1024,
+                                     sinc_len: int | None = None, window: str | None = None, *, device: int = 0):
+    """Batched form: `signals` [n_streams, n_in] (equal lengths) through the product resampler in ONE call ->
+    (outputs [n_streams, frames] float64 ndarray, output_delay, expected_frames)."""
+    spec = _resampler_spec(input_rate, output_rate, chunk_size, sinc_len, window)
+    arr = np.asarray(signals, dtype=np.float64)
+    if arr.ndim != 2:
+        raise ValueError("signals must be a 2-d array [n_streams, n_in]")
+    try:
+        out, shape = simulator(device).product_resampler(arr, spec)
+    except ValueError as error:
+        if str(error).startswith("resampler flush"):
+            raise RuntimeError(str(error)) from None  # PyRuntimeError in the reference (resampling.rs:251-255)
+        raise
+    return out, int(shape.delay), int(shape.expected_frames)
+
+
+def simulate_product_resampler(samples, input_rate: int, output_rate: int, chunk_size: int = 1024,
+                               sinc_len: int | None = None, window: str | None = None, *, device: int = 0):
+    """resampling.rs:170-262 -> (output, output_delay, expected_frames, block_times_ns).  `block_times_ns` (the
+    reference's wall clock per rubato process call) has no per-block counterpart on the GPU: every entry carries the
+    amortised time of the whole call, one entry per block the reference would have processed."""
+    import time
+    arr = np.asarray(samples, dtype=np.float64).reshape(1, -1)
+    started = time.perf_counter_ns()
+    out, delay, expected = simulate_product_resampler_batch(arr, input_rate, output_rate, chunk_size, sinc_len, window,
+                                                            device=device)
+    elapsed = time.perf_counter_ns() - started
+    spec = _resampler_spec(input_rate, output_rate, chunk_size, sinc_len, window)
+    blocks = int(native.resampler_shape(spec, arr.shape[1]).blocks)
+    return out[0].tolist(), delay, expected, [max(1, elapsed // max(blocks, 1))] * blocks
+
+
+def product_resampler_configuration():
+    """resampling.rs:263-272: (sinc_len, window, interpolation, oversampling_factor, chunk_size)."""
+    return (128, "blackman", "cubic", 256, 1024)
+
+
 # ---- names mic_eq/__init__.py:55-58 reads unguarded; the live engine is out of scope here -------------------
 def _out_of_scope(*_args, **_kwargs):
     raise ImportError("the live audio engine is not part of the B200 chain-simulator build")

@@ -32,6 +32,8 @@ EXPORTS = (
     "afsim_multi_create", "afsim_multi_destroy", "afsim_multi_device_count", "afsim_multi_last_error",
     "afsim_multi_create_error", "afsim_multi_chain_sweep", "afsim_multi_partition",
     "afsim_selftest_math", "afsim_auto_makeup_settings_default", "afsim_auto_makeup_control", "afsim_auto_makeup_sweep",
+    "afsim_resampler_spec_default", "afsim_product_resampler_shape", "afsim_product_resampler",
+    "afsim_product_resampler_device", "afsim_product_resampler_plan",
 )
 STAGE_NAMES = ("input", "input_true_peak", "deesser", "eq", "compressor", "limiter", "output", "finalize",
                "comp_r1", "comp_m2", "comp_r3", "comp_m4", "comp_r5", "comp_m6", "lim_m", "lim_r", "tp_fir_in", "tp_r",
@@ -120,6 +122,13 @@ def lib() -> C.CDLL:
     L.afsim_sweep_profile_wavefront.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), f32p, f32p,
                                                 C.POINTER(C.c_int)]
     L.afsim_selftest_math.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    spec_p, shape_p = C.POINTER(abi.AfResamplerSpec), C.POINTER(abi.AfResamplerShape)
+    L.afsim_resampler_spec_default.argtypes = [spec_p]
+    L.afsim_resampler_spec_default.restype = None
+    L.afsim_product_resampler_shape.argtypes = [spec_p, C.c_size_t, shape_p, C.c_char_p, C.c_size_t]
+    L.afsim_product_resampler.argtypes = [vp, spec_p, C.POINTER(f64p), C.c_size_t, C.c_size_t, C.POINTER(f64p), shape_p]
+    L.afsim_product_resampler_device.argtypes = [vp, spec_p, vp, C.c_size_t, C.c_size_t, C.c_size_t, vp, C.c_size_t, f32p]
+    L.afsim_product_resampler_plan.argtypes = [spec_p, C.c_size_t, f64p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), f64p]
     mk_p = C.POINTER(abi.AfAutoMakeupSettings)
     L.afsim_auto_makeup_settings_default.argtypes = [mk_p]
     L.afsim_auto_makeup_settings_default.restype = None
@@ -137,6 +146,49 @@ def _f32p(a: np.ndarray):
 
 def _u32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_uint32)) if a is not None else None
+
+
+def resampler_spec(input_rate: int, output_rate: int, chunk_size: int = 1024, sinc_len: int | None = None,
+                   window: str | None = None) -> abi.AfResamplerSpec:
+    """AfResamplerSpec with the product defaults (128 taps, blackman: resampling.rs:131-138) for None."""
+    spec = abi.AfResamplerSpec()
+    lib().afsim_resampler_spec_default(C.byref(spec))
+    if input_rate < 0 or output_rate < 0 or chunk_size < 0 or (sinc_len is not None and sinc_len < 0):
+        raise OverflowError("can't convert negative int to unsigned")  # PyO3's u32 / usize extraction
+    spec.input_rate, spec.output_rate, spec.chunk_size = int(input_rate), int(output_rate), min(int(chunk_size), 0xFFFFFFFF)
+    if sinc_len is not None:
+        spec.sinc_len = min(int(sinc_len), 0xFFFFFFFF)
+    if window is not None:
+        spec.window = abi.RESAMPLER_WINDOWS.index(window) if window in abi.RESAMPLER_WINDOWS else -1
+    return spec
+
+
+def resampler_shape(spec: abi.AfResamplerSpec, n_in: int, check: bool = True):
+    """(frames, expected_frames, delay, blocks) of a render; host only.  check=False -> None instead of raising."""
+    shape = abi.AfResamplerShape()
+    err = C.create_string_buffer(256)
+    rc = lib().afsim_product_resampler_shape(C.byref(spec), int(n_in), C.byref(shape), err, 256)
+    if rc != abi.AFSIM_OK:
+        if not check:
+            return None
+        if rc == abi.AFSIM_INVALID_ARGUMENT:
+            raise ValueError(err.value.decode())
+        raise AfsimError(rc, err.value.decode())
+    return shape
+
+
+def resampler_plan(spec: abi.AfResamplerSpec, n_in: int, with_table: bool = True):
+    """The planner's phase table and frame list (audit hook of the CPU tests)."""
+    shape = resampler_shape(spec, n_in)
+    n = int(shape.frames)
+    table = np.zeros((256, int(spec.sinc_len)), dtype=np.float64) if with_table else None
+    base, phase, frac = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.float64)
+    rc = lib().afsim_product_resampler_plan(C.byref(spec), int(n_in), table.ctypes.data_as(C.POINTER(C.c_double)) if with_table else None,
+                                            base.ctypes.data_as(C.POINTER(C.c_int64)), phase.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            frac.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc != abi.AFSIM_OK:
+        raise AfsimError(rc, "afsim_product_resampler_plan")
+    return shape, table, base, phase, frac
 
 
 class Sweep:
@@ -254,6 +306,30 @@ class Simulator:
         out = (C.c_uint64 * 6)()
         self._check(lib().afsim_selftest_math(self._h, int(n), out))
         return dict(zip(("log10", "exp10", "div20", "div40", "div3.75", "div_prepared"), (int(v) for v in out)))
+
+    # ---- product resampler simulator ----
+    def product_resampler(self, signals, spec: abi.AfResamplerSpec):
+        """afsim_product_resampler on host buffers: signals [n_streams, n_in] f64 -> (out [n_streams, frames], shape)."""
+        signals = np.ascontiguousarray(signals, dtype=np.float64)
+        if signals.ndim != 2:
+            raise ValueError("signals must be [n_streams, n_in]")
+        n_streams, n_in = signals.shape
+        shape = resampler_shape(spec, n_in, check=False)  # sizes the outputs; the call below owns the error order
+        out = np.zeros((n_streams, int(shape.frames) if shape else 0), dtype=np.float64)
+        f64p = C.POINTER(C.c_double)
+        ins = (f64p * max(n_streams, 1))(*[signals[s].ctypes.data_as(f64p) for s in range(n_streams)])
+        outs = (f64p * max(n_streams, 1))(*[out[s].ctypes.data_as(f64p) for s in range(n_streams)])
+        got = abi.AfResamplerShape()
+        self._check(lib().afsim_product_resampler(self._h, C.byref(spec), ins, n_streams, n_in, outs, C.byref(got)))
+        return out, got
+
+    def product_resampler_device(self, spec: abi.AfResamplerSpec, d_in: int, in_stride: int, n_streams: int, n_in: int,
+                                 d_out: int, out_stride: int) -> float:
+        """afsim_product_resampler_device on device pointers (torch tensors' data_ptr()); -> kernel ms."""
+        ms = C.c_float(0.0)
+        self._check(lib().afsim_product_resampler_device(self._h, C.byref(spec), C.c_void_p(d_in), in_stride, n_streams, n_in,
+                                                         C.c_void_p(d_out), out_stride, C.byref(ms)))
+        return float(ms.value)
 
     # ---- single-stream entry points ----
     def chain_render(self, audio, sample_rate, bands, settings: abi.AfChainSettings, return_audio: bool = False):

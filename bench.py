@@ -20,7 +20,8 @@ sweeps' device tables (`sharding.DeviceGather`) for the final first-safe-scale /
   stages     per stage kernel: share, mean launch duration, streams per launch, bound label
   cpu_baseline  the CPU oracle port (the reference's Rust simulator cannot be built here) on all host threads, on a
              bounded sample of the same workload, with the per-core figure
-  other_configs  (N = 1 only) BASELINE configs 2, 3 and 4 at full size, each with value / e2e / roofline / parity
+  other_configs  (N = 1 only) BASELINE configs 2, 3 and 4 at full size, each with value / e2e / roofline / parity, and
+             `resampler`: the product resampler simulator on its study's 60 s case, 32 signals per call
 
 `--impl reference` times that CPU port alone (rank 0 only).  `--workload c1..c5` picks another BASELINE shape as the
 main record (optionally scaled with --candidates / --passages / --seconds).
@@ -91,7 +92,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS) + ["resampler"],
                     help="BASELINE.json config of the main record; c5 (the north-star target, default)")
     ap.add_argument("--candidates", type=int, default=0, help="override the workload's candidate count")
     ap.add_argument("--passages", type=int, default=0, help="override the workload's passage count")
@@ -100,7 +101,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (also drops `parity`)")
     ap.add_argument("--no-profile", action="store_true", help="skip the serialised per-stage timing pass")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C2 / C3 / C4 sub-records (N = 1)")
-    ap.add_argument("--other-configs", default="c2,c3,c4", help="sub-records to run at N = 1")
+    ap.add_argument("--other-configs", default="c2,c3,c4,resampler", help="sub-records to run at N = 1")
     return ap.parse_args()
 
 
@@ -528,6 +529,88 @@ def measure(shape: Shape, args, rank: int, world: int, local_rank: int, steps: i
     return record
 
 
+def measure_resampler(args, local_rank: int, steps: int = 5, warmup: int = 3, n_streams: int = 32, seconds: float = 60.0):
+    """the product resampler simulator (`simulate_product_resampler`, resampling.rs:170-262) on the
+    long-stream case of the reference's own study (python/tools/evaluate_resampler_quality.py: 60 s, 44.1 -> 48 kHz,
+    128-tap Blackman, 256 phases, cubic), `n_streams` signals in one call.  Unit: output frames per second."""
+    import torch
+
+    from audio_forge_b200 import native
+    from oracle import resampler_oracle  # cpu_baseline / parity legs only
+
+    stream = torch.cuda.current_stream()
+    sim = native.Simulator(local_rank, cuda_stream=stream.cuda_stream)
+    rate_in, rate_out = 44100, 48000
+    n_in = int(rate_in * seconds)
+    spec = native.resampler_spec(rate_in, rate_out)
+    shape = native.resampler_shape(spec, n_in)
+    frames = int(shape.frames)
+    rng = np.random.default_rng(0x5EED)
+    host = (0.25 * rng.standard_normal((n_streams, n_in))).astype(np.float64)
+    d_in = torch.from_numpy(host).to(f"cuda:{local_rank}")
+    d_out = torch.zeros((n_streams, frames), dtype=torch.float64, device=f"cuda:{local_rank}")
+    kernel_ms = []
+    for i in range(warmup + steps):
+        ms = sim.product_resampler_device(spec, d_in.data_ptr(), n_in, n_streams, n_in, d_out.data_ptr(), frames)
+        if i >= warmup:
+            kernel_ms.append(ms)
+    torch.cuda.synchronize()
+    ms_step = float(np.mean(kernel_ms))
+    total_frames = n_streams * frames
+    fp64_peak = sim.issue_peak(0)
+    fma = total_frames * 4 * int(spec.sinc_len)
+    hbm_peak = load_hbm_peak()
+    rec = {
+        "value": total_frames / (ms_step * 1e-3) / 1e6, "unit": "Mframes/s (output)", "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+        "config": {"workload": "product resampler simulator, the reference study's long-stream case as one batch", "streams": n_streams,
+                   "seconds": seconds, "input_rate": rate_in, "output_rate": rate_out, "sinc_len": int(spec.sinc_len), "window": "blackman",
+                   "phases": 256, "interpolation": "cubic", "frames_per_stream": frames,
+                   "l2": f"inputs larger than L2: {host.nbytes / 1e6:.0f} MB in, {total_frames * 8 / 1e6:.0f} MB out per step"},
+        "gpu_launches": steps,
+        "roofline": {"bound": "fp64_issue", "kernel": "k_resample", "achieved": fma / (ms_step * 1e-3) / 1e9, "peak": fp64_peak,
+                     "unit": "1e9 warp-lane FP64 instructions/s (512 DFMA per frame; peak measured in this run on dependent DMUL+DADD chains)",
+                     "frac": fma / (ms_step * 1e-3) / 1e9 / fp64_peak if fp64_peak else None,
+                     "hbm_gb_s": (host.nbytes + total_frames * 8) / (ms_step * 1e-3) / 1e9, "hbm_frac": (host.nbytes + total_frames * 8) / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                     "algorithmic_bytes_per_frame": 16, "traffic": None},
+    }
+    # end to end through the public call with host buffers (H2D + render + D2H inside the timed region)
+    e2e_s = []
+    out = None
+    for i in range(1 + min(steps, 2)):
+        t0 = time.perf_counter()
+        out, _ = sim.product_resampler(host, spec)
+        if i:
+            e2e_s.append(time.perf_counter() - t0)
+    rec["e2e"] = {"value": total_frames / float(np.mean(e2e_s)) / 1e6, "unit": "Mframes/s (output)", "h2d_bytes_per_step": int(host.nbytes),
+                  "d2h_bytes_per_step": int(total_frames * 8), "steps": len(e2e_s)}
+    if not args.no_cpu_baseline:
+        # the oracle on a bounded sample: the first 4 s of two streams (frames sit where the 60 s render puts them, so
+        # the same frames of the GPU's 60 s outputs are the comparison)
+        n_cpu = int(rate_in * 4.0)
+        keep = int(rate_out * 4.0) - 256
+        t0 = time.perf_counter()
+        worst = 0.0
+        for s in range(2):
+            want, _, _, _ = resampler_oracle.simulate_product_resampler(host[s, :n_cpu], rate_in, rate_out)
+            worst = max(worst, float(np.max(np.abs(want[:keep] - out[s, :keep]))))
+        cpu_s = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": 2 * keep / cpu_s / 1e6, "unit": "Mframes/s (output)", "cores": 1, "kind": "port",
+                               "sample": f"2 streams x 4 s through the numpy oracle, {cpu_s:.1f} s",
+                               "reference_published": {"value": 1024 * rate_out / rate_in / 66.0e-6 / 1e6, "unit": "Mframes/s (output)",
+                                                       "what": "the real crate's median 66.0 us per 1024-frame block, evaluation/resampler-quality-report.json (the reference author's machine, one core)"}}
+        rec["parity"] = {"streams": 2, "frames": keep, "max_abs_difference": worst, "tolerance": 1e-12,
+                         "mismatches": int(worst > 1e-12), "what": "numpy oracle (pinned on the reference's published report) vs GPU, full-scale 1.0"}
+    sim.close()
+    return rec
+
+
+def load_hbm_peak() -> float:
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        return 6552.6
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
@@ -538,14 +621,28 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stream = torch.cuda.Stream(device=local_rank)  # the library launches on it, so torch's events see the work
     torch.cuda.set_stream(stream)
 
+    if args.workload == "resampler":  # the 8(f).4 sub-record alone (one GPU)
+        if rank == 0:
+            line = measure_resampler(args, local_rank, steps=args.steps, warmup=args.warmup, seconds=args.seconds or 60.0)
+            line.update({"metric": "product resampler simulator throughput (output frames per second)", "n_gpus": 1, "higher_is_better": True,
+                         "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic"})
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     shape = Shape(args.workload, args.candidates, args.passages, args.seconds)
     line = measure(shape, args, rank, world, local_rank, args.steps, args.warmup, profile=not args.no_profile,
                    cpu_leg=not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_other_configs:
         others = {}
-        for key in [k for k in args.other_configs.split(",") if k in WORKLOADS and k != args.workload]:
+        for key in [k for k in args.other_configs.split(",") if (k in WORKLOADS or k == "resampler") and k != args.workload]:
             t0 = time.perf_counter()
             try:
+                if key == "resampler":
+                    rec = measure_resampler(args, local_rank)
+                    rec["wall_s"] = time.perf_counter() - t0
+                    others[key] = rec
+                    continue
                 rec = measure(Shape(key), args, 0, 1, local_rank, steps=2, warmup=3, profile=not args.no_profile,
                               cpu_leg=not args.no_cpu_baseline)
                 for drop in ("metric", "unit", "higher_is_better", "vs_baseline", "data", "dtype", "n_gpus", "wavefront"):

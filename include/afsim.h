@@ -328,6 +328,58 @@ int afsim_multi_partition(const AfCandidate* candidates, size_t n_candidates, co
                           size_t n_passages, const uint32_t* pair_passage, const uint32_t* pair_candidate,
                           size_t n_pairs, int n_parts, uint32_t* out_owner);
 
+/* ---- product resampler simulator ---------------------------- */
+
+/* Replaces simulate_product_resampler (rust-core/src/audio/processor/resampling.rs:170-262): the signal through
+ * rubato 0.14's SincFixedIn<f64> -- cubic interpolation between 256 windowed-sinc phases, `chunk_size` blocks, one
+ * zero-padded partial block, zero-input flush blocks until expected + delay frames exist -- for `n_streams` signals of
+ * equal length at once.  Every frame is rendered where the reference's block loop puts it (the loop is walked on the
+ * host, addition for addition); results agree with the crate to f64 rounding of the dot products.  rubato is not
+ * vendored in the reference tree: `calculate_cutoff` is available only for the configurations the reference ships and
+ * evaluates (128 blackman -- the product default, resampling.rs:131-138 --, 128 and 256 blackman_harris_squared;
+ * python/tools/evaluate_resampler_quality.py), other pairs return AFSIM_UNSUPPORTED.  The reference's fourth result,
+ * wall-clock nanoseconds per block, is a host measurement and has no counterpart here. */
+typedef enum AfResamplerWindow { /* resampler_window_from_name, resampling.rs:158-168 */
+    AF_WINDOW_BLACKMAN_HARRIS = 0,
+    AF_WINDOW_BLACKMAN_HARRIS2 = 1,
+    AF_WINDOW_BLACKMAN = 2,
+    AF_WINDOW_BLACKMAN2 = 3,
+    AF_WINDOW_HANN = 4,
+    AF_WINDOW_HANN2 = 5
+} AfResamplerWindow;
+typedef struct AfResamplerSpec {
+    uint32_t input_rate, output_rate;
+    uint32_t chunk_size; /* 1 .. 1024 (RESAMPLER_CHUNK_SIZE) */
+    uint32_t sinc_len;   /* power of two, 32 .. 2048 */
+    int32_t window;      /* AfResamplerWindow */
+} AfResamplerSpec;
+typedef struct AfResamplerShape {
+    uint64_t frames;          /* frames the block loop produces (>= expected_frames + delay): length of every output */
+    uint64_t expected_frames; /* round(n_in * output_rate / input_rate) */
+    uint32_t delay;           /* output_delay() of the crate, in output frames */
+    uint32_t blocks;          /* process calls the reference makes (full + partial + flush) */
+} AfResamplerShape;
+/* product_resampler_configuration (resampling.rs:263-272): 128 taps, blackman, chunk 1024; rates left 0. */
+void afsim_resampler_spec_default(AfResamplerSpec* out);
+/* Validation (the reference's messages) and output shape; host only, needs no device.  `err` (nullable) receives the
+ * message on failure. */
+int afsim_product_resampler_shape(const AfResamplerSpec* spec, size_t n_in, AfResamplerShape* out_shape, char* err,
+                                  size_t err_capacity);
+/* Host buffers: samples[s] = n_in doubles (finite, else AFSIM_INVALID_ARGUMENT "samples must be finite"), out[s] =
+ * shape.frames doubles. */
+int afsim_product_resampler(AfsimHandle* handle, const AfResamplerSpec* spec, const double* const* samples,
+                            size_t n_streams, size_t n_in, double* const* out, AfResamplerShape* out_shape);
+/* The same on device-resident buffers (d_in[s * in_stride + i], d_out[s * out_stride + f]); asynchronous on the
+ * handle's stream up to the final synchronisation; out_ms (nullable) = kernel time by CUDA events.  Non-finite input is
+ * the caller's responsibility here. */
+int afsim_product_resampler_device(AfsimHandle* handle, const AfResamplerSpec* spec, const double* d_in,
+                                   size_t in_stride, size_t n_streams, size_t n_in, double* d_out, size_t out_stride,
+                                   float* out_ms);
+/* Test / audit hook: the planner's phase table ([256][sinc_len], nullable) and frame list (base sample, phase,
+ * cubic abscissa; each nullable, shape.frames entries) so that the CPU tier can hold them against the oracle. */
+int afsim_product_resampler_plan(const AfResamplerSpec* spec, size_t n_in, double* out_table, int64_t* out_base,
+                                 int32_t* out_phase, double* out_frac);
+
 /* ---- measurement helpers (bench.py; no reference counterpart) ------------------ */
 
 /* Stage kinds reported by afsim_sweep_profile_stages. */

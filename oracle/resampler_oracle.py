@@ -116,7 +116,25 @@ def output_positions(n_in: int, input_rate: int, output_rate: int, chunk_size: i
             raise RuntimeError("resampler flush produced no frames before reaching the expected length")
         last = last - float(chunk_size)
         b += 1
+    if not idxs:
+        return np.zeros(0, dtype=np.int64), np.zeros(0)
     return np.concatenate(blocks), np.concatenate(idxs)
+
+
+def frame_list(n_in: int, input_rate: int, output_rate: int, chunk_size: int, sinc_len: int):
+    """Per produced frame: the absolute input sample under tap 0 of phase `sub` (buffer position floor(idx) +
+    2 sinc_len of block b holds sample b * chunk + floor(idx)), the phase (get_nearest_times_4's middle-left point) and
+    the cubic's abscissa `frac - floor(frac)`, frac = idx * 256."""
+    ratio = output_rate / input_rate
+    delay = int(sinc_len / 2 * ratio)
+    expected = int(math.floor(n_in * float(output_rate) / float(input_rate) + 0.5))
+    blk, idx = output_positions(n_in, input_rate, output_rate, chunk_size, sinc_len, expected + delay)
+    fl = np.floor(idx)
+    base = blk * chunk_size + fl.astype(np.int64)
+    frac_f = idx * float(OVERSAMPLING)
+    frac_off = frac_f - np.floor(frac_f)
+    sub = np.floor((idx - fl) * float(OVERSAMPLING)).astype(np.int64)
+    return base, sub, frac_off
 
 
 def simulate_product_resampler(samples, input_rate, output_rate, chunk_size=1024, sinc_len=None, window=None,
@@ -144,17 +162,10 @@ def simulate_product_resampler(samples, input_rate, output_rate, chunk_size=1024
     table = make_sincs(sinc_len, effective_cutoff(f_cutoff, ratio), window)
     delay = int(sinc_len / 2 * ratio)  # output_delay(): (sinc_len / 2) as f64 * ratio, truncated
     expected = int(math.floor(x.size * float(output_rate) / float(input_rate) + 0.5))
-    blk, idx = output_positions(x.size, input_rate, output_rate, chunk_size, sinc_len, expected + delay)
-    n_out = idx.size
-    # absolute sample index of buffer position (floor(idx) + 2 sinc_len) of block b: b*chunk + floor(idx)
-    # (buffer[2 sinc_len + j] holds sample j of the current block, earlier positions the previous blocks' tails)
-    fl = np.floor(idx)
-    base = blk * chunk_size + fl.astype(np.int64)
-    frac_f = idx * float(OVERSAMPLING)
-    frac_off = frac_f - np.floor(frac_f)
-    sub = np.floor((idx - fl) * float(OVERSAMPLING)).astype(np.int64)
+    base, sub, frac_off = frame_list(x.size, input_rate, output_rate, chunk_size, sinc_len)
+    n_out = base.size
     pad_lo = 2 * sinc_len + 2
-    total_in = (int(blk[-1]) + 1) * chunk_size
+    total_in = (int(base[-1]) if n_out else 0) + chunk_size + 2 * sinc_len
     xp = np.zeros(pad_lo + total_in + sinc_len + 2, dtype=np.float64)
     xp[pad_lo:pad_lo + x.size] = x
     out = np.zeros(n_out, dtype=np.float64)

@@ -20,7 +20,7 @@ REF = Path("/root/reference")
 sys.path.insert(0, str(ROOT))
 
 FILES = ["test_eq_filter_types.py", "test_dynamics_aliasing_tools.py", "test_limiter_lookahead_tools.py",
-         "test_processing_order_tools.py", "test_auto_makeup_real_speech_tools.py", "test_auto_eq.py", "test_voice_setup.py"]
+         "test_processing_order_tools.py", "test_resampler_quality_tools.py", "test_auto_makeup_real_speech_tools.py", "test_auto_eq.py", "test_voice_setup.py"]
 # Not collected: test_eq_native_response.py imports the Qt curve widget (PyQt6 is not in this image); its two native
 # assertions are restated in tests/test_reference_contract.py.
 DESELECT = [
@@ -50,12 +50,20 @@ class OracleSimulator:
         return pyoracle.auto_makeup_control(audio, sample_rate, vad, noise_floor_db, noise_reliability, settings,
                                             return_audio=return_audio)
 
+    def product_resampler(self, signals, spec):
+        from audio_forge_b200 import abi, native
+        from oracle import resampler_oracle
+        window = abi.RESAMPLER_WINDOWS[spec.window]
+        rows = [resampler_oracle.simulate_product_resampler(row, spec.input_rate, spec.output_rate, spec.chunk_size, spec.sinc_len, window)[0]
+                for row in np.asarray(signals, dtype=np.float64)]
+        return np.stack(rows), native.resampler_shape(spec, np.asarray(signals).shape[1])
+
     def eq_response(self, freqs, bands, sample_rate, typed):
         from oracle import pyoracle
         return (pyoracle.eq_response(freqs, bands, sample_rate, typed=typed),)
 
 
-FAST = FILES[:4]  # seconds; the voice-setup and Auto-EQ files render hundreds of passages through the CPU oracle
+FAST = FILES[:5]  # seconds; the voice-setup and Auto-EQ files render hundreds of passages through the CPU oracle
 
 
 def main(argv):
