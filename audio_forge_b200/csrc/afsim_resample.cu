@@ -145,29 +145,65 @@ int plan_resampler(const AfResamplerSpec& spec, size_t n_in, bool with_frames, b
             const int span = plan->frames[f1].base - plan->frames[f0].base + static_cast<int>(sl) + 3;
             if (span > plan->max_span) plan->max_span = span;
         }
-        if (plan->max_span > 24000) return *msg = "rate ratio too extreme for this build (input span of one frame group exceeds shared memory)", AFSIM_UNSUPPORTED;
+        if (plan->max_span > 6000) return *msg = "rate ratio too extreme for this build (input span of one frame group exceeds shared memory)", AFSIM_UNSUPPORTED;
     }
     if (with_table) build_table(static_cast<int>(sl), plan->cutoff, spec.window, &plan->table);
     return AFSIM_OK;
 }
 
-// One CTA = 128 consecutive frames of one stream: their input span goes through shared memory once; one warp per frame,
-// lane l owns taps l, l + 32, ... of the four phases (phase-table rows read as whole 256-byte lines), the cubic is applied
-// to the lane's partial sums (it is linear in the four points) and ONE butterfly reduction finishes the frame.  Frame k of
-// a warp's 32 lands in lane k, so the output leaves as one coalesced 256-byte store per warp.
+// One CTA = 128 consecutive frames of S streams: their input spans go through shared memory once; one warp per frame, lane l
+// owns taps l, l + 32, ... of the four phases (phase-table rows read as whole 256-byte lines, each value used for all S
+// streams), the cubic is applied to the lane's partial sums (it is linear in the four points) and one reduction over the
+// lanes (pairs at distance 1, 2, 4, 8, 16 -- the same tree for every S, so a batched render equals single renders bit for
+// bit) finishes the frame.  The kernel is bound by L1 bandwidth on the phase table (4 x sinc_len x 8 bytes per frame, every
+// frame another set of rows), which is why S streams share each table load.
+template <int S>
+__device__ __forceinline__ void reduce_and_keep(double (&v)[S], int lane, int k, double* mine);
+
+template <>
+__device__ __forceinline__ void reduce_and_keep<1>(double (&v)[1], int lane, int k, double* mine) {
+    double t = v[0];
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    if (lane == k) *mine = t;  // frame k of the warp's 32 lands in lane k: one coalesced store per warp
+}
+
+template <>
+__device__ __forceinline__ void reduce_and_keep<4>(double (&v)[4], int lane, int k, double* mine) {
+    // distance 1: even lanes go on with streams 0 / 1, odd lanes with 2 / 3; distance 2: bit 1 picks between the two
+    const bool b0 = lane & 1, b1 = lane & 2;
+    const double r0 = __shfl_xor_sync(0xffffffffu, b0 ? v[0] : v[2], 1);
+    const double r1 = __shfl_xor_sync(0xffffffffu, b0 ? v[1] : v[3], 1);
+    const double a = (b0 ? v[2] : v[0]) + r0;
+    const double b = (b0 ? v[3] : v[1]) + r1;
+    const double r2 = __shfl_xor_sync(0xffffffffu, b1 ? a : b, 2);
+    double t = (b1 ? b : a) + r2;
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    // lane l now holds the frame's total of stream ((l & 1) << 1) | ((l >> 1) & 1); lanes 4 j .. 4 j + 3 keep frame j of 8
+    if ((lane >> 2) == (k & 7)) *mine = t;
+}
+
+template <int T, int S>
 __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const double* __restrict__ in, size_t in_stride, long long n_in,
                                                                       double* __restrict__ out, size_t out_stride, long long n_frames,
                                                                       const ResampleFrame* __restrict__ frames,
-                                                                      const double* __restrict__ table, int sinc_len) {
+                                                                      const double* __restrict__ table, int n_streams) {
+    constexpr int SL = 32 * T;
     extern __shared__ double xs[];
     const long long f0 = static_cast<long long>(blockIdx.x) * kResampleFramesPerBlock;
     const int nf = static_cast<int>(min(static_cast<long long>(kResampleFramesPerBlock), n_frames - f0));
-    const double* x = in + static_cast<size_t>(blockIdx.y) * in_stride;
+    const int s_base = blockIdx.y * S;
     const int lo = frames[f0].base - 1;
-    const int span = frames[f0 + nf - 1].base + sinc_len + 2 - lo;
-    for (int i = threadIdx.x; i < span; i += kResampleFramesPerBlock) {
-        const long long s = static_cast<long long>(lo) + i;
-        xs[i] = (s >= 0 && s < n_in) ? x[s] : 0.0;
+    const int span = frames[f0 + nf - 1].base + SL + 2 - lo;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const bool live = s_base + s < n_streams;
+        const double* x = in + static_cast<size_t>(live ? s_base + s : s_base) * in_stride;
+        for (int i = threadIdx.x; i < span; i += kResampleFramesPerBlock) {
+            const long long p = static_cast<long long>(lo) + i;
+            xs[s * span + i] = (live && p >= 0 && p < n_in) ? x[p] : 0.0;
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,7 +216,84 @@ __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const doub
         // interp_cubic (rubato): a0 = y1, a1 = -y0/3 - y1/2 + y2 - y3/6, a2 = (y0 + y2)/2 - y1, a3 = (y1 - y2)/2 + (y3 - y0)/6
         const double w[4] = {-(1.0 / 3.0) * t + 0.5 * t2 - (1.0 / 6.0) * t3, 1.0 - 0.5 * t - t2 + 0.5 * t3, t + 0.5 * t2 - 0.5 * t3,
                              -(1.0 / 6.0) * t + (1.0 / 6.0) * t3};
-        double part = 0.0;
+        double acc[S][4];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc[s][d] = 0.0;
+        const double* xx = xs + (fr.base - lo) + lane;
+        if (fr.sub >= 1 && fr.sub + 2 < kResamplePhases) {  // phases sub - 1 .. sub + 2 are four consecutive rows over one window
+            const double* row = table + static_cast<size_t>(fr.sub - 1) * SL + lane;
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+                double tv[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) tv[d] = __ldg(row + d * SL + 32 * j);
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const double xv = xx[s * span + 32 * j];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) acc[s][d] = fma(xv, tv[d], acc[s][d]);
+                }
+            }
+        } else {  // a phase wraps (3 of 256 positions): the wrapped phases read the window one sample earlier / later
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                int sd = fr.sub + d - 1;
+                const int carry = sd < 0 ? -1 : (sd >= kResamplePhases ? 1 : 0);
+                sd -= carry * kResamplePhases;
+                const double* row = table + static_cast<size_t>(sd) * SL + lane;
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    const double tv = __ldg(row + 32 * j);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) acc[s][d] = fma(xx[s * span + carry + 32 * j], tv, acc[s][d]);
+                }
+            }
+        }
+        double part[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            part[s] = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) part[s] = fma(w[d], acc[s][d], part[s]);
+        }
+        reduce_and_keep<S>(part, lane, k, &mine);
+        if (S == 4 && ((k & 7) == 7 || fi == nf - 1)) {  // eight frames x four streams sit in the warp: 64-byte runs per stream
+            const int frame = (fi & ~7) + (lane >> 2);
+            const int stream = s_base + (((lane & 1) << 1) | ((lane >> 1) & 1));
+            if (frame < nf && stream < n_streams) out[static_cast<size_t>(stream) * out_stride + f0 + frame] = mine;
+        }
+    }
+    if (S == 1 && warp * 32 + lane < nf) out[static_cast<size_t>(s_base) * out_stride + f0 + warp * 32 + lane] = mine;
+}
+
+// any sinc_len (a multiple of 32), one stream per CTA: the fallback of the shapes without an unrolled instance
+__global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample_any(const double* __restrict__ in, size_t in_stride, long long n_in,
+                                                                          double* __restrict__ out, size_t out_stride, long long n_frames,
+                                                                          const ResampleFrame* __restrict__ frames,
+                                                                          const double* __restrict__ table, int sinc_len) {
+    extern __shared__ double xs[];
+    const long long f0 = static_cast<long long>(blockIdx.x) * kResampleFramesPerBlock;
+    const int nf = static_cast<int>(min(static_cast<long long>(kResampleFramesPerBlock), n_frames - f0));
+    const double* x = in + static_cast<size_t>(blockIdx.y) * in_stride;
+    const int lo = frames[f0].base - 1;
+    const int span = frames[f0 + nf - 1].base + sinc_len + 2 - lo;
+    for (int i = threadIdx.x; i < span; i += kResampleFramesPerBlock) {
+        const long long p = static_cast<long long>(lo) + i;
+        xs[i] = (p >= 0 && p < n_in) ? x[p] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double mine = 0.0;
+    for (int k = 0; k < 32; ++k) {
+        const int fi = warp * 32 + k;
+        if (fi >= nf) break;
+        const ResampleFrame fr = frames[f0 + fi];
+        const double t = fr.frac, t2 = t * t, t3 = t2 * t;
+        const double w[4] = {-(1.0 / 3.0) * t + 0.5 * t2 - (1.0 / 6.0) * t3, 1.0 - 0.5 * t - t2 + 0.5 * t3, t + 0.5 * t2 - 0.5 * t3,
+                             -(1.0 / 6.0) * t + (1.0 / 6.0) * t3};
+        double part[1] = {0.0};
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             int sd = fr.sub + d - 1;
@@ -190,32 +303,69 @@ __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const doub
             const double* xx = xs + (fr.base - lo + carry);
             double acc = 0.0;
             for (int p = lane; p < sinc_len; p += 32) acc = fma(xx[p], __ldg(row + p), acc);
-            part = fma(w[d], acc, part);
+            part[0] = fma(w[d], acc, part[0]);
         }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-        if (lane == k) mine = part;
+        reduce_and_keep<1>(part, lane, k, &mine);
     }
-    const long long f = f0 + warp * 32 + lane;
-    if (warp * 32 + lane < nf) out[static_cast<size_t>(blockIdx.y) * out_stride + f] = mine;
+    if (warp * 32 + lane < nf) out[static_cast<size_t>(blockIdx.y) * out_stride + f0 + warp * 32 + lane] = mine;
 }
+
+namespace {
+template <int T, int S>
+cudaError_t launch_instance(const double* d_in, size_t in_stride, size_t n_in, double* d_out, size_t out_stride, size_t n_frames, int first,
+                            int n_streams, const ResampleFrame* d_frames, const double* d_table, int max_span, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(max_span) * S * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        const cudaError_t err = cudaFuncSetAttribute(k_resample<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+    }
+    const unsigned groups = static_cast<unsigned>((n_frames + kResampleFramesPerBlock - 1) / kResampleFramesPerBlock);
+    const int cta_rows = (n_streams + S - 1) / S;
+    for (int r0 = 0; r0 < cta_rows; r0 += 65535) {  // gridDim.y limit
+        const int rows = std::min(65535, cta_rows - r0);
+        const int s0 = first + r0 * S;
+        k_resample<T, S><<<dim3(groups, rows), kResampleFramesPerBlock, smem, stream>>>(
+            d_in + static_cast<size_t>(s0) * in_stride, in_stride, static_cast<long long>(n_in), d_out + static_cast<size_t>(s0) * out_stride,
+            out_stride, static_cast<long long>(n_frames), d_frames, d_table, n_streams - r0 * S);
+    }
+    return cudaGetLastError();
+}
+
+template <int T>
+cudaError_t launch_taps(const double* d_in, size_t in_stride, size_t n_in, double* d_out, size_t out_stride, size_t n_frames, int n_streams,
+                        const ResampleFrame* d_frames, const double* d_table, int max_span, cudaStream_t stream) {
+    // groups of four streams share the phase-table loads; what is left over renders one stream per CTA
+    const int quads = n_streams / 4 * 4;
+    if (quads) {
+        const cudaError_t err = launch_instance<T, 4>(d_in, in_stride, n_in, d_out, out_stride, n_frames, 0, quads, d_frames, d_table, max_span, stream);
+        if (err != cudaSuccess) return err;
+    }
+    if (n_streams > quads)
+        return launch_instance<T, 1>(d_in, in_stride, n_in, d_out, out_stride, n_frames, quads, n_streams - quads, d_frames, d_table, max_span,
+                                     stream);
+    return cudaSuccess;
+}
+}  // namespace
 
 cudaError_t launch_resample(const double* d_in, size_t in_stride, size_t n_in, double* d_out, size_t out_stride, size_t n_frames,
                             int n_streams, const ResampleFrame* d_frames, const double* d_table, int sinc_len, int max_span,
                             cudaStream_t stream) {
     if (n_frames == 0 || n_streams == 0) return cudaSuccess;
+    if (sinc_len == 128) return launch_taps<4>(d_in, in_stride, n_in, d_out, out_stride, n_frames, n_streams, d_frames, d_table, max_span, stream);
+    if (sinc_len == 256) return launch_taps<8>(d_in, in_stride, n_in, d_out, out_stride, n_frames, n_streams, d_frames, d_table, max_span, stream);
     const size_t smem = static_cast<size_t>(max_span) * sizeof(double);
     if (smem > 48 * 1024) {
-        const cudaError_t err = cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        const cudaError_t err = cudaFuncSetAttribute(k_resample_any, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (err != cudaSuccess) return err;
     }
     const unsigned groups = static_cast<unsigned>((n_frames + kResampleFramesPerBlock - 1) / kResampleFramesPerBlock);
     for (int s0 = 0; s0 < n_streams; s0 += 65535) {  // gridDim.y limit
         const int ns = std::min(65535, n_streams - s0);
-        k_resample<<<dim3(groups, ns), kResampleFramesPerBlock, smem, stream>>>(d_in + static_cast<size_t>(s0) * in_stride, in_stride,
-                                                                                static_cast<long long>(n_in),
-                                                                                d_out + static_cast<size_t>(s0) * out_stride, out_stride,
-                                                                                static_cast<long long>(n_frames), d_frames, d_table, sinc_len);
+        k_resample_any<<<dim3(groups, ns), kResampleFramesPerBlock, smem, stream>>>(d_in + static_cast<size_t>(s0) * in_stride, in_stride,
+                                                                                    static_cast<long long>(n_in),
+                                                                                    d_out + static_cast<size_t>(s0) * out_stride, out_stride,
+                                                                                    static_cast<long long>(n_frames), d_frames, d_table, sinc_len);
     }
     return cudaGetLastError();
 }
