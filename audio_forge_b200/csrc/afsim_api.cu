@@ -480,7 +480,9 @@ int build_sweep(AfsimHandle* h, const PassageSource& src, const size_t* passage_
         const int n_chunks = T > 0 ? (T + chunk - 1) / chunk : 0;
         // ring slots = chunks in flight + 1; few-stream batches need the stage wavefront to fill the GPU
         // (a split batch runs up to ~24 stage kernels per chunk: one ring slot per stage keeps all of them busy)
-        int slots = S <= 16384 ? 26 : (S <= 65536 ? 4 : 2);
+        // (fused kernels, 16384 < S <= 32768: eight slots keep ~7 of the ~12 stage kernels of a chunk in flight -- C5 at 32768
+        // streams per GPU 1840 -> 1679 ms; at 65536 streams the GPU is full with three and 8 slots are 90 GB of rings)
+        int slots = S <= 16384 ? 26 : (S <= 32768 ? 8 : (S <= 65536 ? 4 : 2));
         slots = env_int("AFSIM_SLOTS", slots);
         slots = std::max(2, std::min(slots, std::max(2, n_chunks + 1)));
         batch->slots = slots;

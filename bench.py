@@ -331,6 +331,7 @@ def stage_records(shape: Shape, stages, info, clocks_mhz, fp64_peak, fp32_peak, 
                "GBps": STAGE_BYTES.get(name, 8) * samples / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else None}
         row["hbm_frac"] = row["GBps"] / hbm_peak if row["GBps"] else None
         if row["hbm_frac"] and row["hbm_frac"] > 1.2:  # more than the memory system can move: the hand-off stays in L2
+            row["hbm_frac"] = None  # not a fraction of anything: not printed
             row["hbm_note"] = "above the HBM peak: this launch's hand-off rings are L2-resident at this stream count"
         if ncu and name in ncu and launch_ms > 0:
             t = ncu[name]

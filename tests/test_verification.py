@@ -78,3 +78,24 @@ def test_gpu_pair_render_is_bit_identical_to_two_single_calls():
         for key, value in single.items():
             if key != "candidate_runtime_ms":
                 assert sim[key] == value, key
+
+
+@pytest.mark.gpu
+def test_gpu_pair_render_equals_the_oracle():
+    """The GPU's verification renders (speech passage + noise capture, one sweep) against the CPU oracle: audio within
+    1e-5 / -100 dBFS, every metric within 0.01 dB, counts exact -- what voice_setup.py:1537-1660 computes its spectral
+    checks and decision ladder from."""
+    from tests.cases import audio_within_tolerance
+    speech = speech_like(FS * 3 + 77, seed=21, level=0.6)
+    noise = (speech_like(FS * 2, seed=22, level=0.02)).astype(np.float32)
+    processed, rendered, processed_noise, rendered_noise = verification.render_verification_pair(noise, speech, FS, SETUP)
+    want = verification.render_verification_pair(noise, speech, FS, SETUP, simulate_batch=_oracle_batch)
+    for (sim, audio), (o_sim, o_audio) in (((processed, rendered), want[0:2]), ((processed_noise, rendered_noise), want[2:4])):
+        assert audio_within_tolerance(o_audio, audio) <= 0.0
+        for key, value in o_sim.items():
+            if key in ("candidate_runtime_ms", "simulation_backend", "safety_authority"):
+                continue
+            if isinstance(value, float):
+                assert abs(sim[key] - value) <= 0.01 or (np.isinf(value) and sim[key] == value), key
+            else:
+                assert sim[key] == value, key
