@@ -201,18 +201,40 @@ int afsim_multi_partition(const AfCandidate* candidates, size_t n_candidates, co
         if (p >= n_passages || c >= n_candidates) return AFSIM_INVALID_ARGUMENT;
         cost[i] = (40.0 + sections[c]) * static_cast<double>(passage_len[p]);
     }
-    std::vector<uint32_t> order(n_pairs);
-    for (size_t i = 0; i < n_pairs; ++i) order[i] = static_cast<uint32_t>(i);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    // Units of the split: the streams of one candidate, in caller order, in pieces of at most ceil(n / (16 parts)) -- a rank
+    // that holds all passages of its candidates reads 1 / parts of the candidate constants (sharding.shard_units).
+    const size_t cap = std::max<size_t>(1, (n_pairs + 16 * static_cast<size_t>(n_parts) - 1) / (16 * static_cast<size_t>(n_parts)));
+    std::vector<uint32_t> unit_of(n_pairs);
+    std::vector<int64_t> open_unit(n_candidates, -1);
+    std::vector<double> unit_cost;
+    std::vector<size_t> unit_size;
+    for (size_t i = 0; i < n_pairs; ++i) {
+        const size_t c = pair_candidate ? pair_candidate[i] : i / n_passages;
+        int64_t u = open_unit[c];
+        if (u < 0 || unit_size[u] >= cap) {
+            u = static_cast<int64_t>(unit_cost.size());
+            open_unit[c] = u;
+            unit_cost.push_back(0.0);
+            unit_size.push_back(0);
+        }
+        unit_of[i] = static_cast<uint32_t>(u);
+        unit_cost[u] += cost[i];
+        unit_size[u] += 1;
+    }
+    std::vector<uint32_t> order(unit_cost.size());
+    for (size_t u = 0; u < order.size(); ++u) order[u] = static_cast<uint32_t>(u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return unit_cost[a] > unit_cost[b]; });
     typedef std::tuple<double, size_t, int> Load;  // (load, streams, part): least loaded, then fewest streams, then lowest index
     std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
     for (int r = 0; r < n_parts; ++r) heap.emplace(0.0, size_t(0), r);
-    for (uint32_t i : order) {
+    std::vector<uint32_t> unit_owner(unit_cost.size());
+    for (uint32_t u : order) {
         Load top = heap.top();
         heap.pop();
-        out_owner[i] = static_cast<uint32_t>(std::get<2>(top));
-        heap.emplace(std::get<0>(top) + cost[i], std::get<1>(top) + 1, std::get<2>(top));
+        unit_owner[u] = static_cast<uint32_t>(std::get<2>(top));
+        heap.emplace(std::get<0>(top) + unit_cost[u], std::get<1>(top) + unit_size[u], std::get<2>(top));
     }
+    for (size_t i = 0; i < n_pairs; ++i) out_owner[i] = unit_owner[unit_of[i]];
     return AFSIM_OK;
 }
 

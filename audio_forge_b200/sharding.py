@@ -31,6 +31,45 @@ def shard_streams(costs: Sequence[float], world_size: int) -> list[np.ndarray]:
     return [np.sort(np.nonzero(owner == r)[0]) for r in range(world_size)]
 
 
+def shard_units(costs: Sequence[float], group_key: Sequence[int], world_size: int) -> list[np.ndarray]:
+    """The partition rule of a sweep: streams that share a candidate stay on one rank.
+
+    A rank that holds ONE passage of every candidate reads every candidate's constants (2.7 KB each, per stage kernel and
+    chunk) for a single stream; a rank that holds ALL passages of an eighth of the candidates reads an eighth of them,
+    each shared by its passages' streams (north-star shape on 8 GPUs: 601 against 662 ms per sweep).  So the units of the
+    longest-processing-time split are the streams of one candidate, in caller order, cut into pieces of at most
+    ceil(n / (16 world)) streams so that a sweep of few candidates over many passages still spreads over all ranks."""
+    import heapq
+
+    costs = np.asarray(costs, dtype=np.float64)
+    keys = np.asarray(group_key, dtype=np.int64)
+    cap = max(1, -(-costs.size // (16 * world_size)))
+    unit_of = np.empty(costs.size, dtype=np.int64)
+    open_unit: dict[int, int] = {}
+    unit_cost: list[float] = []
+    unit_size: list[int] = []
+    for i, k in enumerate(keys.tolist()):
+        u = open_unit.get(k, -1)
+        if u < 0 or unit_size[u] >= cap:
+            u = len(unit_cost)
+            open_unit[k] = u
+            unit_cost.append(0.0)
+            unit_size.append(0)
+        unit_of[i] = u
+        unit_cost[u] += float(costs[i])
+        unit_size[u] += 1
+    ucost = np.asarray(unit_cost, dtype=np.float64)
+    order = np.argsort(-ucost, kind="stable")
+    heap = [(0.0, 0, r) for r in range(world_size)]  # (load, streams, rank): least loaded, then fewest streams
+    unit_owner = np.empty(ucost.size, dtype=np.int64)
+    for u in order.tolist():
+        load, count, r = heapq.heappop(heap)
+        unit_owner[u] = r
+        heapq.heappush(heap, (load + float(ucost[u]), count + unit_size[u], r))
+    owner = unit_owner[unit_of] if costs.size else np.empty(0, dtype=np.int64)
+    return [np.sort(np.nonzero(owner == r)[0]) for r in range(world_size)]
+
+
 def stream_costs(candidates, pair_candidate: Sequence[int], pair_len: Sequence[int]) -> np.ndarray:
     """Relative render cost of each stream: (fixed chain cost + EQ sections) x samples."""
     sections = []
@@ -143,10 +182,11 @@ class DeviceGather:
 
 
 def plan_shards(candidates, pair_passage, pair_candidate, passage_lens, world: int) -> list[np.ndarray]:
-    """The partition every rank computes identically: streams balanced by (fixed chain cost + EQ sections) x samples."""
+    """The partition every rank computes identically: the streams of a candidate stay together (`shard_units`), ranks
+    balanced by (fixed chain cost + EQ sections) x samples."""
     pair_passage = np.asarray(pair_passage, dtype=np.int64)
     costs = stream_costs(candidates, pair_candidate, np.asarray(passage_lens, dtype=np.float64)[pair_passage])
-    return shard_streams(costs, world)
+    return shard_units(costs, pair_candidate, world)
 
 
 def sharded_chain_sweep(render, passages, sample_rate: float, candidates, pair_passage, pair_candidate, group=None):

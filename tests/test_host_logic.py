@@ -167,6 +167,36 @@ def test_c_abi_partitioner_equals_the_python_one():
             assert np.array_equal(np.nonzero(owner == r)[0], shards[r])
 
 
+def test_partition_keeps_a_candidate_s_passages_together_and_still_spreads_few_candidates():
+    from audio_forge_b200 import native, workloads
+    cands = workloads.full_chain_candidates(256, seed=3)
+    n_pass = 8
+    pc = np.repeat(np.arange(256), n_pass).astype(np.uint32)
+    pp = np.tile(np.arange(n_pass), 256).astype(np.uint32)
+    lens = [48000] * n_pass
+    shards = sharding.plan_shards(cands, pp, pc, lens, 8)
+    assert np.array_equal(np.sort(np.concatenate(shards)), np.arange(256 * n_pass))
+    sizes = [s.size for s in shards]
+    assert max(sizes) - min(sizes) <= 2 * n_pass
+    for s in shards:  # whole candidates: every candidate of a rank comes with all its passages
+        held, counts = np.unique(pc[s], return_counts=True)
+        assert np.all(counts == n_pass) and held.size * n_pass == s.size
+    costs = sharding.stream_costs(cands, pc, np.asarray(lens, dtype=np.float64)[pp])
+    loads = np.array([costs[s].sum() for s in shards])
+    assert loads.max() / loads.min() < 1.02
+    owner = native.partition(cands, lens, pp, pc, 8)
+    for r in range(8):
+        assert np.array_equal(np.nonzero(owner == r)[0], shards[r])
+    # one candidate over many passages (BASELINE config 4): pieces of ceil(n / (16 world)) streams reach every rank
+    one = workloads.full_chain_candidates(1, seed=0)
+    pp1 = np.arange(1000).astype(np.uint32)
+    shards1 = sharding.plan_shards(one, pp1, np.zeros(1000, dtype=np.uint32), [48000] * 1000, 8)
+    assert all(120 <= s.size <= 130 for s in shards1)
+    owner1 = native.partition(one, [48000] * 1000, pp1, np.zeros(1000, dtype=np.uint32), 8)
+    for r in range(8):
+        assert np.array_equal(np.nonzero(owner1 == r)[0], shards1[r])
+
+
 def test_shard_streams_is_balanced_and_complete():
     rng = np.random.default_rng(0)
     costs = rng.choice([50.0, 56.0, 80.0], size=1000) * 480000
