@@ -1857,6 +1857,10 @@ int afsim_product_resampler(AfsimHandle* h, const AfResamplerSpec* spec, const d
     const size_t in_stride = (n_in + 31) / 32 * 32 + 32, out_stride = (frames + 31) / 32 * 32;
     DeviceBuffers mem;
     mem.pool = &h->pool;
+    struct Quiesce {  // whatever way this call ends, nothing is in flight when `mem` hands its buffers back to the pool
+        cudaStream_t st;
+        ~Quiesce() { cudaStreamSynchronize(st); }
+    } quiesce{h->stream};
     // streams go through the device in groups that fit a bounded staging area (a 60 s signal is 21 + 23 MB)
     const size_t per_stream = (in_stride + out_stride) * sizeof(double);
     const size_t group = std::max<size_t>(1, std::min(n_streams, (size_t(4) << 30) / std::max<size_t>(per_stream, 1)));

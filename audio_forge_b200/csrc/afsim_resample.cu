@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace afsim {
 
@@ -184,6 +185,44 @@ __device__ __forceinline__ void reduce_and_keep<4>(double (&v)[4], int lane, int
     if ((lane >> 2) == (k & 7)) *mine = t;
 }
 
+template <>
+__device__ __forceinline__ void reduce_and_keep<8>(double (&v)[8], int lane, int k, double* mine) {
+    // distances 1, 2, 4 halve the eight streams' values over the lanes (bit 0 picks streams 4..7, bit 1 the upper pair of
+    // the four left, bit 2 the upper one of the two left), distances 8 and 16 finish the sum: the tree of reduce_and_keep<1>
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4;
+    double a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (b0 ? v[4 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, b0 ? v[i] : v[4 + i], 1);
+    double b[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) b[i] = (b1 ? a[2 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, b1 ? a[i] : a[2 + i], 2);
+    double t = (b2 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, b2 ? b[0] : b[1], 4);
+#pragma unroll
+    for (int m = 8; m < 32; m <<= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+    // lane l holds the frame's total of stream 4 (l & 1) + 2 ((l >> 1) & 1) + ((l >> 2) & 1); lanes 8 j .. 8 j + 7 keep frame j of 4
+    if ((lane >> 3) == (k & 3)) *mine = t;
+}
+
+// The phase table is mirror symmetric -- row r, tap p equals row 254 - r, tap sinc_len - 1 - p to one ulp (row 255 mirrors into
+// itself) -- so the kernel reads rows 128 .. 254 as the reversed rows 126 .. 0: the rows it touches (128 KB at 128 taps) stay
+// in L1 next to the streamed input, where the whole table (256 KB) did not (L1 hit rate 65 %).
+template <int T, int S, int DIR>
+__device__ __forceinline__ void accumulate_rows(const double* __restrict__ r0, const double* __restrict__ xx, int span, double (&acc)[S][4]) {
+    constexpr int SL = 32 * T;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+        double tv[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) tv[d] = __ldg(r0 + DIR * (d * SL + 32 * j));
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double xv = xx[s * span + 32 * j];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) acc[s][d] = fma(xv, tv[d], acc[s][d]);
+        }
+    }
+}
+
 template <int T, int S>
 __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const double* __restrict__ in, size_t in_stride, long long n_in,
                                                                       double* __restrict__ out, size_t out_stride, long long n_frames,
@@ -222,30 +261,22 @@ __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const doub
 #pragma unroll
             for (int d = 0; d < 4; ++d) acc[s][d] = 0.0;
         const double* xx = xs + (fr.base - lo) + lane;
-        if (fr.sub >= 1 && fr.sub + 2 < kResamplePhases) {  // phases sub - 1 .. sub + 2 are four consecutive rows over one window
-            const double* row = table + static_cast<size_t>(fr.sub - 1) * SL + lane;
-#pragma unroll
-            for (int j = 0; j < T; ++j) {
-                double tv[4];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) tv[d] = __ldg(row + d * SL + 32 * j);
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const double xv = xx[s * span + 32 * j];
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) acc[s][d] = fma(xv, tv[d], acc[s][d]);
-                }
-            }
-        } else {  // a phase wraps (3 of 256 positions): the wrapped phases read the window one sample earlier / later
+        if (fr.sub >= 1 && fr.sub + 2 <= 127) {  // phases sub - 1 .. sub + 2: four consecutive rows over one input window
+            accumulate_rows<T, S, 1>(table + static_cast<size_t>(fr.sub - 1) * SL + lane, xx, span, acc);
+        } else if (fr.sub - 1 >= 128 && fr.sub + 2 <= 254) {  // the same through the mirror: rows 254 - r, taps reversed
+            accumulate_rows<T, S, -1>(table + static_cast<size_t>(254 - (fr.sub - 1)) * SL + (SL - 1 - lane), xx, span, acc);
+        } else {  // a phase wraps into the neighbouring sample (3 of 256 positions) or the four rows straddle the mirror
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 int sd = fr.sub + d - 1;
                 const int carry = sd < 0 ? -1 : (sd >= kResamplePhases ? 1 : 0);
                 sd -= carry * kResamplePhases;
-                const double* row = table + static_cast<size_t>(sd) * SL + lane;
+                const bool mirrored = sd >= 128 && sd <= 254;
+                const double* row = table + static_cast<size_t>(mirrored ? 254 - sd : sd) * SL + (mirrored ? SL - 1 - lane : lane);
+                const int step = mirrored ? -32 : 32;
 #pragma unroll
                 for (int j = 0; j < T; ++j) {
-                    const double tv = __ldg(row + 32 * j);
+                    const double tv = __ldg(row + step * j);
 #pragma unroll
                     for (int s = 0; s < S; ++s) acc[s][d] = fma(xx[s * span + carry + 32 * j], tv, acc[s][d]);
                 }
@@ -259,6 +290,11 @@ __global__ void __launch_bounds__(kResampleFramesPerBlock) k_resample(const doub
             for (int d = 0; d < 4; ++d) part[s] = fma(w[d], acc[s][d], part[s]);
         }
         reduce_and_keep<S>(part, lane, k, &mine);
+        if (S == 8 && ((k & 3) == 3 || fi == nf - 1)) {  // four frames x eight streams sit in the warp
+            const int frame = (fi & ~3) + (lane >> 3);
+            const int stream = s_base + (((lane & 1) << 2) | (lane & 2) | ((lane >> 2) & 1));
+            if (frame < nf && stream < n_streams) out[static_cast<size_t>(stream) * out_stride + f0 + frame] = mine;
+        }
         if (S == 4 && ((k & 7) == 7 || fi == nf - 1)) {  // eight frames x four streams sit in the warp: 64-byte runs per stream
             const int frame = (fi & ~7) + (lane >> 2);
             const int stream = s_base + (((lane & 1) << 1) | ((lane >> 1) & 1));
@@ -335,14 +371,25 @@ cudaError_t launch_instance(const double* d_in, size_t in_stride, size_t n_in, d
 template <int T>
 cudaError_t launch_taps(const double* d_in, size_t in_stride, size_t n_in, double* d_out, size_t out_stride, size_t n_frames, int n_streams,
                         const ResampleFrame* d_frames, const double* d_table, int max_span, cudaStream_t stream) {
-    // groups of four streams share the phase-table loads; what is left over renders one stream per CTA
-    const int quads = n_streams / 4 * 4;
-    if (quads) {
-        const cudaError_t err = launch_instance<T, 4>(d_in, in_stride, n_in, d_out, out_stride, n_frames, 0, quads, d_frames, d_table, max_span, stream);
+    // groups of eight, then four streams share the phase-table loads; what is left over renders one stream per CTA
+    // (AFSIM_RESAMPLE_GROUP = 4 / 1 caps the group size: measurement knob, read per call)
+    const char* env = std::getenv("AFSIM_RESAMPLE_GROUP");
+    const int max_group = env ? std::atoi(env) : 8;
+    int done = 0;
+    if (max_group >= 8 && n_streams - done >= 8) {
+        const int n = (n_streams - done) / 8 * 8;
+        const cudaError_t err = launch_instance<T, 8>(d_in, in_stride, n_in, d_out, out_stride, n_frames, done, n, d_frames, d_table, max_span, stream);
         if (err != cudaSuccess) return err;
+        done += n;
     }
-    if (n_streams > quads)
-        return launch_instance<T, 1>(d_in, in_stride, n_in, d_out, out_stride, n_frames, quads, n_streams - quads, d_frames, d_table, max_span,
+    if (max_group >= 4 && n_streams - done >= 4) {
+        const int n = (n_streams - done) / 4 * 4;
+        const cudaError_t err = launch_instance<T, 4>(d_in, in_stride, n_in, d_out, out_stride, n_frames, done, n, d_frames, d_table, max_span, stream);
+        if (err != cudaSuccess) return err;
+        done += n;
+    }
+    if (n_streams > done)
+        return launch_instance<T, 1>(d_in, in_stride, n_in, d_out, out_stride, n_frames, done, n_streams - done, d_frames, d_table, max_span,
                                      stream);
     return cudaSuccess;
 }

@@ -63,12 +63,23 @@ def test_empty_input_flushes_to_the_delay():
 
 
 def test_batch_equals_single_calls_bit_for_bit():
-    signals = np.stack([_signal("noise", 12000, seed=s) for s in range(5)] + [_signal("tones", 12000)])
+    # 13 signals: one group of eight, one of four and a single one -- the three instances of the kernel
+    signals = np.stack([_signal("noise", 12000, seed=s) for s in range(12)] + [_signal("tones", 12000)])
     out, delay, expected = mic_eq_core.simulate_product_resampler_batch(signals, 48000, 44100)
-    assert out.shape[0] == 6 and delay == 58 and expected == 11025
+    assert out.shape[0] == 13 and delay == 58 and expected == 11025
     for s in range(signals.shape[0]):
         single, _, _, _ = mic_eq_core.simulate_product_resampler(signals[s], 48000, 44100)
         assert np.array_equal(out[s], np.asarray(single))
+
+
+def test_batch_of_the_long_filter_equals_single_calls_and_the_oracle():
+    signals = np.stack([_signal("noise", 9000, seed=40 + s) for s in range(9)])
+    out, _, _ = mic_eq_core.simulate_product_resampler_batch(signals, 44100, 48000, 1024, 256, "blackman_harris_squared")
+    for s in (0, 7, 8):
+        single, _, _, _ = mic_eq_core.simulate_product_resampler(signals[s], 44100, 48000, 1024, 256, "blackman_harris_squared")
+        assert np.array_equal(out[s], np.asarray(single))
+    want, _, _, _ = R.simulate_product_resampler(signals[3], 44100, 48000, 1024, 256, "blackman_harris_squared")
+    assert np.max(np.abs(out[3] - want)) <= TOL
 
 
 def test_linearity_and_silence():
