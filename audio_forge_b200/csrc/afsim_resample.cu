@@ -100,7 +100,7 @@ int plan_resampler(const AfResamplerSpec& spec, size_t n_in, bool with_frames, b
     plan->n_in = n_in;
     plan->cutoff = static_cast<double>(cutoff32);
     const double expected_f = std::round(static_cast<double>(n_in) * static_cast<double>(spec.output_rate) / static_cast<double>(spec.input_rate));
-    if (expected_f > 2.0e9) return *msg = "signal too long", AFSIM_INVALID_ARGUMENT;
+    if (expected_f > 2.0e9 || n_in > 0x7ff00000ull) return *msg = "signal too long", AFSIM_INVALID_ARGUMENT;  // frame windows are int32
     plan->shape.expected_frames = static_cast<uint64_t>(expected_f);
     plan->shape.delay = static_cast<uint32_t>(static_cast<double>(sl / 2) * ratio);
     // the block loop of SincFixedIn::process_into_buffer, frames only
