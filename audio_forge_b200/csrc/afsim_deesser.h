@@ -552,10 +552,10 @@ struct DeEsserReduction {  // R_c1c
                         red[b] = smooth_ar(red[b], target[b], attack, release);
                         total_red += red[b];
                         const double dyn_gain = -red[b];
-                        gain_out[b][o] = dyn_gain;
                         if (fabs(built_gain[b] - dyn_gain) > 0.001) {  // set_gain_db_immediate rebuilds the filter
                             built_gain[b] = dyn_gain;
                             mask |= 1u << b;
+                            gain_out[b][o] = dyn_gain;  // M_c2 reads the gain of flagged (sample, band) pairs only
                         }
                     }
                     current = fmin(total_red, max_red);
@@ -578,20 +578,17 @@ AF_HD int de_coef_ring(int band, int i) { return band == 0 ? (i < 3 ? 1 + i : 7)
 constexpr int kDeRebuildGroup = 2;
 AF_HD void deesser_rebuild(double* const (&w)[13], size_t stride, int valid, const DeConst& k) {
     constexpr int G = kDeRebuildGroup;
-    double mask[G], g0[G], g1[G], g2[G];
+    double mask[G];
     load_tile((const double*)w[0], stride, valid, mask);
-    load_tile((const double*)w[4], stride, valid, g0);
-    load_tile((const double*)w[5], stride, valid, g1);
-    load_tile((const double*)w[6], stride, valid, g2);
 #pragma unroll
     for (int u = 0; u < G; ++u) {
         if (u >= valid) continue;
         const unsigned m = (unsigned)mask[u];
-        const double gains[3] = {g0[u], g1[u], g2[u]};
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            if (m & (1u << b)) {
-                const Bq c = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), gains[b]);
+            if (m & (1u << b)) {  // the gain rings hold a value for the flagged pairs only (R_c1c), and only those are fetched
+                const double gain = w[4 + b][(size_t)u * stride];
+                const Bq c = design_peaking(k(DE_DYN_COS + b), k(DE_DYN_ALPHA + b), gain);
                 w[de_coef_ring(b, 0)][(size_t)u * stride] = c.b0;
                 w[de_coef_ring(b, 1)][(size_t)u * stride] = c.b1;
                 w[de_coef_ring(b, 2)][(size_t)u * stride] = c.b2;
@@ -603,6 +600,7 @@ AF_HD void deesser_rebuild(double* const (&w)[13], size_t stride, int valid, con
 
 // ---- R_c3: the time-varying dynamic EQ ------------------------------------------------------------------------------------
 constexpr int kDeRc3Depth = 3;
+constexpr int kDeRc3Look = kDeRc3Depth;  // tiles the rebuild masks are staged ahead of the coefficients they gate
 struct DeEsserFilter {
     Bq dyn[3];        // live dynamic-EQ coefficients
     double yz[3][2];  // dynamic-EQ state
@@ -676,20 +674,43 @@ struct DeEsserFilter {
 #pragma unroll
         for (int i = 0; i < 13; ++i) ws[i] = w[i] + (size_t)t_head * stride;
         const int m = len - t_head;
+        // Only the flagged (sample, band) pairs carry coefficients (M_c2 wrote nothing else), so only those are fetched: the
+        // rebuild masks are staged kDeRc3Look tiles AHEAD of the coefficients they gate (their copies ride in the commit group
+        // of tile kt - Look, which has landed when tile kt is issued: pipelined_tiles_depth waits for group k - 1 before it
+        // issues tile k + Depth - 1, and Look = Depth); the first Look tiles of a chunk read their masks through.  Fetching all
+        // 13 rings for every sample made this serial kernel HBM bound (1.28 GB per launch at 5.9 TB/s for 8192 streams).
+        constexpr int kLook = kDeRc3Look;
         const StageRing<float, kDeRc3Depth> sx = stg.ring<float, kDeRc3Depth>();
-        StageRing<double, kDeRc3Depth> sw[13];
+        const StageRing<double, kDeRc3Depth + kLook> smask = stg.ring<double, kDeRc3Depth + kLook>();
+        StageRing<double, kDeRc3Depth> sw[13];  // sw[0] unused: the mask has its own, deeper ring
 #pragma unroll
-        for (int i = 0; i < 13; ++i) sw[i] = stg.ring<double, kDeRc3Depth>();
+        for (int i = 1; i < 13; ++i) sw[i] = stg.ring<double, kDeRc3Depth>();
+        sw[0] = sw[1];
         auto issue = [&](int kt, auto full) {
             constexpr bool FULL = decltype(full)::value;
+            if (!sx.on) return;  // direct mode: nothing is staged
             const int t0 = kt * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (FULL || t0 + u < m) {
                     const size_t o = (size_t)(t0 + u) * stride;
                     sx.fetch(kt, u, xis + (size_t)(t0 + u) * xin_stride);
+                    unsigned mask;
+                    if (kt < kLook) {
+                        mask = (unsigned)ws[0][o];
+                        smask.fetch(kt, u, ws[0] + o);
+                    } else {
+                        mask = (unsigned)*smask.at(kt, u);
+                    }
 #pragma unroll
-                    for (int i = 0; i < 13; ++i) sw[i].fetch(kt, u, ws[i] + o);
+                    for (int b = 0; b < 3; ++b) {
+                        if (mask & (1u << b)) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) sw[de_coef_ring(b, i)].fetch(kt, u, ws[de_coef_ring(b, i)] + o);
+                        }
+                    }
+                    const int ta = t0 + kLook * U + u;
+                    if (ta < m) smask.fetch(kt + kLook, u, ws[0] + (size_t)ta * stride);
                 }
             }
         };
@@ -703,7 +724,7 @@ struct DeEsserFilter {
                 y[u] = 0.0f;
                 if (FULL || u < valid) {
                     const size_t o = (size_t)(t0 + u) * stride;
-                    const unsigned mask = (unsigned)sw[0].get(kt, u, ws[0] + o);
+                    const unsigned mask = (unsigned)smask.get(kt, u, ws[0] + o);
                     float processed = sx.get(kt, u, xis + (size_t)(t0 + u) * xin_stride);
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
@@ -724,6 +745,6 @@ struct DeEsserFilter {
         pipelined_tiles_depth<kDeRc3Depth>(m, issue, body);
     }
 };
-constexpr size_t kDeRc3StagingBytesPerLane = (size_t)kDeRc3Depth * 8 * (4 + 13 * 8);
+constexpr size_t kDeRc3StagingBytesPerLane = (size_t)kDeRc3Depth * 8 * (4 + 12 * 8) + (size_t)(kDeRc3Depth + kDeRc3Look) * 8 * 8;
 
 }  // namespace afsim
