@@ -346,9 +346,9 @@ struct DeEsserTargets {  // R_c1
                     double gains[3];
                     const unsigned mask = sample(voice_db, lv, ct, k, conf_lo, conf_div, gains);
                     w[0][o] = (double)mask;
-                    w[4][o] = gains[0];
-                    w[5][o] = gains[1];
-                    w[6][o] = gains[2];
+                    if (mask & 1u) w[4][o] = gains[0];  // M_c2 reads the gain of flagged (sample, band) pairs only
+                    if (mask & 2u) w[5][o] = gains[1];
+                    if (mask & 4u) w[6][o] = gains[2];
                     if (clk.at_end(n0 + t0 + u)) {  // block-end meter sample (block_processor.rs:129-133)
                         rows_de[(size_t)clk.blk * stride] = (float)current;
                         clk.advance();
