@@ -57,3 +57,19 @@ def test_batched_study_fails_the_legacy_configuration_on_the_published_gates():
     rows = GOLDEN["legacy-blackman-harris-squared-128"]
     assert abs(got["measurements"]["passband_and_offline_reference"][0]["max_absolute_error_db"]
                - rows["/measurements/passband_and_offline_reference[0]/max_absolute_error_db"]["published"]) < 1e-11
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_batched_study_on_the_gpu_reproduces_the_published_product_configuration():
+    got = resampler_eval.evaluate_configuration("product", 128, "blackman", native_default=True, duration_seconds=60)
+    assert got["native_calls"] == 11 and got["status"] == "passed"
+    rows = GOLDEN["product"]
+    for key, value in _leaves({"checks": got["checks"], "measurements": got["measurements"]}):
+        published = rows[key]["published"]
+        if isinstance(published, float) and not isinstance(published, bool):
+            assert abs(value - published) <= (1e-6 if published < -120.0 else 1e-9), (key, value, published)
+        else:
+            assert value == published, (key, value, published)
